@@ -1,0 +1,58 @@
+// FASTQ(.gz) reader reproducing ReadLoader::load_reads
+// (src/abismal.cpp:150-213) for batches of any size.
+#ifndef ABISMAL_B200_READ_LOADER_HPP
+#define ABISMAL_B200_READ_LOADER_HPP
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ab2 {
+
+// Reads of one batch in flat arrays: read i is seq[seq_off[i] .. seq_off[i+1]),
+// its name is names[name_off[i] .. name_off[i+1]).
+struct ReadBatch {
+  std::vector<char> seq;
+  std::vector<uint32_t> seq_off{0};
+  std::vector<char> names;
+  std::vector<uint32_t> name_off{0};
+
+  uint32_t size() const { return static_cast<uint32_t>(seq_off.size() - 1); }
+  uint32_t read_len(uint32_t i) const { return seq_off[i + 1] - seq_off[i]; }
+  uint32_t max_read_len() const;
+  void clear();
+};
+
+class FastqReader {
+public:
+  static constexpr uint32_t min_read_length = 25 + 20 - 1;  // abismal.cpp:212-213
+  static constexpr size_t padding_size = 32767;              // seed::padding_size
+
+  explicit FastqReader(const std::string &filename);
+  ~FastqReader();
+  FastqReader(const FastqReader &) = delete;
+  FastqReader &operator=(const FastqReader &) = delete;
+
+  bool is_open() const { return file_ != nullptr; }
+  // true until a read attempt has hit end of file (ReadLoader::operator bool)
+  bool good() const { return !eof_; }
+  // Appends up to max_reads reads to `out` (cleared first).  Throws
+  // std::runtime_error on an empty name line or an over-long read.
+  void load_reads(ReadBatch &out, size_t max_reads);
+  uint64_t current_read() const { return cur_line_ / 4; }
+
+private:
+  bool getline(const char *&line, size_t &len);  // bgzf_getline semantics
+  bool fill();
+
+  std::string filename_;
+  void *file_ = nullptr;  // gzFile
+  std::vector<char> buf_;
+  size_t beg_ = 0, end_ = 0;
+  std::string carry_;
+  bool eof_ = false, src_eof_ = false;
+  uint64_t cur_line_ = 0;
+};
+
+}  // namespace ab2
+#endif
