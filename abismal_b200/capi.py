@@ -1,0 +1,283 @@
+"""ctypes binding of include/abismal_b200.h (and, for tests, of the oracle's
+identical data contract in oracle/abismal_oracle.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+MODE_PAIRED = 1
+MODE_A_RICH = 2
+MODE_RANDOM_PBAT = 4
+
+FLAG_RC = 0x10
+FLAG_AMBIG = 0x100
+FLAG_A_RICH = 0x1000
+
+HIT_DTYPE = np.dtype([("diffs", "<i2"), ("flags", "<u2"), ("pos", "<u4")])
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class AbgError(RuntimeError):
+    pass
+
+
+class abg_index_view(C.Structure):
+    _fields_ = [
+        ("genome", C.c_void_p), ("genome_words", C.c_uint64), ("genome_size", C.c_uint64),
+        ("counter", C.c_void_p), ("counter_size", C.c_uint64),
+        ("counter_t", C.c_void_p), ("counter_a", C.c_void_p), ("counter_size_three", C.c_uint64),
+        ("index", C.c_void_p), ("index_size", C.c_uint64),
+        ("index_t", C.c_void_p), ("index_a", C.c_void_p), ("index_size_three", C.c_uint64),
+        ("max_candidates", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class abg_params(C.Structure):
+    _fields_ = [
+        ("mode", C.c_uint32), ("allow_ambig", C.c_uint32), ("min_dist", C.c_uint32), ("max_dist", C.c_uint32),
+        ("valid_frac", C.c_double), ("max_candidates", C.c_uint32), ("cigar_stride", C.c_uint32),
+    ]
+
+
+class abg_batch(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32), ("reserved", C.c_uint32),
+        ("seq1", C.c_void_p), ("off1", C.c_void_p), ("seq2", C.c_void_p), ("off2", C.c_void_p),
+    ]
+
+
+class abg_results(C.Structure):
+    _fields_ = [
+        ("pe_r1", C.c_void_p), ("pe_r2", C.c_void_p), ("se1", C.c_void_p), ("se2", C.c_void_p),
+        ("cigar1", C.c_void_p), ("cigar2", C.c_void_p), ("n_cigar1", C.c_void_p), ("n_cigar2", C.c_void_p),
+    ]
+
+
+class abg_work_counters(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_lookup", "n_entry", "n_cmp", "n_word", "n_align", "n_dpref")]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+def lib_path():
+    return os.path.join(_HERE, "libabismal_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libabismal_b200.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise AbgError("%s not found: build it with `make -C abismal_b200/csrc` "
+                       "(or __graft_entry__.build()); there is no CPU fallback" % p)
+    lib = C.CDLL(p)
+    lib.abg_last_error.restype = C.c_char_p
+    lib.abg_device_count.restype = C.c_int
+    lib.abg_index_create.argtypes = [C.POINTER(abg_index_view), C.c_int, C.POINTER(C.c_void_p)]
+    lib.abg_index_destroy.argtypes = [C.c_void_p]
+    lib.abg_index_destroy.restype = None
+    lib.abg_index_device_bytes.argtypes = [C.c_void_p]
+    lib.abg_index_device_bytes.restype = C.c_uint64
+    lib.abg_mapper_create.argtypes = [C.c_void_p, C.POINTER(abg_params), C.c_uint32, C.c_uint32, C.c_int,
+                                      C.POINTER(C.c_void_p)]
+    lib.abg_mapper_destroy.argtypes = [C.c_void_p]
+    lib.abg_mapper_destroy.restype = None
+    lib.abg_map_batch.argtypes = [C.c_void_p, C.POINTER(abg_batch), C.POINTER(abg_results)]
+    lib.abg_mapper_upload.argtypes = [C.c_void_p, C.POINTER(abg_batch)]
+    lib.abg_mapper_run.argtypes = [C.c_void_p]
+    lib.abg_mapper_sync.argtypes = [C.c_void_p]
+    lib.abg_mapper_download.argtypes = [C.c_void_p, C.POINTER(abg_results)]
+    lib.abg_mapper_last_kernel_ms.argtypes = [C.c_void_p]
+    lib.abg_mapper_last_kernel_ms.restype = C.c_float
+    lib.abg_mapper_launches_per_run.argtypes = [C.c_void_p]
+    lib.abg_mapper_launches_per_run.restype = C.c_uint32
+    lib.abg_mapper_get_counters.argtypes = [C.c_void_p, C.POINTER(abg_work_counters)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_view(ix):
+    """abg_index_view over the numpy arrays of an index_file.IndexFile."""
+    v = abg_index_view()
+    v.genome = _ptr(ix.genome)
+    v.genome_words = ix.genome.size
+    v.genome_size = ix.genome_size
+    v.counter = _ptr(ix.counter)
+    v.counter_size = ix.counter_size
+    v.counter_t = _ptr(ix.counter_t)
+    v.counter_a = _ptr(ix.counter_a)
+    v.counter_size_three = ix.counter_size_three
+    v.index = _ptr(ix.index)
+    v.index_size = ix.index_size
+    v.index_t = _ptr(ix.index_t)
+    v.index_a = _ptr(ix.index_a)
+    v.index_size_three = ix.index_size_three
+    v.max_candidates = ix.max_candidates
+    return v
+
+
+def make_params(mode=0, allow_ambig=False, min_dist=32, max_dist=3000, valid_frac=0.1, max_candidates=0,
+                cigar_stride=64):
+    p = abg_params()
+    p.mode = mode
+    p.allow_ambig = 1 if allow_ambig else 0
+    p.min_dist = min_dist
+    p.max_dist = max_dist
+    p.valid_frac = valid_frac
+    p.max_candidates = max_candidates
+    p.cigar_stride = cigar_stride
+    return p
+
+
+class Results:
+    """Host result arrays for one batch (numpy, caller owned)."""
+
+    def __init__(self, n, paired, stride):
+        self.n, self.paired, self.stride = n, paired, stride
+        self.se1 = np.zeros(n, HIT_DTYPE)
+        self.cigar1 = np.zeros((n, stride), np.uint32)
+        self.n_cigar1 = np.zeros(n, np.uint32)
+        if paired:
+            self.pe_r1 = np.zeros(n, HIT_DTYPE)
+            self.pe_r2 = np.zeros(n, HIT_DTYPE)
+            self.se2 = np.zeros(n, HIT_DTYPE)
+            self.cigar2 = np.zeros((n, stride), np.uint32)
+            self.n_cigar2 = np.zeros(n, np.uint32)
+        else:
+            self.pe_r1 = self.pe_r2 = self.se2 = self.cigar2 = self.n_cigar2 = None
+
+    def struct(self):
+        r = abg_results()
+        for k in ("pe_r1", "pe_r2", "se1", "se2", "cigar1", "cigar2", "n_cigar1", "n_cigar2"):
+            setattr(r, k, _ptr(getattr(self, k)))
+        return r
+
+    def d2h_bytes(self):
+        tot = 0
+        for k in ("pe_r1", "pe_r2", "se1", "se2", "cigar1", "cigar2", "n_cigar1", "n_cigar2"):
+            a = getattr(self, k)
+            if a is not None:
+                tot += a.nbytes
+        return tot
+
+    def cigars(self, end):
+        cig, n = (self.cigar1, self.n_cigar1) if end == 1 else (self.cigar2, self.n_cigar2)
+        return [cig[i, :n[i]].copy() for i in range(self.n)]
+
+
+def batch_struct(b1, b2=None):
+    s = abg_batch()
+    s.n = b1.n
+    s.seq1 = _ptr(b1.seq)
+    s.off1 = _ptr(b1.off)
+    if b2 is not None:
+        s.seq2 = _ptr(b2.seq)
+        s.off2 = _ptr(b2.off)
+    return s
+
+
+class Index:
+    """The AbismalIndex arrays resident in the HBM of one GPU."""
+
+    def __init__(self, index_file, device=0):
+        self.lib = load_library()
+        self.index_file = index_file
+        self._h = C.c_void_p()
+        v = make_view(index_file)
+        rc = self.lib.abg_index_create(C.byref(v), device, C.byref(self._h))
+        if rc != 0:
+            raise AbgError(self.lib.abg_last_error().decode())
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.abg_index_device_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            self.lib.abg_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Mapper:
+    """One stream's worth of mapping state on the GPU holding `index`."""
+
+    def __init__(self, index, mode=0, allow_ambig=False, min_dist=32, max_dist=3000, valid_frac=0.1,
+                 max_candidates=0, cigar_stride=64, max_batch=65536, max_read_len=256, count_work=False):
+        self.lib = index.lib
+        self.index = index
+        self.params = make_params(mode, allow_ambig, min_dist, max_dist, valid_frac, max_candidates, cigar_stride)
+        self.paired = bool(mode & MODE_PAIRED)
+        self.stride = cigar_stride
+        self._h = C.c_void_p()
+        rc = self.lib.abg_mapper_create(index._h, C.byref(self.params), max_batch, max_read_len,
+                                        1 if count_work else 0, C.byref(self._h))
+        if rc != 0:
+            raise AbgError(self.lib.abg_last_error().decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AbgError(self.lib.abg_last_error().decode())
+
+    def map_batch(self, b1, b2=None, results=None):
+        """Host buffers in, host buffers out (the call a user makes)."""
+        res = results if results is not None else Results(b1.n, self.paired, self.stride)
+        bs, rs = batch_struct(b1, b2), res.struct()
+        self._check(self.lib.abg_map_batch(self._h, C.byref(bs), C.byref(rs)))
+        return res
+
+    def upload(self, b1, b2=None):
+        bs = batch_struct(b1, b2)
+        self._check(self.lib.abg_mapper_upload(self._h, C.byref(bs)))
+
+    def run(self):
+        self._check(self.lib.abg_mapper_run(self._h))
+
+    def sync(self):
+        self._check(self.lib.abg_mapper_sync(self._h))
+
+    def download(self, n, results=None):
+        res = results if results is not None else Results(n, self.paired, self.stride)
+        rs = res.struct()
+        self._check(self.lib.abg_mapper_download(self._h, C.byref(rs)))
+        return res
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.abg_mapper_last_kernel_ms(self._h))
+
+    @property
+    def launches_per_run(self):
+        return int(self.lib.abg_mapper_launches_per_run(self._h))
+
+    def counters(self):
+        c = abg_work_counters()
+        self._check(self.lib.abg_mapper_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def close(self):
+        if self._h:
+            self.lib.abg_mapper_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,171 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C
+ABI (ctypes) and through the `abismal-b200 map` front end, against
+ (a) the CPU restatement (oracle/libabismal_oracle.so) record by record, and
+ (b) the unmodified reference binary (oracle/_ref/abismal) as SAM text,
+ (c) the reference's golden md5s for its own four map tests.
+Everything is integer work: the bar is bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from test_oracle_vs_ref import MAP_CMDS, MAP_PRE, UNPINNED, golden_md5
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from abismal_b200 import capi
+    lib = capi.load_library()  # raises if the CUDA library is missing: no fallback
+    if lib.abg_device_count() < 1:
+        pytest.fail("no CUDA device visible to libabismal_b200.so")
+    return capi
+
+
+@pytest.fixture(scope="module")
+def rep_index(workspace, gpu):
+    from abismal_b200 import Index, IndexFile
+    workspace.need_repeat()
+    ixf = IndexFile(workspace.path("rep.idx"))
+    ix = Index(ixf, 0)
+    yield ixf, ix
+    ix.close()
+
+
+def _fq(workspace, name, limit=None):
+    from abismal_b200 import load_fastq
+    return load_fastq(workspace.path(name), limit)
+
+
+RECORD_CASES = [
+    # tag, mode bits, kwargs, fastq files
+    ("se", 0, {}, ("rep_se_1.fq",)),
+    ("se_arich", 2, {}, ("rep_se_1.fq",)),
+    ("se_rpbat", 4, {}, ("rep_se_1.fq",)),
+    ("se_ambig_m", 0, {"allow_ambig": True, "valid_frac": 0.2}, ("rep_pe_1.fq",)),
+    ("se_c5", 0, {"max_candidates": 5}, ("rep_pe_2.fq",)),
+    ("pe", 1, {}, ("rep_pe_1.fq", "rep_pe_2.fq")),
+    ("pe_pbat", 1 | 2, {}, ("rep_pbat_1.fq", "rep_pbat_2.fq")),
+    ("pe_rpbat", 1 | 4, {}, ("rep_rpe_1.fq", "rep_rpe_2.fq")),
+    ("pe_rpbat_ambig", 1 | 4, {"allow_ambig": True}, ("rep_rpe_1.fq", "rep_rpe_2.fq")),
+    ("pe_frag", 1, {"min_dist": 50, "max_dist": 300, "valid_frac": 0.2}, ("rep_pe_1.fq", "rep_pe_2.fq")),
+    ("pe_c10", 1, {"max_candidates": 10}, ("rep_pe_1.fq", "rep_pe_2.fq")),
+]
+
+
+@pytest.mark.parametrize("tag,mode,kw,files", RECORD_CASES, ids=[c[0] for c in RECORD_CASES])
+def test_records_equal_oracle(workspace, rep_index, gpu, tag, mode, kw, files):
+    from abismal_b200 import Mapper
+    ixf, ix = rep_index
+    b = [_fq(workspace, f) for f in files]
+    max_len = max(x.max_len for x in b)
+    m = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max(max_len, 64), **kw)
+    o = helpers.OracleMapper(ixf, mode=mode, **kw)
+    got = m.map_batch(*b)
+    want = o.map_batch(*b)
+    helpers.assert_results_equal(got, want, bool(mode & 1))
+    mapped = want.pe_r1["pos"] != 0 if mode & 1 else want.se1["pos"] != 0
+    assert mapped.sum() > 0.2 * b[0].n  # the case is not vacuous
+    m.close()
+    o.close()
+
+
+def test_batch_split_and_repeat_invariance(workspace, rep_index, gpu):
+    """Size-independent properties: results do not depend on how reads are
+    batched, on their order, or on how often a batch is mapped."""
+    from abismal_b200 import Mapper
+    ixf, ix = rep_index
+    b1, b2 = _fq(workspace, "rep_pe_1.fq"), _fq(workspace, "rep_pe_2.fq")
+    m = Mapper(ix, mode=1, max_batch=b1.n, max_read_len=160)
+    full = m.map_batch(b1, b2)
+    again = m.map_batch(b1, b2)
+    helpers.assert_results_equal(full, again, True)
+    cut = b1.n // 3
+    lo = m.map_batch(b1.slice(0, cut), b2.slice(0, cut))
+    hi = m.map_batch(b1.slice(cut, b1.n), b2.slice(cut, b2.n))
+    for k in ("pe_r1", "pe_r2", "se1", "se2", "n_cigar1", "n_cigar2"):
+        assert np.array_equal(np.concatenate([getattr(lo, k), getattr(hi, k)]), getattr(full, k)), k
+    m.close()
+
+
+def test_empty_and_ragged_batches(workspace, rep_index, gpu):
+    from abismal_b200 import Mapper, ReadBatch
+    ixf, ix = rep_index
+    src = _fq(workspace, "rep_pe_1.fq", 64)
+    seqs = [src.sequence(i) for i in range(src.n)]
+    # ragged: skipped reads (empty), trimmed reads of different lengths, an all-N-masked read
+    seqs[0] = ""
+    seqs[5] = seqs[5][:44]
+    seqs[6] = seqs[6][:47]
+    seqs[7] = seqs[7][:48]
+    seqs[8] = seqs[8][:60] + "N" * 20 + seqs[8][80:]
+    seqs[9] = "ACGT" * 30
+    seqs[10] = "A" * 100
+    b = ReadBatch(["r%d" % i for i in range(len(seqs))], seqs)
+    m = Mapper(ix, mode=0, max_batch=256, max_read_len=160)
+    o = helpers.OracleMapper(ixf, mode=0)
+    helpers.assert_results_equal(m.map_batch(b), o.map_batch(b), False)
+    # paired with one or both ends empty
+    seqs2 = list(reversed(seqs))
+    seqs2[0] = ""
+    seqs2[-1] = ""
+    b2 = ReadBatch(b.names, seqs2)
+    mp = Mapper(ix, mode=1, max_batch=256, max_read_len=160)
+    op = helpers.OracleMapper(ixf, mode=1)
+    helpers.assert_results_equal(mp.map_batch(b, b2), op.map_batch(b, b2), True)
+    # an empty batch is legal
+    e = ReadBatch([], [])
+    r = m.map_batch(e)
+    assert r.n == 0
+    for x in (m, mp, o, op):
+        x.close()
+
+
+def test_bad_arguments_fail_loudly(rep_index, gpu):
+    from abismal_b200 import AbgError, Mapper, ReadBatch
+    ixf, ix = rep_index
+    m = Mapper(ix, mode=0, max_batch=8, max_read_len=100)
+    with pytest.raises(AbgError):
+        m.map_batch(ReadBatch(["x"], ["ACGT" * 50]))  # longer than max_read_len
+    with pytest.raises(AbgError):
+        m.map_batch(ReadBatch(["x"] * 9, ["ACGT" * 20] * 9))  # more than max_batch
+    with pytest.raises(AbgError):
+        m.map_batch(ReadBatch(["x"], ["ACGT" * 5]))  # shorter than 44: loader must empty it
+    m.close()
+
+
+@pytest.mark.parametrize("tag", sorted(MAP_CMDS))
+def test_cli_golden_md5(workspace, gpu, tag):
+    """The reference's own md5-pinned map tests, run through abismal-b200."""
+    workspace.need_trex()
+    g = golden_md5()
+    sam, st, _ = workspace.map_with(helpers.CLI, tag, MAP_CMDS[tag], MAP_PRE[tag])
+    assert helpers.md5(sam) == g["tests/%s.sam" % tag]
+    assert helpers.md5(st) == g["tests/%s.mstats" % tag]
+
+
+@pytest.mark.parametrize("tag,args", UNPINNED, ids=[u[0] for u in UNPINNED])
+def test_cli_equals_reference_binary(workspace, gpu, tag, args):
+    workspace.need_repeat()
+    rsam, rst, _ = workspace.map_with(helpers.REF_BIN, "ref_" + tag, args)
+    gsam, gst, _ = workspace.map_with(helpers.CLI, "gpu_" + tag, args)
+    assert helpers.sam_body(rsam) == helpers.sam_body(gsam)
+    assert open(rst).read() == open(gst).read()
+
+
+def test_cli_small_gpu_batches_and_gz(workspace, gpu):
+    """Output order and content do not depend on the GPU batch size; .gz input works."""
+    workspace.need_repeat()
+    import gzip
+    import shutil
+    for k in (1, 2):
+        with open(workspace.path("rep_pe_%d.fq" % k), "rb") as fi, gzip.open(workspace.path("rep_pe_%d.fq.gz" % k), "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    a, ast_, _ = workspace.map_with(helpers.CLI, "b_default", ["-i", "tests/rep.idx", "tests/rep_pe_1.fq", "tests/rep_pe_2.fq"])
+    b, bst, _ = workspace.map_with(helpers.CLI, "b_777", ["-gpu-batch", "777", "-i", "tests/rep.idx",
+                                                        "tests/rep_pe_1.fq.gz", "tests/rep_pe_2.fq.gz"])
+    assert helpers.sam_body(a)[3:] == helpers.sam_body(b)[3:]
+    assert open(ast_).read() == open(bst).read()

@@ -1,0 +1,75 @@
+"""CPU-only: pins the oracle.
+
+1. oracle/_ref/abismal (the UNMODIFIED reference compiled against the htslib
+   stand-in) must reproduce the reference's own golden md5s
+   (data/md5sum.txt -> tests/golden/reference_md5sum.txt), running the exact
+   commands of test_scripts/*.test.
+2. The CPU restatement (oracle/abismal_oracle.cpp, driven through the product's
+   host front end as oracle/oracle_map) must reproduce the same md5s for
+   SAM and stats, and must equal the reference binary on the modes no golden
+   file pins (-R, -A, -a, -m, -c, -l/-L, -j, PE files mapped single-end).
+"""
+import os
+
+import pytest
+
+import helpers
+
+MAP_CMDS = {  # test_scripts/test_abismal{,_pe,_pbat,_rpbat}.test
+    "reads": ["-i", "tests/tRex1.idx", "tests/reads_1.fq"],
+    "reads_pe": ["-i", "tests/tRex1.idx", "tests/reads_pe_1.fq", "tests/reads_pe_2.fq"],
+    "reads_pbat_pe": ["-i", "tests/tRex1.idx", "tests/reads_pbat_pe_1.fq", "tests/reads_pbat_pe_2.fq"],
+    "reads_rpbat_pe": ["-i", "tests/tRex1.idx", "tests/reads_rpbat_pe_1.fq", "tests/reads_rpbat_pe_2.fq"],
+}
+MAP_PRE = {"reads": [], "reads_pe": [], "reads_pbat_pe": ["-P"], "reads_rpbat_pe": ["-P"]}
+
+
+def golden_md5():
+    out = {}
+    with open(os.path.join(helpers.GOLDEN, "reference_md5sum.txt")) as f:
+        for ln in f:
+            h, p = ln.split()
+            out[p] = h
+    return out
+
+
+def test_reference_binary_reproduces_inputs_and_index(workspace):
+    workspace.need_trex()
+    g = golden_md5()
+    for name in ("tRex1.idx", "reads_1.fq", "reads_pe_1.fq", "reads_pe_2.fq", "reads_pbat_pe_1.fq",
+                 "reads_pbat_pe_2.fq", "reads_rpbat_pe_1.fq", "reads_rpbat_pe_2.fq"):
+        assert helpers.md5(workspace.path(name)) == g["tests/" + name], name
+
+
+@pytest.mark.parametrize("tag", sorted(MAP_CMDS))
+def test_golden_sam_md5_reference_and_oracle(workspace, tag):
+    workspace.need_trex()
+    g = golden_md5()
+    for tool in (helpers.REF_BIN, helpers.ORACLE_MAP):
+        sam, st, _ = workspace.map_with(tool, tag, MAP_CMDS[tag], MAP_PRE[tag])
+        assert helpers.md5(sam) == g["tests/%s.sam" % tag], (tool, tag)
+        assert helpers.md5(st) == g["tests/%s.mstats" % tag], (tool, tag)
+
+
+UNPINNED = [
+    ("se_R", ["-R", "-i", "tests/rep.idx", "tests/rep_se_1.fq"]),
+    ("se_A_a", ["-A", "-a", "-i", "tests/rep.idx", "tests/rep_se_1.fq"]),
+    ("se_c5", ["-c", "5", "-i", "tests/rep.idx", "tests/rep_se_1.fq"]),
+    ("pe", ["-i", "tests/rep.idx", "tests/rep_pe_1.fq", "tests/rep_pe_2.fq"]),
+    ("pe_a_j", ["-a", "-j", "-i", "tests/rep.idx", "tests/rep_pe_1.fq", "tests/rep_pe_2.fq"]),
+    ("pe_m_l_L", ["-m", "0.2", "-l", "50", "-L", "300", "-i", "tests/rep.idx", "tests/rep_pe_1.fq", "tests/rep_pe_2.fq"]),
+    ("pe_P", ["-P", "-i", "tests/rep.idx", "tests/rep_pbat_1.fq", "tests/rep_pbat_2.fq"]),
+    ("pe_R", ["-R", "-i", "tests/rep.idx", "tests/rep_rpe_1.fq", "tests/rep_rpe_2.fq"]),
+    ("pe_R_a", ["-R", "-a", "-i", "tests/rep.idx", "tests/rep_rpe_1.fq", "tests/rep_rpe_2.fq"]),
+    ("pe2_as_se_P", ["-P", "-i", "tests/rep.idx", "tests/rep_pe_2.fq"]),
+]
+
+
+@pytest.mark.parametrize("tag,args", UNPINNED, ids=[u[0] for u in UNPINNED])
+def test_oracle_equals_reference_on_unpinned_modes(workspace, tag, args):
+    workspace.need_repeat()
+    rsam, rst, _ = workspace.map_with(helpers.REF_BIN, "ref_" + tag, args)
+    osam, ost, _ = workspace.map_with(helpers.ORACLE_MAP, "or_" + tag, args)
+    assert helpers.sam_body(rsam) == helpers.sam_body(osam)
+    assert open(rst).read() == open(ost).read()
+    assert len(helpers.sam_body(rsam)) > 10
