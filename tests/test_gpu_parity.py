@@ -68,7 +68,7 @@ def test_records_equal_oracle(workspace, rep_index, gpu, tag, mode, kw, files):
     want = o.map_batch(*b)
     helpers.assert_results_equal(got, want, bool(mode & 1))
     mapped = want.pe_r1["pos"] != 0 if mode & 1 else want.se1["pos"] != 0
-    assert mapped.sum() > 0.2 * b[0].n  # the case is not vacuous
+    assert mapped.sum() > 50  # the case is not vacuous
     m.close()
     o.close()
 
