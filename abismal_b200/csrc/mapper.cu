@@ -82,6 +82,7 @@ struct abg_mapper {
   unsigned int *h_flags = nullptr;
   abg_work_counters counters{};
   uint32_t cur_n = 0;
+  bool timed = false;  // ev0/ev1 have been recorded
 };
 
 extern "C" {
@@ -331,6 +332,7 @@ int abg_mapper_run(abg_mapper *m) {
     ABG_CUDA(cudaGetLastError());
   }
   ABG_CUDA(cudaEventRecord(m->ev1, m->stream));
+  m->timed = true;
   return ABG_OK;
 }
 
@@ -338,7 +340,10 @@ int abg_mapper_sync(abg_mapper *m) {
   if (!m) return fail(ABG_ERR_INVALID, "abg_mapper_sync: null mapper");
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ABG_CUDA(cudaStreamSynchronize(m->stream));
-  if (cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) m->last_ms = 0.f;
+  if (!m->timed || cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) {
+    m->last_ms = 0.f;
+    (void)cudaGetLastError();  // do not leave a stale error behind
+  }
   return ABG_OK;
 }
 
@@ -362,7 +367,10 @@ int abg_mapper_download(abg_mapper *m, abg_results *r) {
     ABG_CUDA(cudaMemcpyAsync(&m->counters, m->d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              m->stream));
   ABG_CUDA(cudaStreamSynchronize(m->stream));
-  if (cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) m->last_ms = 0.f;
+  if (!m->timed || cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) {
+    m->last_ms = 0.f;
+    (void)cudaGetLastError();  // do not leave a stale error behind
+  }
   if (m->h_flags[1] != 0u)
     return fail(ABG_ERR_CIGAR_OVERFLOW, "abg_map_batch: a CIGAR needed more than cigar_stride operations");
   std::memcpy(r->se1, m->h_se[0], (size_t)n * sizeof(abg_hit));

@@ -19,7 +19,7 @@ class ReadBatch:
 
     def slice(self, lo, hi):
         b = ReadBatch.__new__(ReadBatch)
-        b.names = self.names[lo:hi]
+        b.names = self.names[lo:hi] if self.names is not None else None
         b.n = hi - lo
         b.off = (self.off[lo:hi + 1] - self.off[lo]).astype(np.uint32)
         b.seq = self.seq[int(self.off[lo]):max(int(self.off[hi]), int(self.off[lo]) + 1)].copy()
