@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -14,6 +15,8 @@
 #include "mapper_kernels.cuh"
 
 namespace {
+
+constexpr int kDefaultMinB = 3;
 
 thread_local std::string g_err;
 
@@ -58,8 +61,9 @@ struct abg_mapper {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
   // launch shape
-  int grid = 0;
+  int grid = 0, minb = 0;
   size_t smem = 0;
+  const void *kernel = nullptr;
   // device batch
   char *d_seq[2] = {nullptr, nullptr};
   uint32_t *d_off[2] = {nullptr, nullptr};
@@ -70,8 +74,8 @@ struct abg_mapper {
   // scratch
   uint64_t *d_pe_overflow = nullptr;
   int16_t *d_mem_scr = nullptr;
-  uint32_t *d_tb = nullptr;
-  uint32_t tb_rows = 0;
+  uint64_t *d_tb = nullptr;
+  uint32_t tb_words = 0;
   unsigned int *d_work = nullptr;   // [0] work counter, [1] error flag
   unsigned long long *d_counters = nullptr;
   // pinned staging
@@ -104,6 +108,9 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
   ABG_CUDA(cudaGetDeviceCount(&n_dev));
   if (device < 0 || device >= n_dev) return fail(ABG_ERR_CUDA, "abg_index_create: no such CUDA device");
   ABG_CUDA(cudaSetDevice(device));
+  // The path is random 8..88-byte gathers: ask L2 to fetch single 32-byte sectors from HBM instead of
+  // promoting every miss to 64/128 bytes (a hint; ignored where unsupported).
+  if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) != cudaSuccess) (void)cudaGetLastError();
   abg_index *ix = new (std::nothrow) abg_index();
   if (!ix) return fail(ABG_ERR_INVALID, "out of host memory");
   ix->device = device;
@@ -181,19 +188,20 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   ABG_M(cudaEventCreate(&m->ev1));
 
   // launch shape: persistent grid, as many CTAs per SM as shared memory/registers allow
+  m->smem = ab2dev::block_smem_bytes(m->ml, m->paired);
   {
-    size_t b = 0;
-    const size_t ml = m->ml;
-    b += 2 * ml + (ml + 32) + ml / 2 + ((ml + 64) / 16 + 2) * 8 + (size_t)2 * ab2dev::kSeSlots * 8;
-    if (m->paired) b += (size_t)2 * ab2dev::kPeSmemSlots * 8;
-    b = (b + 15) & ~(size_t)15;
-    m->smem = b * ab2dev::kWarpsPerBlock;
+    // register-allocation variant (CTAs per SM the kernel is bounded for); ABISMAL_B200_MINB overrides for tuning
+    const char *e = std::getenv("ABISMAL_B200_MINB");
+    const int v = e ? std::atoi(e) : 0;
+    m->minb = (v >= 2 && v <= 4) ? v : kDefaultMinB;
   }
-  ABG_M(cudaFuncSetAttribute(ab2dev::map_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  m->kernel = m->minb == 2 ? (const void *)ab2dev::map_reads_kernel<2>
+            : m->minb == 4 ? (const void *)ab2dev::map_reads_kernel<4>
+                           : (const void *)ab2dev::map_reads_kernel<3>;
+  ABG_M(cudaFuncSetAttribute(m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
   int n_sm = 0, per_sm = 0;
   ABG_M(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ix->device));
-  ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ab2dev::map_reads_kernel, ab2dev::kThreadsPerBlock,
-                                                     m->smem));
+  ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->kernel, ab2dev::kThreadsPerBlock, m->smem));
   if (per_sm < 1) {
     abg_mapper_destroy(m);
     return fail(ABG_ERR_CUDA, "abg_mapper_create: kernel does not fit on an SM");
@@ -222,8 +230,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     ABG_M(cudaMalloc(&m->d_pe_overflow, slots * 2 * ab2dev::kPeLarge * sizeof(uint64_t)));
     ABG_M(cudaMalloc(&m->d_mem_scr, slots * ab2dev::kPeLarge * sizeof(int16_t)));
   }
-  m->tb_rows = m->ml + 64;
-  ABG_M(cudaMalloc(&m->d_tb, slots * m->tb_rows * 4 * sizeof(uint32_t)));
+  m->tb_words = ab2dev::tb_sm_words(m->ml);
+  ABG_M(cudaMalloc(&m->d_tb, slots * 2 * m->tb_words * 32 * sizeof(uint64_t)));
   ABG_M(cudaMalloc(&m->d_work, 2 * sizeof(unsigned int)));
   ABG_M(cudaMallocHost(&m->h_flags, 2 * sizeof(unsigned int)));
   if (m->count_work) ABG_M(cudaMalloc(&m->d_counters, 6 * sizeof(unsigned long long)));
@@ -319,7 +327,7 @@ int abg_mapper_run(abg_mapper *m) {
   P.pe_overflow = m->d_pe_overflow;
   P.mem_scr = m->d_mem_scr;
   P.tb = m->d_tb;
-  P.tb_rows = m->tb_rows;
+  P.tb_words = m->tb_words;
   P.work_counter = m->d_work;
   P.error_flag = m->d_work + 1;
   P.counters = m->d_counters;
@@ -328,8 +336,8 @@ int abg_mapper_run(abg_mapper *m) {
   ABG_CUDA(cudaEventRecord(m->ev0, m->stream));
   if (P.n > 0) {
     const int grid = (int)std::min<uint64_t>((uint64_t)m->grid, ((uint64_t)P.n + ab2dev::kWarpsPerBlock - 1) / ab2dev::kWarpsPerBlock);
-    ab2dev::map_reads_kernel<<<grid, ab2dev::kThreadsPerBlock, m->smem, m->stream>>>(P);
-    ABG_CUDA(cudaGetLastError());
+    void *args[] = {&P};
+    ABG_CUDA(cudaLaunchKernel(m->kernel, dim3(grid), dim3(ab2dev::kThreadsPerBlock), args, m->smem, m->stream));
   }
   ABG_CUDA(cudaEventRecord(m->ev1, m->stream));
   m->timed = true;

@@ -14,21 +14,30 @@
 //   SE selection           align_se_candidates              abismal.cpp:1435-1497
 //   PE mating + selection  best_pair/best_single/...        abismal.cpp:1715-1885
 //
-// Parallel decomposition inside the warp (the results are order dependent in
-// the reference, so only PURE quantities are computed in parallel):
-//   * 32 seed offsets at a time: each lane hashes one offset and gathers its two
-//     counter pairs; bucket sizes are prefix-summed across the warp so that
-//   * 32 candidates at a time (in the reference's canonical order: offset,
-//     two-letter bucket before three-letter bucket, bucket order) each get one
-//     lane doing the index gather + packed-genome gather + popcount compare;
+// The reference's results are order dependent (cutoffs tighten as hits arrive,
+// heaps evict, ties break by iteration order), so only PURE quantities are
+// computed in parallel and the order-dependent state machine is replayed in the
+// reference's sequence on warp-uniform state:
+//   * seed hashes come from three bit planes of the encoded read (two-letter
+//     bit, three-letter digit bits) built with ballots; a lane extracts its
+//     25-bit key with a funnel shift + brev and its base-3 key with four table
+//     look-ups, then gathers its two counter pairs (4 loads in flight per lane);
+//   * candidates are enumerated in the reference's canonical order (offset,
+//     two-letter bucket before three-letter bucket, bucket order) and compared
+//     kCand per lane at a time: all index gathers are issued together, then all
+//     first-stage genome gathers, so a lane keeps up to 5*kCand independent
+//     loads in flight instead of one dependent chain (the HBM-gather hot spot);
 //   * survivors (ballot) are replayed IN ORDER against the candidate set with
-//     libstdc++'s heap routines restated verbatim, executed redundantly by all
-//     lanes on warp-uniform state (same-value writes), so the cutoff tightening,
-//     evictions, sure_ambig exits and the specific->sensitive gate match the
-//     reference bit for bit;
-//   * banded DP: lanes are band columns (1 or 2 per lane), rows are sequential,
-//     the serial from_left recurrence is a warp max-plus prefix scan, traceback
-//     arrows go to 2-bit planes written with ballots.
+//     libstdc++'s heap routines restated verbatim, so cutoff tightening,
+//     evictions, sure_ambig exits and the specific->sensitive gate match;
+//   * banded DP runs as a wavefront: lane l owns band columns 2l and 2l+1 and,
+//     at iteration T, row T-l; one shuffle per cell column replaces the serial
+//     from_left scan.  Traceback arrows are packed 4 bits per iteration into a
+//     per-lane 64-bit shift register and flushed every 16 iterations.
+//
+// All per-warp state that device functions share lives in SHARED memory (the
+// kernel parameters are copied there too), so no function takes a context
+// struct by reference: nothing is forced into local memory.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -47,8 +56,9 @@ constexpr int kPeSmall = 32;        // pe_candidates::max_size_small
 constexpr int kPeLarge = 32 << 10;  // pe_candidates::max_size_large
 constexpr int kPeSmemSlots = 128;   // PE heap entries kept in shared memory
 constexpr int kMaxDiffs = 32767;
-constexpr int kNegInf = -(1 << 28);
-constexpr uint32_t kHashMaskThree = 43046721u;
+constexpr int kCand = 4;            // candidates per lane per compare chunk (tight bound; 2 under a loose bound)
+constexpr int kTbLanesSm = 8;       // traceback words of lanes < 8 (band <= 16) stay in shared memory
+constexpr int kTbCacheMaxCands = 4; // record traceback while scoring when a set has at most this many candidates
 
 struct IndexDev {
   const uint64_t *genome;
@@ -72,11 +82,11 @@ struct KernelParams {
   uint32_t mode, allow_ambig, min_dist, max_dist, max_candidates;
   double valid_frac;
   // per-warp-slot scratch
-  uint32_t ml;  // padded max read length (multiple of 32)
+  uint32_t ml;            // padded max read length (multiple of 32)
   uint64_t *pe_overflow;  // [slots][2][kPeLarge]
   int16_t *mem_scr;       // [slots][kPeLarge]
-  uint32_t *tb;           // [slots][tb_rows][4]
-  uint32_t tb_rows;
+  uint64_t *tb;           // [slots][2][tb_words][32]
+  uint32_t tb_words;      // 64-bit traceback words per lane per alignment
   unsigned int *work_counter;
   unsigned int *error_flag;
   unsigned long long *counters;  // abg_work_counters layout, or nullptr
@@ -105,18 +115,6 @@ struct Hit {
   __device__ __forceinline__ uint64_t key() const { return ((uint64_t)pos() << 16) | flags(); }
 };
 
-// heap storage: first `cap_sm` entries in shared memory, the rest in global
-struct HeapRef {
-  uint64_t *sm;
-  uint64_t *gm;
-  int cap_sm;
-  __device__ __forceinline__ Hit get(int i) const { return Hit(i < cap_sm ? sm[i] : gm[i]); }
-  __device__ __forceinline__ void set(int i, Hit h) const {
-    if (i < cap_sm) sm[i] = h.w;
-    else gm[i] = h.w;
-  }
-};
-
 // ---- thresholds: evaluated in double exactly as the reference writes them ----
 __device__ __forceinline__ int frac_of(double f, uint32_t x) {  // static_cast<score_t>(f * x)
   return (int)(int16_t)__double2int_rz(__dmul_rn(f, (double)x));
@@ -128,12 +126,160 @@ __device__ __forceinline__ bool valid_len(uint32_t aln_len, uint32_t readlen) { 
   return aln_len >= (a > 44u ? a : 44u);
 }
 
-// ---- candidate set: se_candidates or pe_candidates, warp-uniform state -------
+// ---- shared memory ----------------------------------------------------------------
+// block: [KernelParams | base-3 tables | warp 0 | warp 1 | ...]
+struct CandState {  // scalar state of one se_candidates / pe_candidates
+  int sz, cutoff, good_cutoff, capacity;
+  int sure_ambig, is_pe;
+  uint64_t best;  // SE only
+};
+
+struct AlnOut {
+  int score, row, col, bw;
+};
+
+struct TbKey {  // which alignment the traceback words of a slot belong to
+  uint32_t pos, key, valid;
+  int score, row, col, bw;
+  uint32_t pad;
+};
+
+struct WarpScalars {
+  uint32_t len[2];
+  uint32_t qkey[2];     // which (flags) is encoded in qcode[e]; ~0u = none
+  uint32_t packed_key;  // which (end, flags) is in packed/planes; ~0u = none
+  uint32_t pad[3];
+  TbKey tbk[2];
+  unsigned long long cnt[6];
+};
+
+constexpr int kParamBytes = 512;
+constexpr int kTab3Bytes = 2 * 256 * 4;
+static_assert(sizeof(KernelParams) <= kParamBytes, "KernelParams must fit its shared-memory slot");
+
+__host__ __device__ __forceinline__ uint32_t tb_sm_words(uint32_t ml) { return (ml + 64u + 32u + 15u) / 16u; }
+
+struct WarpLayout {
+  uint32_t o_packed, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_base, o_qcode, o_refb, total;
+  uint32_t plane_words;
+};
+
+__host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool paired) {
+  WarpLayout L;
+  uint32_t o = 0;
+  L.o_packed = o;
+  o += ml / 2;                               // packed read, ml/16 u64
+  L.o_se = o;
+  o += 2u * kSeSlots * 8u;                   // two SE heaps
+  L.o_pe = o;
+  if (paired) o += 2u * kPeSmemSlots * 8u;   // two PE heap heads
+  L.o_cs = o;
+  o += 4u * (uint32_t)sizeof(CandState);
+  L.o_scal = o;
+  o += (uint32_t)sizeof(WarpScalars);
+  L.o_tb = o;
+  o += 2u * tb_sm_words(ml) * kTbLanesSm * 8u;  // traceback words of 2 slots
+  L.plane_words = ml / 32u + 2u;
+  L.o_planes = o;
+  o += 3u * L.plane_words * 4u;
+  L.o_base = o;
+  o += 2u * ml;
+  L.o_qcode = o;
+  o += 2u * (ml + 32u);
+  L.o_refb = o;
+  o += ml + 64u + 32u;
+  L.total = (o + 15u) & ~15u;
+  return L;
+}
+
+__host__ __device__ __forceinline__ size_t block_smem_bytes(uint32_t ml, bool paired) {
+  return (size_t)kParamBytes + kTab3Bytes + (size_t)warp_layout(ml, paired).total * kWarpsPerBlock;
+}
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__device__ __forceinline__ const KernelParams &params() { return *reinterpret_cast<const KernelParams *>(smem_raw); }
+__device__ __forceinline__ const uint32_t *tab3() { return reinterpret_cast<const uint32_t *>(smem_raw + kParamBytes); }
+
+struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside every function
+  unsigned char *base_ptr;
+  WarpLayout L;
+  int lane;
+  __device__ __forceinline__ Warp() {
+    const KernelParams &P = params();
+    L = warp_layout(P.ml, (P.mode & ABG_MODE_PAIRED) != 0);
+    base_ptr = smem_raw + kParamBytes + kTab3Bytes + (size_t)L.total * (threadIdx.x >> 5);
+    lane = threadIdx.x & 31;
+  }
+  __device__ __forceinline__ uint64_t *packed() const { return reinterpret_cast<uint64_t *>(base_ptr + L.o_packed); }
+  __device__ __forceinline__ uint64_t *se_heap(int i) const { return reinterpret_cast<uint64_t *>(base_ptr + L.o_se) + i * kSeSlots; }
+  __device__ __forceinline__ uint64_t *pe_heap(int i) const { return reinterpret_cast<uint64_t *>(base_ptr + L.o_pe) + i * kPeSmemSlots; }
+  __device__ __forceinline__ CandState *cs(int id) const { return reinterpret_cast<CandState *>(base_ptr + L.o_cs) + id; }
+  __device__ __forceinline__ WarpScalars *scal() const { return reinterpret_cast<WarpScalars *>(base_ptr + L.o_scal); }
+  __device__ __forceinline__ uint64_t *tb_sm(int slot) const {
+    return reinterpret_cast<uint64_t *>(base_ptr + L.o_tb) + (size_t)slot * tb_sm_words(params().ml) * kTbLanesSm;
+  }
+  __device__ __forceinline__ uint32_t *plane(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_planes) + k * L.plane_words; }
+  __device__ __forceinline__ uint8_t *base(int e) const { return base_ptr + L.o_base + (size_t)e * params().ml; }
+  __device__ __forceinline__ uint8_t *qcode(int e) const { return base_ptr + L.o_qcode + (size_t)e * (params().ml + 32u); }
+  __device__ __forceinline__ uint8_t *refb() const { return base_ptr + L.o_refb; }
+  __device__ __forceinline__ size_t slot() const { return (size_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); }
+  __device__ __forceinline__ uint64_t *tb_gm(int s) const {
+    const KernelParams &P = params();
+    return P.tb + (slot() * 2 + s) * (size_t)P.tb_words * 32;
+  }
+};
+
+// candidate set ids: 0,1 = se_candidates of end 1 / end 2; 2,3 = the two pe_candidates of a map_fragments call
+struct HeapRef {
+  uint64_t *sm;
+  uint64_t *gm;
+  int cap_sm;
+  __device__ __forceinline__ Hit get(int i) const { return Hit(i < cap_sm ? sm[i] : gm[i]); }
+  __device__ __forceinline__ void set(int i, Hit h) const {
+    if (i < cap_sm) sm[i] = h.w;
+    else gm[i] = h.w;
+  }
+};
+
+__device__ __forceinline__ HeapRef heap_of(const Warp &W, int id) {
+  if (id < 2) return HeapRef{W.se_heap(id), nullptr, kSeSlots};
+  uint64_t *ov = params().pe_overflow + W.slot() * (size_t)2 * kPeLarge;
+  return HeapRef{W.pe_heap(id - 2), ov + (size_t)(id - 2) * kPeLarge, kPeSmemSlots};
+}
+
+// ---- candidate set: register working copy of CandState + heap, warp-uniform ------------
 struct CandSet {
   HeapRef v;
   int sz, cutoff, good_cutoff, capacity;
   bool sure_ambig, is_pe;
   Hit best;  // SE only
+
+  __device__ __forceinline__ void load(const Warp &W, int id) {
+    v = heap_of(W, id);
+    const CandState *s = W.cs(id);
+    sz = s->sz;
+    cutoff = s->cutoff;
+    good_cutoff = s->good_cutoff;
+    capacity = s->capacity;
+    sure_ambig = s->sure_ambig != 0;
+    is_pe = s->is_pe != 0;
+    best = Hit(s->best);
+  }
+  __device__ __forceinline__ void store(const Warp &W, int id) const {  // same values from every lane
+    CandState *s = W.cs(id);
+    __syncwarp();
+    if (W.lane == 0) {
+      s->sz = sz;
+      s->cutoff = cutoff;
+      s->good_cutoff = good_cutoff;
+      s->capacity = capacity;
+      s->sure_ambig = sure_ambig;
+      s->is_pe = is_pe;
+      s->best = best.w;
+    }
+    __syncwarp();
+  }
 
   __device__ __forceinline__ bool full() const { return sz == (is_pe ? capacity : kSeMax); }
 
@@ -192,6 +338,7 @@ struct CandSet {
   }
   __device__ void reset_pe(uint32_t readlen) {  // pe_candidates::reset :778-787
     is_pe = true;
+    best = Hit(0);
     v.set(0, Hit(invalid_hit_diffs(readlen), 0, 0));
     sure_ambig = false;
     cutoff = invalid_hit_diffs(readlen);
@@ -207,7 +354,7 @@ struct CandSet {
   __device__ __forceinline__ bool should_align() const { return sz != kPeLarge || cutoff != 0; }
 
   // se_candidates::update :394-404 / pe_candidates::update :824-842
-  __device__ void update(bool specific, int d, uint32_t flags, uint32_t pos) {
+  __device__ __forceinline__ void update(bool specific, int d, uint32_t flags, uint32_t pos) {
     if (!is_pe) {
       if (d == 0) {
         if (best.empty()) best = Hit(0, flags, pos);
@@ -242,24 +389,6 @@ struct CandSet {
   }
 };
 
-// ---- per-warp context ----------------------------------------------------------
-struct WarpCtx {
-  const KernelParams *P;
-  int lane;
-  // shared memory
-  uint8_t *base[2];   // one-hot base codes of each end, FASTQ orientation
-  uint8_t *qcode;     // current pass: bisulfite-encoded read, zero padded
-  uint64_t *packed;   // current pass: pack_read
-  uint64_t *refw;     // DP: staged genome words
-  uint32_t len[2];
-  uint32_t cur_key;   // which (end, flags) is in qcode/packed; ~0u = none
-  // global scratch
-  uint32_t *tb;
-  int16_t *mem_scr;
-  // counters (lane-local partial sums, reduced at the end)
-  unsigned long long c_lookup, c_entry, c_word, c_align, c_dpref;
-};
-
 __device__ __forceinline__ uint32_t get_bit(uint32_t nt) { return (nt & 5u) == 0u; }
 __device__ __forceinline__ uint32_t three_num(bool g_to_a, uint32_t nt) {
   return g_to_a ? ((((nt & 8u) != 0u) << 1) | ((nt & 2u) != 0u)) : ((((nt & 4u) != 0u) << 1) | ((nt & 1u) != 0u));
@@ -270,72 +399,86 @@ __device__ __forceinline__ uint32_t genome_base(const uint64_t *g, uint64_t pos)
 }
 
 // Load one end of a read/pair: ASCII -> one-hot nibble (A1 C2 G4 T8, else 0).
-__device__ void load_end(WarpCtx &c, int end, const char *s, uint32_t n) {
-  c.len[end] = n;
-  for (uint32_t i = c.lane; i < n; i += 32) {
+__device__ __forceinline__ void load_end(const Warp &W, int end, const char *s, uint32_t n) {
+  uint8_t *b = W.base(end);
+  for (uint32_t i = W.lane; i < n; i += 32) {
     const char ch = s[i];
-    uint8_t b = 0;
-    if (ch == 'A' || ch == 'a') b = 1;
-    else if (ch == 'C' || ch == 'c') b = 2;
-    else if (ch == 'G' || ch == 'g') b = 4;
-    else if (ch == 'T' || ch == 't') b = 8;
-    c.base[end][i] = b;
+    uint8_t x = 0;
+    if (ch == 'A' || ch == 'a') x = 1;
+    else if (ch == 'C' || ch == 'c') x = 2;
+    else if (ch == 'G' || ch == 'g') x = 4;
+    else if (ch == 'T' || ch == 't') x = 8;
+    b[i] = x;
   }
   __syncwarp();
 }
 
-// prep_read + pack_read for the pass identified by `flags` on `end`:
+// prep_read for the pass identified by `flags` on `end` into qcode[end]:
 // orientation by the rc bit, encoding by a_rich XOR rc (abismal.cpp:1463-1465).
-__device__ void build_pass(WarpCtx &c, int end, uint32_t flags) {
-  const uint32_t key = ((uint32_t)end << 16) | (flags & (ABG_FLAG_RC | ABG_FLAG_A_RICH));
-  if (c.cur_key == key) return;
-  c.cur_key = key;
+__device__ __noinline__ void build_qcode(int end, uint32_t flags) {
+  const Warp W;
+  WarpScalars *S = W.scal();
+  const uint32_t key = flags & (ABG_FLAG_RC | ABG_FLAG_A_RICH);
+  if (S->qkey[end] == key) return;
+  __syncwarp();
   const bool rc = flags & ABG_FLAG_RC;
   const bool enc_a = ((flags & ABG_FLAG_A_RICH) != 0) != rc;
-  const uint32_t n = c.len[end];
-  const uint8_t *b = c.base[end];
-  __syncwarp();
-  for (uint32_t i = c.lane; i < n + 32; i += 32) {
+  const uint32_t n = S->len[end];
+  const uint8_t *b = W.base(end);
+  uint8_t *q = W.qcode(end);
+  for (uint32_t i = W.lane; i < n + 32; i += 32) {
     uint32_t code = 0;
     if (i < n) {
       uint32_t x = rc ? b[n - 1 - i] : b[i];
-      if (rc) x = ((x & 1u) << 3) | ((x & 2u) << 1) | ((x & 4u) >> 1) | ((x & 8u) >> 3);  // complement
+      if (rc) x = (__brev(x) >> 28);  // complement of a one-hot nibble = bit reversal (A1<->T8, C2<->G4)
       code = enc_a ? (x == 1u ? 5u : x) : (x == 8u ? 10u : x);
     }
-    c.qcode[i] = (uint8_t)code;
+    q[i] = (uint8_t)code;
   }
+  if (W.lane == 0) S->qkey[end] = key;
   __syncwarp();
+}
+
+// pack_read (abismal.cpp:1393-1426) + the three hash bit planes for qcode[end]
+__device__ __noinline__ void build_packed(int end, uint32_t flags) {
+  const Warp W;
+  WarpScalars *S = W.scal();
+  const uint32_t key = ((uint32_t)end << 16) | (flags & (ABG_FLAG_RC | ABG_FLAG_A_RICH));
+  if (S->packed_key == key) return;
+  __syncwarp();
+  const bool g_to_a = ((flags & ABG_FLAG_A_RICH) != 0) != ((flags & ABG_FLAG_RC) != 0);
+  const uint32_t n = S->len[end];
+  const uint8_t *q = W.qcode(end);
+  uint64_t *packed = W.packed();
   const uint32_t nw = (n + 15) / 16;
-  for (uint32_t w = c.lane; w < nw; w += 32) {
+  for (uint32_t w = W.lane; w < nw; w += 32) {
     uint64_t word = 0;
 #pragma unroll
     for (uint32_t j = 0; j < 16; ++j) {
       const uint32_t i = 16 * w + j;
-      const uint64_t nib = i < n ? c.qcode[i] : 0xFull;  // tail matches anything :1424-1425
+      const uint64_t nib = i < n ? q[i] : 0xFull;  // tail matches anything :1424-1425
       word |= nib << (4 * j);
     }
-    c.packed[w] = word;
+    packed[w] = word;
   }
+  // planes: bit p of word w describes base 32w+p; bases past the end encode as 0 (zero padding)
+  uint32_t *p2 = W.plane(0), *p3a = W.plane(1), *p3b = W.plane(2);
+  const uint32_t pw = W.L.plane_words;
+  for (uint32_t w = 0; w < pw; ++w) {
+    const uint32_t i = 32 * w + W.lane;
+    const uint32_t code = i < n ? q[i] : 0u;
+    const uint32_t t = three_num(g_to_a, code);
+    const unsigned m2 = __ballot_sync(FULL, get_bit(code));
+    const unsigned ma = __ballot_sync(FULL, t & 1u);
+    const unsigned mb = __ballot_sync(FULL, t & 2u);
+    if (W.lane == 0) {
+      p2[w] = m2;
+      p3a[w] = ma;
+      p3b[w] = mb;
+    }
+  }
+  if (W.lane == 0) S->packed_key = key;
   __syncwarp();
-}
-
-// full_compare (abismal.cpp:1105-1122): exact distance if it is <= cutoff,
-// otherwise some value > cutoff (early exit).
-__device__ __forceinline__ int full_compare(const uint64_t *__restrict__ genome, uint32_t the_pos,
-                                            const uint64_t *packed, int n_words, int cutoff, int &words_seen) {
-  const uint64_t *g = genome + (the_pos >> 4);
-  const uint32_t off = (the_pos & 15u) << 2;
-  int d = 0;
-  uint64_t cur = __ldg(g);
-  int w = 0;
-  for (; w < n_words && d <= cutoff; ++w) {
-    const uint64_t nxt = __ldg(g + w + 1);
-    const uint64_t gw = (cur >> off) | ((nxt << (63u - off)) << 1);
-    d += 16 - __popcll(packed[w] & gw);
-    cur = nxt;
-  }
-  words_seen = w;
-  return d;
 }
 
 // std::lower_bound over idx[low, high): first entry whose genome base at
@@ -356,9 +499,14 @@ __device__ __forceinline__ uint32_t lower_bound_idx(const uint32_t *idx, uint32_
   return first;
 }
 
+struct SeedRange {  // narrowed bucket [low, high) and the seed length reached
+  uint32_t low, high, p;
+};
+
 // find_candidates<25> (abismal.cpp:1163-1194); `read_start` = qcode + i
-__device__ uint32_t find_candidates(const IndexDev &ix, uint32_t maxc, const uint8_t *read_start, uint32_t read_lim,
-                                    uint32_t &low, uint32_t &high) {
+__device__ __noinline__ SeedRange find_candidates(uint32_t maxc, const uint8_t *read_start, uint32_t read_lim,
+                                                  uint32_t low, uint32_t high) {
+  const IndexDev &ix = params().ix;
   uint32_t p = 25;
   uint32_t prev_low = low, prev_high = high;
   for (; p != read_lim && (high - low) > maxc; ++p) {
@@ -376,13 +524,14 @@ __device__ uint32_t find_candidates(const IndexDev &ix, uint32_t maxc, const uin
     low = prev_low;
     high = prev_high;
   }
-  return p;
+  return SeedRange{low, high, p};
 }
 
 // find_candidates_three<16, conv> (abismal.cpp:1214-1259)
-__device__ uint32_t find_candidates_three(const IndexDev &ix, const uint32_t *index3, bool g_to_a, uint32_t maxc,
-                                          const uint8_t *read_start, uint32_t max_size, uint32_t &low,
-                                          uint32_t &high) {
+__device__ __noinline__ SeedRange find_candidates_three(const uint32_t *index3, bool g_to_a, uint32_t maxc,
+                                                        const uint8_t *read_start, uint32_t max_size, uint32_t low,
+                                                        uint32_t high) {
+  const IndexDev &ix = params().ix;
   uint32_t p = 16;
   uint32_t prev_low = low, prev_high = high;
   const uint32_t v1 = g_to_a ? 2u : 1u, v2 = g_to_a ? 8u : 4u;
@@ -405,7 +554,7 @@ __device__ uint32_t find_candidates_three(const IndexDev &ix, const uint32_t *in
     low = prev_low;
     high = prev_high;
   }
-  return p;
+  return SeedRange{low, high, p};
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan_add(uint32_t x, int lane) {
@@ -417,17 +566,141 @@ __device__ __forceinline__ uint32_t warp_incl_scan_add(uint32_t x, int lane) {
   return x;
 }
 
-// process_seeds (abismal.cpp:1269-1375) for the pass currently in qcode/packed
-__device__ __noinline__ void process_seeds(WarpCtx &c, uint32_t strand_code, uint32_t readlen, CandSet &res) {
-  const KernelParams &P = *c.P;
+// 32 plane bits starting at base i (bit j of the result describes base i + j)
+__device__ __forceinline__ uint32_t plane_window(const uint32_t *pl, uint32_t i) {
+  const uint32_t w = i >> 5;
+  return __funnelshift_r(pl[w], pl[w + 1], i & 31u);
+}
+
+// packed word w of the genome window starting at base the_pos: 16 bases from word g0 (low) and g1
+__device__ __forceinline__ uint64_t window_word(uint64_t g0, uint64_t g1, uint32_t off) {
+  return (g0 >> off) | ((g1 << (63u - off)) << 1);
+}
+
+// One compare chunk: kCand candidates per lane, candidate (k, lane) = canonical index c0 + 32k + lane.
+// S0 = packed words compared in the first stage (S0 + 1 genome words gathered at once per candidate).
+// full_compare (abismal.cpp:1105-1122) stops at the first word after which the running distance exceeds the
+// cutoff; a word can contribute a NEGATIVE amount (multi-bit IUPAC genome codes give popcounts > 16), so a
+// candidate is accepted iff the MAXIMUM prefix sum pm is <= the cutoff, and then d is the full sum.
+template <int KC, int S0>
+__device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
+                                              const uint64_t *packed, int n_words, int bound, uint32_t c0,
+                                              uint32_t total, uint32_t base_off, uint32_t incl, uint32_t tot,
+                                              uint32_t n2, uint32_t s2, uint32_t s3, int lane, int (&d)[KC],
+                                              int (&pm)[KC], uint32_t (&the_pos)[KC],
+                                              unsigned long long &n_entry,
+                                              unsigned long long &n_word) {
+  bool valid[KC];
+  uint32_t sub[KC];
+  // ---- owners + index gathers (KC independent loads per lane) ----
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const uint32_t cidx = c0 + 32u * k + lane;
+    valid[k] = cidx < total;
+    // owner lane = number of lanes whose inclusive sum is <= cidx
+    int o = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const uint32_t vv = __shfl_sync(FULL, incl, (o + s - 1) & 31);
+      if (vv <= cidx) o += s;
+    }
+    o &= 31;
+    const uint32_t o_incl = __shfl_sync(FULL, incl, o);
+    const uint32_t o_tot = __shfl_sync(FULL, tot, o);
+    const uint32_t o_n2 = __shfl_sync(FULL, n2, o);
+    const uint32_t o_s2 = __shfl_sync(FULL, s2, o);
+    const uint32_t o_s3 = __shfl_sync(FULL, s3, o);
+    uint32_t entry = 0;
+    if (valid[k]) {
+      const uint32_t r = cidx - (o_incl - o_tot);
+      entry = (r < o_n2) ? __ldg(ix.index + o_s2 + r) : __ldg(index3 + o_s3 + (r - o_n2));
+    }
+    the_pos[k] = entry;
+    sub[k] = base_off + (uint32_t)o;
+  }
+#pragma unroll
+  for (int k = 0; k < KC; ++k) the_pos[k] -= sub[k];
+
+  // ---- stage 0: S0 + 1 genome words per candidate, all gathers issued before any use ----
+  uint64_t g[KC][S0 + 1];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const uint64_t *gp = ix.genome + (the_pos[k] >> 4);
+#pragma unroll
+    for (int j = 0; j <= S0; ++j) g[k][j] = (valid[k] && j <= n_words) ? __ldg(gp + j) : 0ull;
+  }
+  uint64_t carry[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const uint32_t off = (the_pos[k] & 15u) << 2;
+    int dd = 0, mx = 0;
+#pragma unroll
+    for (int j = 0; j < S0; ++j)
+      if (j < n_words) {
+        dd += 16 - __popcll(packed[j] & window_word(g[k][j], g[k][j + 1], off));
+        mx = max(mx, dd);
+      }
+    d[k] = dd;
+    pm[k] = valid[k] ? mx : (1 << 30);
+    carry[k] = g[k][S0];
+    if (valid[k]) {
+      n_entry += 1;
+      n_word += (unsigned long long)min(S0, n_words);
+    }
+  }
+  // ---- later stages: two more words for every candidate still within the bound ----
+  for (int w = S0; w < n_words; w += 2) {
+    uint64_t a[KC], b[KC];
+    bool alive[KC], any = false;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      alive[k] = pm[k] <= bound;
+      any = any || alive[k];
+      const uint64_t *gp = ix.genome + (the_pos[k] >> 4) + w;
+      a[k] = alive[k] ? __ldg(gp + 1) : 0ull;
+      b[k] = (alive[k] && w + 1 < n_words) ? __ldg(gp + 2) : 0ull;
+    }
+    if (!any) break;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      if (alive[k]) {
+        const uint32_t off = (the_pos[k] & 15u) << 2;
+        int dd = d[k] + 16 - __popcll(packed[w] & window_word(carry[k], a[k], off));
+        pm[k] = max(pm[k], dd);
+        if (w + 1 < n_words) {
+          dd += 16 - __popcll(packed[w + 1] & window_word(a[k], b[k], off));
+          pm[k] = max(pm[k], dd);
+        }
+        d[k] = dd;
+        carry[k] = b[k];
+        n_word += (w + 1 < n_words) ? 2ull : 1ull;
+      }
+    }
+  }
+}
+
+// process_seeds (abismal.cpp:1269-1375) for pass `strand_code` of `end` into candidate set `set_id`
+__device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_code) {
+  const Warp W;
+  const KernelParams &P = params();
   const IndexDev &ix = P.ix;
-  const int lane = c.lane;
+  const int lane = W.lane;
+  build_qcode(end, strand_code);
+  build_packed(end, strand_code);
+  const uint32_t readlen = W.scal()->len[end];
+  const uint8_t *qcode = W.qcode(end);
+  const uint64_t *packed = W.packed();
+  const uint32_t *p2 = W.plane(0), *p3a = W.plane(1), *p3b = W.plane(2);
+  const uint32_t *T3 = tab3();
   const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
   const uint32_t *counter3 = g_to_a ? ix.counter_a : ix.counter_t;
   const uint32_t *index3 = g_to_a ? ix.index_a : ix.index_t;
   const uint32_t maxc = P.max_candidates;
   const int n_words = (int)((readlen + 15) / 16);
-  const bool count = P.counters != nullptr;
+  unsigned long long c_lookup = 0, c_entry = 0, c_word = 0;
+
+  CandSet res;
+  res.load(W, set_id);
 
   const uint32_t specific_len = min(readlen - 20u, readlen >> 1);
   const uint32_t specific_lim = max(20u, readlen >> 1);
@@ -437,7 +710,7 @@ __device__ __noinline__ void process_seeds(WarpCtx &c, uint32_t strand_code, uin
     const bool specific = phase == 0;
     if (specific) res.set_specific();
     else {
-      if (!res.should_do_sensitive()) return;
+      if (!res.should_do_sensitive()) break;
       res.set_sensitive();
     }
     const uint32_t n_off = specific ? specific_lim : lim_two;
@@ -446,24 +719,28 @@ __device__ __noinline__ void process_seeds(WarpCtx &c, uint32_t strand_code, uin
       const bool active = i < n_off;
       uint32_t s2 = 0, e2 = 0, s3 = 0, e3 = 0, n2 = 0, n3 = 0;
       if (active) {
-        // get_1bit_hash / get_base_3_hash at offset i (rolling == direct)
-        const uint8_t *r = c.qcode + i;
-        uint32_t k = 0, k3 = 0;
-#pragma unroll
-        for (int j = 0; j < 25; ++j) k = (k << 1) | get_bit(r[j]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) k3 = k3 * 3u + three_num(g_to_a, r[j]);
+        // get_1bit_hash / get_base_3_hash at offset i (rolling == direct), AbismalIndex.hpp:285-305
+        const uint32_t k = __brev(plane_window(p2, i)) >> 7;
+        const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
+        const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
         s2 = __ldg(ix.counter + k);
         e2 = __ldg(ix.counter + k + 1);
         s3 = __ldg(counter3 + k3);
         e3 = __ldg(counter3 + k3 + 1);
         if (specific) {
-          uint32_t l_two = 24, l_three = 15;
-          if (e2 - s2 > maxc || e2 == s2) l_two = find_candidates(ix, maxc, r, readlen - i, s2, e2);
-          else l_two = 25;
-          if (e3 - s3 > maxc || e3 == s3)
-            l_three = find_candidates_three(ix, index3, g_to_a, maxc, r, readlen - i, s3, e3);
-          else l_three = 16;
+          uint32_t l_two = 25, l_three = 16;
+          if (e2 - s2 > maxc || e2 == s2) {
+            const SeedRange r = find_candidates(maxc, qcode + i, readlen - i, s2, e2);
+            s2 = r.low;
+            e2 = r.high;
+            l_two = r.p;
+          }
+          if (e3 - s3 > maxc || e3 == s3) {
+            const SeedRange r = find_candidates_three(index3, g_to_a, maxc, qcode + i, readlen - i, s3, e3);
+            s3 = r.low;
+            e3 = r.high;
+            l_three = r.p;
+          }
           const uint32_t d_two = e2 - s2, d_three = e3 - s3;
           n2 = (d_two <= maxc || l_two >= specific_len) ? d_two : 0u;
           n3 = (d_three <= maxc || l_three >= specific_len) ? d_three : 0u;
@@ -473,58 +750,79 @@ __device__ __noinline__ void process_seeds(WarpCtx &c, uint32_t strand_code, uin
           n2 = (d_two != 0u && d_two <= maxc && (d_three == 0u || d_two <= 10u * d_three)) ? d_two : 0u;
           n3 = (d_three != 0u && d_three <= maxc) ? d_three : 0u;
         }
-        if (count) c.c_lookup += 2;
+        c_lookup += 2;
       }
       __syncwarp();
       const uint32_t tot = n2 + n3;
       const uint32_t incl = warp_incl_scan_add(tot, lane);
       const uint32_t total = __shfl_sync(FULL, incl, 31);
-      for (uint32_t c0 = 0; c0 < total && !res.sure_ambig; c0 += 32) {
-        const uint32_t cidx = c0 + lane;
-        const bool valid = cidx < total;
-        // owner lane = number of lanes whose inclusive sum is <= cidx
-        int o = 0;
+      for (uint32_t c0 = 0; c0 < total && !res.sure_ambig;) {
+        int d[kCand], pm[kCand];
+        uint32_t the_pos[kCand];
+        const int bound = res.cutoff;
+        // tight bound (specific phase): most candidates die within 2 words -> 4 candidates x 3 words per lane;
+        // loose bound (sensitive phase, ~6 words per candidate): 2 candidates x 5 words per lane
+        int kc;
+        if (bound >= 30) {
+          int d2[2], pm2[2];
+          uint32_t pos2[2];
+          compare_chunk<2, 4>(ix, index3, packed, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3, lane,
+                              d2, pm2, pos2, c_entry, c_word);
 #pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-          const uint32_t vv = __shfl_sync(FULL, incl, (o + s - 1) & 31);
-          if (vv <= cidx) o += s;
-        }
-        o &= 31;
-        const uint32_t o_incl = __shfl_sync(FULL, incl, o);
-        const uint32_t o_tot = __shfl_sync(FULL, tot, o);
-        const uint32_t o_n2 = __shfl_sync(FULL, n2, o);
-        const uint32_t o_s2 = __shfl_sync(FULL, s2, o);
-        const uint32_t o_s3 = __shfl_sync(FULL, s3, o);
-        int d = kMaxDiffs;
-        uint32_t the_pos = 0;
-        const int cutoff = res.cutoff;
-        if (valid) {
-          const uint32_t r = cidx - (o_incl - o_tot);
-          const uint32_t entry = (r < o_n2) ? __ldg(ix.index + o_s2 + r) : __ldg(index3 + o_s3 + (r - o_n2));
-          the_pos = entry - (base_off + (uint32_t)o);
-          int words = 0;
-          d = full_compare(ix.genome, the_pos, c.packed, n_words, cutoff, words);
-          if (count) {
-            c.c_entry += 1;
-            c.c_word += (unsigned long long)words;
+          for (int k = 0; k < kCand; ++k) {
+            d[k] = k < 2 ? d2[k & 1] : 0;
+            pm[k] = k < 2 ? pm2[k & 1] : (1 << 30);
+            the_pos[k] = k < 2 ? pos2[k & 1] : 0u;
           }
+          kc = 2;
         }
+        else {
+          compare_chunk<kCand, 2>(ix, index3, packed, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3,
+                                  lane, d, pm, the_pos, c_entry, c_word);
+          kc = kCand;
+        }
+        c0 += 32u * kc;
         __syncwarp();
-        unsigned mask = __ballot_sync(FULL, valid && d <= cutoff);
-        while (mask != 0u && !res.sure_ambig) {
-          const int l = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int dd = __shfl_sync(FULL, d, l);
-          const uint32_t pp = __shfl_sync(FULL, the_pos, l);
-          if (dd <= res.cutoff) res.update(true, dd, strand_code, pp);
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) {
+          if (k >= kc) break;
+          unsigned mask = __ballot_sync(FULL, pm[k] <= bound);
+          while (mask != 0u && !res.sure_ambig) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int dd = __shfl_sync(FULL, d[k], l);
+            const int mm = __shfl_sync(FULL, pm[k], l);
+            const uint32_t pp = __shfl_sync(FULL, the_pos[k], l);
+            if (mm <= res.cutoff) res.update(true, dd, strand_code, pp);  // check_hits<.., true> in both phases
+          }
         }
       }
     }
   }
+  res.store(W, set_id);
+  if (P.counters != nullptr) {
+    unsigned long long *cnt = W.scal()->cnt;
+    for (int d = 16; d >= 1; d >>= 1) {
+      c_lookup += __shfl_xor_sync(FULL, c_lookup, d);
+      c_entry += __shfl_xor_sync(FULL, c_entry, d);
+      c_word += __shfl_xor_sync(FULL, c_word, d);
+    }
+    if (lane == 0) {
+      cnt[0] += c_lookup;
+      cnt[1] += c_entry;
+      cnt[2] += c_word;
+    }
+    __syncwarp();
+  }
 }
 
 // ---- sort by (pos, flags) + unique: prepare_for_alignments / prepare_for_mating ----
-__device__ __noinline__ void sort_unique(const HeapRef &v, int &sz, int lane) {
+__device__ __noinline__ void sort_unique(int set_id) {
+  const Warp W;
+  const int lane = W.lane;
+  const HeapRef v = heap_of(W, set_id);
+  CandState *st = W.cs(set_id);
+  const int sz = st->sz;
   int n2 = 1;
   while (n2 < sz) n2 <<= 1;
   if (n2 < 2) return;
@@ -566,106 +864,128 @@ __device__ __noinline__ void sort_unique(const HeapRef &v, int &sz, int lane) {
     out += __popc(m);
     __syncwarp();
   }
-  sz = out;
+  if (lane == 0) st->sz = out;
+  __syncwarp();
 }
 
 // ---- banded alignment --------------------------------------------------------------
-struct AlnOut {
-  int score, row, col, bw;
-};
-
 __device__ __forceinline__ int band_width(int diffs, int max_diffs) {  // AbismalAlign.hpp:333-334
   const int want = 2 * min(diffs, max_diffs) + 1;
   return want < 0 ? 61 : min(61, want);
 }
 
-// AbismalAlign::align<do_traceback> (AbismalAlign.hpp:320-386); diffs != 0.
-// CPL = band columns per lane.  Query = c.qcode (length q_sz).
-template <int CPL>
-__device__ void align_rows(WarpCtx &c, bool do_tb, int bw, int q_sz, uint32_t t_pos, AlnOut &out) {
-  const int lane = c.lane;
+// AbismalAlign::align<do_traceback> (AbismalAlign.hpp:320-386) for diffs != 0, as a wavefront.
+// Lane l owns band columns 2l (value A) and 2l+1 (value B); at iteration T it is on table row
+// i = T - l (reference base t_beg + i - 1).  Dependencies of cell (i, j):
+//   diag  (i-1, j)   own value of the previous iteration
+//   above (i-1, j+1) A: own B of the previous iteration; B: lane l+1's A of THIS iteration (its row is i-1)
+//   left  (i, j-1)   A: lane l-1's B of the previous iteration (its row was i); B: own A of this iteration
+// Arrow precedence on ties is left (I) > above (D) > diag (M), the reference's write order; the result is
+// the first maximum in row-major order (std::max_element).
+__device__ __noinline__ void align_wave(bool do_tb, int tb_slot, int end, int bw, int q_sz, uint32_t t_pos,
+                                        AlnOut *out) {
+  const Warp W;
+  const KernelParams &P = params();
+  const int lane = W.lane;
+  const uint8_t *q = W.qcode(end);
+  uint8_t *refb = W.refb();
   const uint32_t t_beg = t_pos - (uint32_t)((bw - 1) / 2);
   const int t_shift = q_sz + bw;
-  const uint32_t w0 = t_beg >> 4;
-  const int nw = (int)(((t_beg + (uint32_t)t_shift - 2u) >> 4) - w0) + 1;
-  __syncwarp();
-  for (int k = lane; k < nw; k += 32) c.refw[k] = __ldg(c.P->ix.genome + w0 + k);
-  if (do_tb && lane < 4) c.tb[lane] = 0xffffffffu;  // row 0: every cell is "stop"
-  __syncwarp();
-
-  int prev[CPL];
+  // stage the reference bases of rows 1 .. t_shift-1 as bytes: refb[i - 1] = genome base t_beg + i - 1
+  {
+    const uint32_t w0 = t_beg >> 4;
+    const int n_ref = t_shift - 1;
+    const int nw = (int)(((t_beg + (uint32_t)n_ref - 1u) >> 4) - w0) + 1;
+    const int shift0 = (int)(t_beg & 15u);
+    __syncwarp();
+    for (int k = lane; k < nw; k += 32) {
+      const uint64_t word = __ldg(P.ix.genome + w0 + k);
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) prev[k] = 0;
+      for (int n = 0; n < 16; ++n) {
+        const int r = 16 * k + n - shift0;
+        if (r >= 0 && r < n_ref) refb[r] = (uint8_t)((word >> (4 * n)) & 15u);
+      }
+    }
+    __syncwarp();
+  }
+  const int nl = (bw + 1) >> 1;  // lanes in use
+  const int n_iter = (t_shift - 1) + (nl - 1);
+  const int jA = 2 * lane, jB = 2 * lane + 1;
+  uint64_t *tbs = W.tb_sm(tb_slot) + lane;           // [word][kTbLanesSm]
+  uint64_t *tbg = W.tb_gm(tb_slot) + lane;           // [word][32]
+  int A = 0, B = 0;
   int best = 0, best_row = 0, best_col = 0;
-  const uint8_t *q = c.qcode;
-
-  for (int i = 1; i < t_shift; ++i) {
-    const int left = i < bw ? bw - i : 0;
-    const int right = min(bw, t_shift - i);
-    const uint32_t gp = t_beg + (uint32_t)i - 1u;
-    const uint32_t ref = (uint32_t)(c.refw[(gp >> 4) - w0] >> ((gp & 15u) << 2)) & 15u;
-    // prev[j + 1] of the last column of this lane lives in the next lane
-    const int nxt_lane_first = __shfl_down_sync(FULL, prev[0], 1);
-    int val[CPL], arrow[CPL], u[CPL];
-    bool in[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      const int j = lane * CPL + k;
-      in[k] = j >= left && j < right;
-      int v = 0, a = 3;
-      if (in[k]) {
-        const uint32_t qb = q[i + j - bw];
-        const int diag = prev[k] + ((qb & ref) ? 2 : -3);
-        v = max(0, diag);
-        a = (v == diag) ? 0 : 3;
-        if (j + 1 < right) {
-          const int above = ((k + 1 < CPL) ? prev[(k + 1) % CPL] : nxt_lane_first) - 4;
-          v = max(v, above);
-          if (v == above) a = 2;
+  uint64_t tbw = 0;
+  for (int T = 1; T <= n_iter; ++T) {
+    const int i = T - lane;
+    const bool row_ok = i >= 1 && i < t_shift;
+    const int left_lim = max(0, bw - i);
+    const int right_lim = min(bw, t_shift - i);
+    const uint32_t ref = row_ok ? refb[i - 1] : 0u;
+    const int b_up = __shfl_up_sync(FULL, B, 1);
+    int newA = 0, codeA = 3;
+    if (row_ok && jA >= left_lim && jA < right_lim) {
+      const uint32_t qb = q[i + jA - bw];
+      const int diag = A + ((qb & ref) ? 2 : -3);
+      int v = max(0, diag);
+      int a = (v == diag) ? 0 : 3;
+      if (jA + 1 < right_lim) {
+        const int above = B - 4;
+        v = max(v, above);
+        if (v == above) a = 2;
+      }
+      if (lane > 0) {
+        const int left = b_up - 4;
+        if (left >= v) {
+          v = left;
+          a = 1;
         }
       }
-      val[k] = v;
-      arrow[k] = a;
-      u[k] = in[k] ? v + 4 * j : kNegInf;
-    }
-    // from_left: cur[j] = max(val[j], cur[j-1] - 4)  ==  prefix-max of (val[j] + 4j) - 4j
-    int lane_max = u[0];
-#pragma unroll
-    for (int k = 1; k < CPL; ++k) lane_max = max(lane_max, u[k]);
-    int incl = lane_max;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int y = __shfl_up_sync(FULL, incl, d);
-      if (lane >= d) incl = max(incl, y);
-    }
-    int run = __shfl_up_sync(FULL, incl, 1);  // prefix max over all earlier columns
-    if (lane == 0) run = kNegInf;
-    unsigned code_bits = 0;
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      const int j = lane * CPL + k;
-      int cur = 0, code = 3;
-      if (in[k]) {
-        const int U = max(run, u[k]);
-        cur = U - 4 * j;
-        int a = arrow[k];
-        if (u[k] <= run) a = 1;  // cur[j] == cur[j-1] - 4  => I (precedence I > D > M)
-        code = cur > 0 ? a : 3;
-        if (cur > best) {
-          best = cur;
-          best_row = i;
-          best_col = j;
-        }
-        run = U;
+      codeA = v > 0 ? a : 3;
+      if (v > best) {
+        best = v;
+        best_row = i;
+        best_col = jA;
       }
-      prev[k] = cur;
-      code_bits |= (unsigned)code << (2 * k);
+      newA = v;
     }
+    const int a_down = __shfl_down_sync(FULL, newA, 1);
+    int newB = 0, codeB = 3;
+    if (row_ok && jB >= left_lim && jB < right_lim) {
+      const uint32_t qb = q[i + jB - bw];
+      const int diag = B + ((qb & ref) ? 2 : -3);
+      int v = max(0, diag);
+      int a = (v == diag) ? 0 : 3;
+      if (jB + 1 < right_lim) {
+        const int above = a_down - 4;
+        v = max(v, above);
+        if (v == above) a = 2;
+      }
+      {
+        const int left = newA - 4;
+        if (left >= v) {
+          v = left;
+          a = 1;
+        }
+      }
+      codeB = v > 0 ? a : 3;
+      if (v > best) {
+        best = v;
+        best_row = i;
+        best_col = jB;
+      }
+      newB = v;
+    }
+    A = newA;
+    B = newB;
     if (do_tb) {
-#pragma unroll
-      for (int pl = 0; pl < 2 * CPL; ++pl) {
-        const unsigned m = __ballot_sync(FULL, (code_bits >> pl) & 1u);
-        if (lane == pl) c.tb[(size_t)i * 4 + pl] = m;
+      tbw |= (uint64_t)(uint32_t)(codeA | (codeB << 2)) << (4 * (T & 15));
+      if ((T & 15) == 15 || T == n_iter) {
+        if (lane < nl) {
+          if (lane < kTbLanesSm) tbs[(T >> 4) * kTbLanesSm] = tbw;
+          else tbg[(size_t)(T >> 4) * 32] = tbw;
+        }
+        tbw = 0;
       }
     }
   }
@@ -683,24 +1003,50 @@ __device__ void align_rows(WarpCtx &c, bool do_tb, int bw, int q_sz, uint32_t t_
       bc = oc;
     }
   }
-  out.score = bv;
-  out.row = br;
-  out.col = bc;
-  out.bw = bw;
+  out->score = bv;
+  out->row = br;
+  out->col = bc;
+  out->bw = bw;
   __syncwarp();
 }
 
-// returns the alignment score; out is meaningful only when diffs != 0
-__device__ __noinline__ int align(WarpCtx &c, bool do_tb, int diffs, int max_diffs, int q_sz, uint32_t t_pos,
-                                  AlnOut &out) {
+// Returns the alignment score of qcode[end] (encoded for `flags`) against the genome at t_pos.
+// record_tb: also keep the traceback words in `tb_slot` (so that a later traceback of the very
+// same alignment can skip the DP); need_tb: the caller will read the traceback right away.
+// `out` is meaningful only when diffs != 0.
+__device__ __forceinline__ int align(bool record_tb, bool need_tb, int tb_slot, int end, uint32_t flags, int diffs,
+                                     int max_diffs, int q_sz, uint32_t t_pos, AlnOut &out) {
   if (diffs == 0) return 2 * q_sz;  // AbismalAlign.hpp:329-330
+  const Warp W;
   const int bw = band_width(diffs, max_diffs);
-  if (c.P->counters != nullptr && c.lane == 0) {
-    c.c_align += 1;
-    c.c_dpref += (unsigned long long)(q_sz + bw);
+  TbKey *tk = &W.scal()->tbk[tb_slot];
+  const uint32_t key = ((uint32_t)end << 16) | (flags & (ABG_FLAG_RC | ABG_FLAG_A_RICH));
+  if (tk->valid && tk->pos == t_pos && tk->key == key && tk->bw == bw) {
+    out.score = tk->score;
+    out.row = tk->row;
+    out.col = tk->col;
+    out.bw = bw;
+    return out.score;
   }
-  if (bw <= 32) align_rows<1>(c, do_tb, bw, q_sz, t_pos, out);
-  else align_rows<2>(c, do_tb, bw, q_sz, t_pos, out);
+  build_qcode(end, flags);
+  const bool tb = record_tb || need_tb;
+  if (params().counters != nullptr && W.lane == 0) {
+    W.scal()->cnt[3] += 1;
+    W.scal()->cnt[4] += (unsigned long long)(q_sz + bw);
+  }
+  __syncwarp();
+  if (tb && W.lane == 0) tk->valid = 0;
+  align_wave(tb, tb_slot, end, bw, q_sz, t_pos, &out);
+  if (tb && W.lane == 0) {
+    tk->pos = t_pos;
+    tk->key = key;
+    tk->score = out.score;
+    tk->row = out.row;
+    tk->col = out.col;
+    tk->bw = bw;
+    tk->valid = 1;
+  }
+  __syncwarp();
   return out.score;
 }
 
@@ -720,28 +1066,38 @@ __device__ __forceinline__ void cigar_default(CigarOut &cg, uint32_t len, int la
 
 // build_cigar_len_and_pos + get_traceback (AbismalAlign.hpp:388-440, :166-193)
 // followed by simple_aln::edit_distance (:73-89).  Uniform across the warp.
-__device__ __noinline__ int build_cigar(WarpCtx &c, int diffs, const AlnOut &a, int q_sz, int scr_for_nm,
-                                        CigarOut &cg, uint32_t &len, uint32_t &t_pos) {
-  const int lane = c.lane;
+__device__ __noinline__ int build_cigar(int tb_slot, int diffs, int a_score, int a_row, int a_col, int bw, int q_sz,
+                                        int scr_for_nm, uint32_t *ops, uint32_t stride, uint32_t *n_out,
+                                        uint32_t *ref_len_out, uint32_t *len_out, uint32_t *t_pos_io) {
+  const Warp W;
+  const int lane = W.lane;
   int ins = 0, del = 0;
-  if (diffs == 0 || a.score == 0) {
-    cigar_default(cg, (uint32_t)q_sz, lane);
+  uint32_t len;
+  if (diffs == 0 || a_score == 0) {
+    if (lane == 0 && stride > 0) ops[0] = (uint32_t)q_sz << 4;
+    *n_out = 1;
+    *ref_len_out = (uint32_t)q_sz;
     len = (uint32_t)q_sz;
+    __syncwarp();
   }
   else {
-    const int bw = a.bw;
-    const int cpl = bw <= 32 ? 1 : 2;
-    int row = a.row, col = a.col;
+    const uint64_t *tbs = W.tb_sm(tb_slot);
+    const uint64_t *tbg = W.tb_gm(tb_slot);
+    int row = a_row, col = a_col;
     const int clip_bottom = (q_sz + (bw - 1)) - (row + col);
+    __syncwarp();
+    // traceback word holding cell (r, cc): lane l = cc / 2, iteration T = r + l
+    const auto word_at = [&](int T, int l) -> uint64_t {
+      return l < kTbLanesSm ? tbs[(T >> 4) * kTbLanesSm + l] : *(volatile const uint64_t *)(tbg + (size_t)(T >> 4) * 32 + l);
+    };
     const auto code_at = [&](int r, int cc) -> int {
       if (cc < 0 || cc >= bw || r <= 0) return 3;
-      const int ln = cc / cpl, k = cc % cpl;
-      const uint32_t p0 = c.tb[(size_t)r * 4 + 2 * k], p1 = c.tb[(size_t)r * 4 + 2 * k + 1];
-      return (int)((p0 >> ln) & 1u) | ((int)((p1 >> ln) & 1u) << 1);
+      const int l = cc >> 1, T = r + l;
+      return (int)(word_at(T, l) >> (4 * (T & 15) + 2 * (cc & 1))) & 3;
     };
     uint32_t n_ops = 0, ref_len = 0;
     const auto emit = [&](uint32_t n, int op) {
-      if (n_ops < cg.stride && lane == 0) cg.ops[n_ops] = (n << 4) | (uint32_t)op;
+      if (n_ops < stride && lane == 0) ops[n_ops] = (n << 4) | (uint32_t)op;
       ++n_ops;
       if (op == 1) ins += (int)(n & 0xffu);  // abismal_bam_cigar_oplen returns uint8_t
       if (op == 2) del += (int)(n & 0xffu);
@@ -757,47 +1113,68 @@ __device__ __noinline__ int build_cigar(WarpCtx &c, int diffs, const AlnOut &a, 
     }
     uint32_t n = 1;
     for (;;) {
-      const int arrow = code_at(row, col);
+      if (col < 0 || col >= bw || row <= 0) break;
+      const int l = col >> 1, T = row + l;
+      const uint64_t word = word_at(T, l);
+      const int pos = T & 15;
+      const int arrow = (int)(word >> (4 * pos + 2 * (col & 1))) & 3;
       if (arrow == 3) break;  // table[row][col] <= 0
-      const bool is_del = arrow == 2, is_ins = arrow == 1;
-      row -= !is_ins;
-      col -= is_ins;
-      col += is_del;
-      if (arrow != prev_arrow) {
-        emit(n, prev_arrow);
-        n = 0;
+      if (arrow == 0) {
+        // a run of diagonal arrows stays in this lane's column: count them inside the word
+        // (codes of this column for iterations pos, pos-1, ..., 0, most recent first)
+        const uint64_t m = ((word >> (2 * (col & 1))) & 0x3333333333333333ull) << (4 * (15 - pos));
+        int run = m == 0 ? pos + 1 : (__clzll((long long)m) >> 2);  // leading zero codes
+        if (run > row) run = row;
+        if (prev_arrow != 0) {
+          emit(n, prev_arrow);
+          n = 0;
+        }
+        n += (uint32_t)run;
+        row -= run;
+        prev_arrow = 0;
       }
-      ++n;
-      prev_arrow = arrow;
+      else {
+        const bool is_del = arrow == 2, is_ins = arrow == 1;
+        row -= !is_ins;
+        col -= is_ins;
+        col += is_del;
+        if (arrow != prev_arrow) {
+          emit(n, prev_arrow);
+          n = 0;
+        }
+        ++n;
+        prev_arrow = arrow;
+      }
     }
     emit(n, prev_arrow);
     const int clip_top = (row + col) - (bw - 1);
     if (clip_top > 0) {
-      if (n_ops < cg.stride && lane == 0) cg.ops[n_ops] = ((uint32_t)clip_top << 4) | 4u;
+      if (n_ops < stride && lane == 0) ops[n_ops] = ((uint32_t)clip_top << 4) | 4u;
       ++n_ops;
     }
     __syncwarp();
     // reverse in place
-    const uint32_t m = min(n_ops, cg.stride);
-    if (n_ops <= cg.stride) {
+    const uint32_t m = min(n_ops, stride);
+    if (n_ops <= stride) {
       for (uint32_t k = lane; k < m / 2; k += 32) {
-        const uint32_t x = cg.ops[k], y = cg.ops[m - 1 - k];
-        cg.ops[k] = y;
-        cg.ops[m - 1 - k] = x;
+        const uint32_t x = ops[k], y = ops[m - 1 - k];
+        ops[k] = y;
+        ops[m - 1 - k] = x;
       }
     }
     __syncwarp();
     if (clip_bottom > 0) {
-      if (n_ops < cg.stride && lane == 0) cg.ops[n_ops] = ((uint32_t)clip_bottom << 4) | 4u;
+      if (n_ops < stride && lane == 0) ops[n_ops] = ((uint32_t)clip_bottom << 4) | 4u;
       ++n_ops;
     }
     __syncwarp();
-    cg.n = n_ops;
-    cg.ref_len = ref_len;
+    *n_out = n_ops;
+    *ref_len_out = ref_len;
     len = (uint32_t)(q_sz - clip_bottom - clip_top);
-    const uint32_t t_beg = t_pos - (uint32_t)((bw - 1) / 2);
-    t_pos = t_beg + (uint32_t)row;
+    const uint32_t t_beg = *t_pos_io - (uint32_t)((bw - 1) / 2);
+    *t_pos_io = t_beg + (uint32_t)row;
   }
+  *len_out = len;
   // edit_distance(scr, len, cigar): same promotions as the reference (unsigned quotient)
   if (scr_for_nm == 0) return (int)(int16_t)len;
   const int A = (int)(int16_t)(scr_for_nm + 4 * (ins + del));
@@ -806,34 +1183,56 @@ __device__ __noinline__ int build_cigar(WarpCtx &c, int diffs, const AlnOut &a, 
   return (int)(int16_t)(mism + ins + del);
 }
 
+__device__ __forceinline__ int build_cigar(int tb_slot, int diffs, const AlnOut &a, int q_sz, int scr_for_nm,
+                                           CigarOut &cg, uint32_t &len, uint32_t &t_pos) {
+  uint32_t n = 0, ref_len = 0, l = 0, p = t_pos;
+  const int nm = build_cigar(tb_slot, diffs, a.score, a.row, a.col, a.bw, q_sz, scr_for_nm, cg.ops, cg.stride, &n,
+                             &ref_len, &l, &p);
+  cg.n = n;
+  cg.ref_len = ref_len;
+  len = l;
+  t_pos = p;
+  return nm;
+}
+
 __device__ __forceinline__ bool same_pos(uint32_t a, uint32_t b) { return (a > b ? a - b : b - a) <= 3u; }
 
-// align_se_candidates (abismal.cpp:1435-1497)
-__device__ __noinline__ void align_se_candidates(WarpCtx &c, int end, uint32_t readlen_u, double cutoff,
-                                                 CandSet &res, Hit &best, CigarOut &cg) {
+// align_se_candidates (abismal.cpp:1435-1497) on se set `end`
+__device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uint32_t *ops, uint32_t stride,
+                                                     uint32_t *cg_n, uint32_t *cg_ref_len, uint64_t best_in) {
+  const Warp W;
+  const uint32_t readlen_u = W.scal()->len[end];
   const int readlen = (int)(int16_t)readlen_u;
   const int max_diffs = frac_of(cutoff, (uint32_t)readlen);
   const int max_scr = (int)(int16_t)(2 * readlen);
-  if (!res.best.empty()) {
-    best = res.best;
-    cigar_default(cg, (uint32_t)readlen, c.lane);
-    return;
+  Hit best(best_in);
+  CandState *st = W.cs(end);
+  if (!Hit(st->best).empty()) {
+    best = Hit(st->best);
+    if (W.lane == 0 && stride > 0) ops[0] = (uint32_t)readlen << 4;  // make_default_cigar
+    *cg_n = 1;
+    *cg_ref_len = (uint32_t)readlen;
+    __syncwarp();
+    return best.w;
   }
   int best_scr = 0;
   uint32_t best_pos = 0;
-  sort_unique(res.v, res.sz, c.lane);
+  sort_unique(end);
+  const HeapRef v = heap_of(W, end);
   int it = 0;
-  const int lim = res.sz;
-  for (; it != lim && res.v.get(it).empty(); ++it) {
+  const int lim = st->sz;
+  for (; it != lim && v.get(it).empty(); ++it) {
   }
+  const bool record_tb = (lim - it) <= kTbCacheMaxCands;
   const int invalid = frac_of(0.4, (uint32_t)readlen);
+  const int q_sz = (int)readlen_u;
   AlnOut ao;
   for (; it != lim; ++it) {
-    const Hit h = res.v.get(it);
+    const Hit h = v.get(it);
     if (h.diffs() < invalid) {
-      build_pass(c, end, h.flags());
       const uint32_t cand_pos = h.pos();
-      const int cand_scr = (int)(int16_t)align(c, false, h.diffs(), max_diffs, (int)c.len[end], cand_pos, ao);
+      const int cand_scr =
+        (int)(int16_t)align(record_tb, false, 0, end, h.flags(), h.diffs(), max_diffs, q_sz, cand_pos, ao);
       if (cand_scr > best_scr) {
         best = h;
         best_scr = cand_scr;
@@ -844,16 +1243,19 @@ __device__ __noinline__ void align_se_candidates(WarpCtx &c, int end, uint32_t r
     }
   }
   if (best.pos() != 0) {
-    build_pass(c, end, best.flags());
     ao.score = 0;
-    align(c, true, best.diffs(), max_diffs, (int)c.len[end], best.pos(), ao);
+    align(false, true, 0, end, best.flags(), best.diffs(), max_diffs, q_sz, best.pos(), ao);
     uint32_t len = 0, pos = best.pos();
-    const int nm = build_cigar(c, best.diffs(), ao, (int)c.len[end], best_scr, cg, len, pos);
+    CigarOut cg{ops, stride, 0u, 0u};
+    const int nm = build_cigar(0, best.diffs(), ao, q_sz, best_scr, cg, len, pos);
+    *cg_n = cg.n;
+    *cg_ref_len = cg.ref_len;
     best.set_pos(pos);
     best.set_diffs(nm);
     if (!(valid_len(len, (uint32_t)readlen) && nm <= frac_of(cutoff, (uint32_t)readlen))) best.reset();
   }
   else best.reset();
+  return best.w;
 }
 
 // pe_element (abismal.cpp:547-622)
@@ -888,18 +1290,22 @@ struct PeBest {
   __device__ int diffs() const { return (int)(int16_t)(r1.diffs() + r2.diffs()); }
 };
 
-// best_pair<swap_ends> (abismal.cpp:1722-1831).  e1/e2 = which end of the pair
-// plays "1" (un-reversed) / "2" (reversed) in this map_fragments call.
-__device__ __noinline__ void best_pair(WarpCtx &c, bool swap_ends, int e1, uint32_t flags1, int e2, uint32_t flags2,
-                                       const CandSet &res1, const CandSet &res2, CigarOut &cg1, CigarOut &cg2,
-                                       PeBest &best) {
-  const KernelParams &P = *c.P;
-  const int j1_end = res1.sz, j2_end = res2.sz;
+// best_pair<swap_ends> (abismal.cpp:1722-1831) over pe sets 2 (end e1, un-reversed) and 3 (end e2, reversed).
+// The traceback slot of an end is its end number.
+__device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, uint32_t flags2, CigarOut *cgs,
+                                       PeBest *best_io) {
+  const Warp W;
+  const KernelParams &P = params();
+  const int e2 = 1 - e1;
+  PeBest best = *best_io;
+  const HeapRef v1 = heap_of(W, 2), v2 = heap_of(W, 3);
+  const int j1_end = W.cs(2)->sz, j2_end = W.cs(3)->sz;
+  int16_t *mem_scr = P.mem_scr + W.slot() * (size_t)kPeLarge;
   int j1 = 0, j2 = 0;
   __syncwarp();
-  for (int k = c.lane; k < res1.sz; k += 32) c.mem_scr[k] = 0;
+  for (int k = W.lane; k < j1_end; k += 32) mem_scr[k] = 0;
   __syncwarp();
-  const uint32_t readlen1 = c.len[e1], readlen2 = c.len[e2];
+  const uint32_t readlen1 = W.scal()->len[e1], readlen2 = W.scal()->len[e2];
   const int max_diffs1 = frac_of(P.valid_frac, readlen1);
   const int max_diffs2 = frac_of(P.valid_frac, readlen2);
   const uint32_t min_dist = P.min_dist, max_dist = P.max_dist;
@@ -907,32 +1313,30 @@ __device__ __noinline__ void best_pair(WarpCtx &c, bool swap_ends, int e1, uint3
   uint32_t best_pos1 = 0, best_pos2 = 0;
   AlnOut ao;
 
-  for (; j1 != j1_end && res1.v.get(j1).empty(); ++j1) {
+  for (; j1 != j1_end && v1.get(j1).empty(); ++j1) {
   }
-  for (; j2 != j2_end && res2.v.get(j2).empty(); ++j2) {
+  for (; j2 != j2_end && v2.get(j2).empty(); ++j2) {
   }
+  const bool rec1 = (j1_end - j1) <= kTbCacheMaxCands, rec2 = (j2_end - j2) <= kTbCacheMaxCands;
   for (; j2 != j2_end && !best.sure_ambig(); ++j2) {
-    const Hit s2 = res2.v.get(j2);
+    const Hit s2 = v2.get(j2);
     int scr2 = 0;
     const uint32_t lim = s2.pos() + readlen2;
-    for (; (j1 == j1_end) || (j1 != 0 && res1.v.get(j1).pos() + max_dist >= lim); --j1) {
+    for (; (j1 == j1_end) || (j1 != 0 && v1.get(j1).pos() + max_dist >= lim); --j1) {
     }
-    for (; j1 != j1_end && res1.v.get(j1).pos() + max_dist < lim; ++j1) {
+    for (; j1 != j1_end && v1.get(j1).pos() + max_dist < lim; ++j1) {
     }
     for (; j1 != j1_end && !best.sure_ambig(); ++j1) {
-      const Hit s1 = res1.v.get(j1);
+      const Hit s1 = v1.get(j1);
       if (!(s1.pos() + min_dist <= lim)) break;
-      if (scr2 == 0) {
-        build_pass(c, e2, flags2);
-        scr2 = (int)(int16_t)align(c, false, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), ao);
-      }
-      int m1 = c.mem_scr[j1];
+      if (scr2 == 0)
+        scr2 = (int)(int16_t)align(rec2, false, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), ao);
+      int m1 = *(volatile int16_t *)(mem_scr + j1);
       if (m1 == 0) {
-        build_pass(c, e1, flags1);
-        scr1 = (int)(int16_t)align(c, false, s1.diffs(), max_diffs1, (int)readlen1, s1.pos(), ao);
+        scr1 = (int)(int16_t)align(rec1, false, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, s1.pos(), ao);
         m1 = scr1;
         __syncwarp();
-        if (c.lane == 0) c.mem_scr[j1] = (int16_t)scr1;
+        if (W.lane == 0) mem_scr[j1] = (int16_t)scr1;
         __syncwarp();
       }
       const int pair_scr = (int)(int16_t)(scr2 + m1);
@@ -948,16 +1352,14 @@ __device__ __noinline__ void best_pair(WarpCtx &c, bool swap_ends, int e1, uint3
     Hit s1 = swap_ends ? best.r2 : best.r1;
     Hit s2 = swap_ends ? best.r1 : best.r2;
     uint32_t len1 = 0, len2 = 0;
-    build_pass(c, e1, flags1);
     ao.score = 0;
-    align(c, true, s1.diffs(), max_diffs1, (int)readlen1, best_pos1, ao);
-    int nm = build_cigar(c, s1.diffs(), ao, (int)readlen1, best_scr1, cg1, len1, best_pos1);
+    align(false, true, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, best_pos1, ao);
+    int nm = build_cigar(e1, s1.diffs(), ao, (int)readlen1, best_scr1, cgs[e1], len1, best_pos1);
     s1.set_pos(best_pos1);
     s1.set_diffs(nm);
-    build_pass(c, e2, flags2);
     ao.score = 0;
-    align(c, true, s2.diffs(), max_diffs2, (int)readlen2, best_pos2, ao);
-    nm = build_cigar(c, s2.diffs(), ao, (int)readlen2, best_scr2, cg2, len2, best_pos2);
+    align(false, true, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, best_pos2, ao);
+    nm = build_cigar(e2, s2.diffs(), ao, (int)readlen2, best_scr2, cgs[e2], len2, best_pos2);
     s2.set_pos(best_pos2);
     s2.set_diffs(nm);
     const uint32_t frag_end = best_pos2 + len2;
@@ -967,14 +1369,21 @@ __device__ __noinline__ void best_pair(WarpCtx &c, bool swap_ends, int e1, uint3
     }
     else best.reset();
   }
+  *best_io = best;
 }
 
-// best_single (abismal.cpp:1715-1720)
-__device__ void best_single(const CandSet &pres, CandSet &res) {
-  for (int i = 0; i != pres.sz && !res.sure_ambig; ++i) {
-    const Hit h = pres.v.get(i);
+// best_single (abismal.cpp:1715-1720): feed every PE candidate of set `pe_id` into SE set `se_id`
+__device__ __noinline__ void best_single(int pe_id, int se_id) {
+  const Warp W;
+  const HeapRef pv = heap_of(W, pe_id);
+  const int n = W.cs(pe_id)->sz;
+  CandSet res;
+  res.load(W, se_id);
+  for (int i = 0; i != n && !res.sure_ambig; ++i) {
+    const Hit h = pv.get(i);
     res.update(false, h.diffs(), h.flags(), h.pos());
   }
+  res.store(W, se_id);
 }
 
 __device__ __forceinline__ abg_hit to_abg(Hit h) {
@@ -985,64 +1394,54 @@ __device__ __forceinline__ abg_hit to_abg(Hit h) {
   return r;
 }
 
-__device__ __forceinline__ size_t smem_per_warp(uint32_t ml, bool paired) {
-  size_t b = 0;
-  b += 2 * (size_t)ml;                                        // base[2]
-  b += (size_t)ml + 32;                                       // qcode
-  b += (size_t)ml / 2;                                        // packed
-  b += ((size_t)(ml + 64) / 16 + 2) * 8;                      // refw
-  b += (size_t)2 * kSeSlots * 8;                              // two SE sets
-  if (paired) b += (size_t)2 * kPeSmemSlots * 8;              // two PE heaps (head)
-  return (b + 15) & ~(size_t)15;
+__device__ __forceinline__ void reset_set(const Warp &W, int id, int kind, uint32_t readlen) {
+  CandSet s;
+  s.v = heap_of(W, id);
+  s.capacity = kSeMax;
+  s.good_cutoff = 0;
+  if (kind == 0) s.reset_se(readlen);
+  else if (kind == 1) s.reset_pe(readlen);
+  else {
+    s.load(W, id);
+    s.reset_se_noarg();
+  }
+  s.store(W, id);
 }
 
-__global__ void __launch_bounds__(kThreadsPerBlock) map_reads_kernel(const KernelParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+// MINB = resident CTAs per SM the register allocation is bounded for (2: <=128 regs, 3: <=80, 4: <=64)
+template <int MINB>
+__global__ void __launch_bounds__(kThreadsPerBlock, MINB) map_reads_kernel(const __grid_constant__ KernelParams Pin) {
+  // kernel parameters + base-3 hash tables to shared memory (every device function reads them there)
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&Pin);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(smem_raw);
+    for (uint32_t k = threadIdx.x; k < sizeof(KernelParams) / 4; k += blockDim.x) dst[k] = src[k];
+    uint32_t *T3 = reinterpret_cast<uint32_t *>(smem_raw + kParamBytes);
+    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
+      // bit j of x0/x1 is base j of the 16-base window; digit weight of base j is 3^(15-j)
+      uint32_t lo = 0, hi = 0, w = 1;
+      for (int j = 7; j >= 0; --j) {  // hi table: bases 8..15 (bit j -> base 8+j, weight 3^(7-j))
+        if (b & (1u << j)) hi += w;
+        w *= 3u;
+      }
+      for (int j = 7; j >= 0; --j) {  // lo table: bases 0..7 (weight 3^(15-j)), w continues at 3^8
+        if (b & (1u << j)) lo += w;
+        w *= 3u;
+      }
+      T3[b] = lo;
+      T3[256 + b] = hi;
+    }
+  }
+  __syncthreads();
+  const KernelParams &P = params();
+  const Warp W;
+  const int lane = W.lane;
   const bool paired = P.mode & ABG_MODE_PAIRED;
   const bool a_rich = P.mode & ABG_MODE_A_RICH;
   const bool rpbat = P.mode & ABG_MODE_RANDOM_PBAT;
-  const size_t per_warp = smem_per_warp(P.ml, paired);
-  unsigned char *sp = smem_raw + per_warp * warp;
-  const size_t slot = (size_t)blockIdx.x * kWarpsPerBlock + warp;
-
-  WarpCtx c;
-  c.P = &P;
-  c.lane = lane;
-  // 8-byte aligned arrays first
-  c.packed = reinterpret_cast<uint64_t *>(sp);
-  sp += (size_t)P.ml / 2;
-  c.refw = reinterpret_cast<uint64_t *>(sp);
-  sp += ((size_t)(P.ml + 64) / 16 + 2) * 8;
-  uint64_t *se_sm0 = reinterpret_cast<uint64_t *>(sp);
-  sp += (size_t)kSeSlots * 8;
-  uint64_t *se_sm1 = reinterpret_cast<uint64_t *>(sp);
-  sp += (size_t)kSeSlots * 8;
-  uint64_t *pe_sm0 = nullptr, *pe_sm1 = nullptr;
-  if (paired) {
-    pe_sm0 = reinterpret_cast<uint64_t *>(sp);
-    sp += (size_t)kPeSmemSlots * 8;
-    pe_sm1 = reinterpret_cast<uint64_t *>(sp);
-    sp += (size_t)kPeSmemSlots * 8;
-  }
-  c.base[0] = sp;
-  sp += P.ml;
-  c.base[1] = sp;
-  sp += P.ml;
-  c.qcode = sp;
-  c.tb = P.tb + slot * (size_t)P.tb_rows * 4;
-  c.mem_scr = P.mem_scr ? P.mem_scr + slot * (size_t)kPeLarge : nullptr;
-  c.c_lookup = c.c_entry = c.c_word = c.c_align = c.c_dpref = 0;
-
-  CandSet se0, se1, pe0, pe1;
-  se0.v = HeapRef{se_sm0, nullptr, kSeSlots};
-  se1.v = HeapRef{se_sm1, nullptr, kSeSlots};
-  if (paired) {
-    uint64_t *ov = P.pe_overflow + slot * (size_t)2 * kPeLarge;
-    pe0.v = HeapRef{pe_sm0, ov, kPeSmemSlots};
-    pe1.v = HeapRef{pe_sm1, ov + kPeLarge, kPeSmemSlots};
-  }
+  WarpScalars *S = W.scal();
+  if (lane < 6) S->cnt[lane] = 0;
+  __syncwarp();
 
   const uint32_t T = 0, A = ABG_FLAG_A_RICH, RC = ABG_FLAG_RC;
 
@@ -1051,56 +1450,65 @@ __global__ void __launch_bounds__(kThreadsPerBlock) map_reads_kernel(const Kerne
     if (lane == 0) item = atomicAdd(P.work_counter, 1u);
     item = __shfl_sync(FULL, item, 0);
     if (item >= P.n) break;
-    c.cur_key = ~0u;
+    if (lane == 0) {
+      S->qkey[0] = S->qkey[1] = ~0u;
+      S->packed_key = ~0u;
+      S->tbk[0].valid = S->tbk[1].valid = 0;
+    }
+    __syncwarp();
 
     if (!paired) {
       // map_single_ended<conv> / map_single_ended_rand (abismal.cpp:1511-1704)
       const uint32_t o0 = P.off[0][item], len = P.off[0][item + 1] - o0;
-      CigarOut cg{P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride, 0u, 0u};
+      uint32_t cg_n = 0, cg_ref = 0;
       Hit best(kMaxDiffs, 0, 0);
+      if (lane == 0) S->len[0] = len;
+      __syncwarp();
       if (len != 0) {
-        load_end(c, 0, P.seq[0] + o0, len);
-        se0.reset_se(len);
-        uint32_t passes[4];
-        int n_pass;
+        load_end(W, 0, P.seq[0] + o0, len);
+        reset_set(W, 0, 0, len);
         if (rpbat) {
-          passes[0] = T; passes[1] = A; passes[2] = A | RC; passes[3] = T | RC;
-          n_pass = 4;
+          process_seeds(0, 0, T);
+          process_seeds(0, 0, A);
+          process_seeds(0, 0, A | RC);
+          process_seeds(0, 0, T | RC);
         }
         else {
           const uint32_t cv = a_rich ? A : T;
-          passes[0] = cv; passes[1] = cv | RC;
-          n_pass = 2;
+          process_seeds(0, 0, cv);
+          process_seeds(0, 0, cv | RC);
         }
-        for (int p = 0; p < n_pass; ++p) {
-          build_pass(c, 0, passes[p]);
-          process_seeds(c, passes[p], len, se0);
-        }
-        align_se_candidates(c, 0, len, P.valid_frac, se0, best, cg);
+        best = Hit(align_se_candidates(0, P.valid_frac, P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride,
+                                       &cg_n, &cg_ref, best.w));
       }
       if (lane == 0) {
         P.se[0][item] = to_abg(best);
-        P.n_cigar[0][item] = cg.n;
-        if (cg.n > cg.stride) atomicExch(P.error_flag, 1u);
+        P.n_cigar[0][item] = cg_n;
+        if (cg_n > P.cigar_stride) atomicExch(P.error_flag, 1u);
       }
     }
     else {
       // map_paired_ended<conv> / map_paired_ended_rand (abismal.cpp:1887-2185)
-      uint32_t len[2];
-      for (int e = 0; e < 2; ++e) {
-        const uint32_t o = P.off[e][item];
-        len[e] = P.off[e][item + 1] - o;
-        c.len[e] = len[e];
-        if (len[e] != 0) load_end(c, e, P.seq[e] + o, len[e]);
+      uint32_t len0, len1;
+      {
+        const uint32_t oa = P.off[0][item], ob = P.off[1][item];
+        len0 = P.off[0][item + 1] - oa;
+        len1 = P.off[1][item + 1] - ob;
+        if (lane == 0) {
+          S->len[0] = len0;
+          S->len[1] = len1;
+        }
+        __syncwarp();
+        if (len0 != 0) load_end(W, 0, P.seq[0] + oa, len0);
+        if (len1 != 0) load_end(W, 1, P.seq[1] + ob, len1);
       }
       CigarOut cg[2] = {{P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride, 0u, 0u},
                         {P.cigar[1] + (size_t)item * P.cigar_stride, P.cigar_stride, 0u, 0u}};
-      CandSet *res_se[2] = {&se0, &se1};
-      se0.reset_se(len[0]);
-      se1.reset_se(len[1]);
+      reset_set(W, 0, 0, len0);
+      reset_set(W, 1, 0, len1);
       PeBest best;
-      best.reset(len[0], len[1]);
-      Hit best_se[2] = {Hit(invalid_hit_diffs(len[0]), 0, 0), Hit(invalid_hit_diffs(len[1]), 0, 0)};
+      best.reset(len0, len1);
+      Hit best_se0(invalid_hit_diffs(len0), 0, 0), best_se1(invalid_hit_diffs(len1), 0, 0);
       bool any_success = false;
       const int n_calls = rpbat ? 4 : 2;
       for (int call = 0; call < n_calls; ++call) {
@@ -1113,48 +1521,46 @@ __global__ void __launch_bounds__(kThreadsPerBlock) map_reads_kernel(const Kerne
         const uint32_t f1 = enc_a_call ? A : T;         // un-reversed read: a_rich bit == encoding
         const uint32_t f2 = (enc_a_call ? T : A) | RC;  // reversed read: a_rich bit == !encoding
         const int e1 = first_is_r1 ? 0 : 1, e2 = 1 - e1;
-        pe0.reset_pe(len[e1]);
-        pe1.reset_pe(len[e2]);
-        if (len[e1] == 0 && len[e2] == 0) continue;
+        const uint32_t l1 = first_is_r1 ? len0 : len1, l2 = first_is_r1 ? len1 : len0;
+        reset_set(W, 2, 1, l1);
+        reset_set(W, 3, 1, l2);
+        if (l1 == 0 && l2 == 0) continue;
         any_success = true;
-        if (len[e1] != 0) {
-          build_pass(c, e1, f1);
-          process_seeds(c, f1, len[e1], pe0);
-        }
-        if (len[e2] != 0) {
-          build_pass(c, e2, f2);
-          process_seeds(c, f2, len[e2], pe1);
-        }
+        if (l1 != 0) process_seeds(2, e1, f1);
+        if (l2 != 0) process_seeds(3, e2, f2);
         // select_maps (abismal.cpp:1833-1847)
-        if (pe0.should_align() && pe1.should_align()) {
-          sort_unique(pe0.v, pe0.sz, lane);
-          sort_unique(pe1.v, pe1.sz, lane);
-          best_pair(c, swap_ends, e1, f1, e2, f2, pe0, pe1, cg[e1], cg[e2], best);
+        CandSet t0, t1;
+        t0.load(W, 2);
+        t1.load(W, 3);
+        if (t0.should_align() && t1.should_align()) {
+          sort_unique(2);
+          sort_unique(3);
+          best_pair(swap_ends, e1, f1, f2, cg, &best);
         }
-        best_single(pe0, *res_se[e1]);
-        best_single(pe1, *res_se[e2]);
+        best_single(2, e1);
+        best_single(3, e2);
       }
       if (!any_success) {
         best.reset();
-        se0.reset_se_noarg();
-        se1.reset_se_noarg();
+        reset_set(W, 0, 2, 0);
+        reset_set(W, 1, 2, 0);
       }
       {  // valid_pair (abismal.cpp:624-631)
         const uint32_t al1 = cg[0].ref_len, al2 = cg[1].ref_len;
-        const bool ok = valid_len(al1, len[0]) && valid_len(al2, len[1]) &&
+        const bool ok = valid_len(al1, len0) && valid_len(al2, len1) &&
                         best.diffs() <= frac_of(P.valid_frac, al1 + al2);
         if (!ok) best.reset();
       }
       if (!best.should_report(P.allow_ambig != 0u)) {
         const double half = P.valid_frac / 2.0;
-        align_se_candidates(c, 0, len[0], half, se0, best_se[0], cg[0]);
-        align_se_candidates(c, 1, len[1], half, se1, best_se[1], cg[1]);
+        best_se0 = Hit(align_se_candidates(0, half, cg[0].ops, cg[0].stride, &cg[0].n, &cg[0].ref_len, best_se0.w));
+        best_se1 = Hit(align_se_candidates(1, half, cg[1].ops, cg[1].stride, &cg[1].n, &cg[1].ref_len, best_se1.w));
       }
       if (lane == 0) {
         P.pe_r1[item] = to_abg(best.r1);
         P.pe_r2[item] = to_abg(best.r2);
-        P.se[0][item] = to_abg(best_se[0]);
-        P.se[1][item] = to_abg(best_se[1]);
+        P.se[0][item] = to_abg(best_se0);
+        P.se[1][item] = to_abg(best_se1);
         P.n_cigar[0][item] = cg[0].n;
         P.n_cigar[1][item] = cg[1].n;
         if (cg[0].n > cg[0].stride || cg[1].n > cg[1].stride) atomicExch(P.error_flag, 1u);
@@ -1163,22 +1569,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock) map_reads_kernel(const Kerne
     __syncwarp();
   }
 
-  if (P.counters != nullptr) {
-    unsigned long long v[5] = {c.c_lookup, c.c_entry, c.c_word, c.c_align, c.c_dpref};
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      unsigned long long x = v[k];
-      for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
-      v[k] = x;
-    }
-    if (lane == 0) {
-      atomicAdd(P.counters + 0, v[0]);  // n_lookup
-      atomicAdd(P.counters + 1, v[1]);  // n_entry
-      atomicAdd(P.counters + 2, v[1]);  // n_cmp == n_entry
-      atomicAdd(P.counters + 3, v[2]);  // n_word
-      atomicAdd(P.counters + 4, v[3]);  // n_align
-      atomicAdd(P.counters + 5, v[4]);  // n_dpref
-    }
+  if (P.counters != nullptr && lane == 0) {
+    atomicAdd(P.counters + 0, S->cnt[0]);  // n_lookup
+    atomicAdd(P.counters + 1, S->cnt[1]);  // n_entry
+    atomicAdd(P.counters + 2, S->cnt[1]);  // n_cmp == n_entry
+    atomicAdd(P.counters + 3, S->cnt[2]);  // n_word
+    atomicAdd(P.counters + 4, S->cnt[3]);  // n_align
+    atomicAdd(P.counters + 5, S->cnt[4]);  // n_dpref
   }
 }
 
