@@ -32,6 +32,28 @@ int fail(int code, const std::string &msg) {
       return fail(ABG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+// Emptiness bitmap of one counter table (bit k = bucket k non-empty).  Kept only when the table is sparse
+// enough for the L2-resident filter to save HBM probes; *out stays null otherwise.
+int make_bitmap(const uint32_t *d_counter, uint64_t n_buckets, uint32_t **out) {
+  *out = nullptr;
+  uint32_t *bits = nullptr;
+  unsigned long long *d_n = nullptr, n_set = 0;
+  const uint64_t words = (n_buckets + 31) / 32;
+  ABG_CUDA(cudaMalloc(reinterpret_cast<void **>(&bits), words * 4));
+  ABG_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_n), 8));
+  ABG_CUDA(cudaMemset(d_n, 0, 8));
+  ab2dev::bucket_bitmap_kernel<<<148 * 8, 256>>>(d_counter, n_buckets, bits, d_n);
+  ABG_CUDA(cudaGetLastError());
+  ABG_CUDA(cudaMemcpy(&n_set, d_n, 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_n);
+  if (n_set * 2 > n_buckets) {  // dense table: almost every probe would need the counters anyway
+    cudaFree(bits);
+    return ABG_OK;
+  }
+  *out = bits;
+  return ABG_OK;
+}
+
 template <class T>
 int upload(const T *host, uint64_t n, uint64_t n_alloc, T **dev) {
   *dev = nullptr;
@@ -50,6 +72,7 @@ struct abg_index {
   uint64_t *genome = nullptr;
   uint32_t *counter = nullptr, *counter_t = nullptr, *counter_a = nullptr;
   uint32_t *index = nullptr, *index_t = nullptr, *index_a = nullptr;
+  uint32_t *bits = nullptr, *bits_t = nullptr, *bits_a = nullptr;
 };
 
 struct abg_mapper {
@@ -126,6 +149,15 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
     abg_index_destroy(ix);
     return rc;
   }
+  if ((rc = make_bitmap(ix->counter, v->counter_size, &ix->bits)) ||
+      (rc = make_bitmap(ix->counter_t, v->counter_size_three, &ix->bits_t)) ||
+      (rc = make_bitmap(ix->counter_a, v->counter_size_three, &ix->bits_a))) {
+    abg_index_destroy(ix);
+    return rc;
+  }
+  ix->dev.bits = ix->bits;
+  ix->dev.bits_t = ix->bits_t;
+  ix->dev.bits_a = ix->bits_a;
   ix->bytes = (v->genome_words + 4) * 8 + (v->counter_size + 1) * 4 + 2 * (v->counter_size_three + 1) * 4 +
               v->index_size * 4 + 2 * v->index_size_three * 4;
   ix->dev.genome = ix->genome;
@@ -150,6 +182,9 @@ void abg_index_destroy(abg_index *ix) {
   cudaFree(ix->index);
   cudaFree(ix->index_t);
   cudaFree(ix->index_a);
+  cudaFree(ix->bits);
+  cudaFree(ix->bits_t);
+  cudaFree(ix->bits_a);
   delete ix;
 }
 

@@ -57,6 +57,8 @@ constexpr int kPeLarge = 32 << 10;  // pe_candidates::max_size_large
 constexpr int kPeSmemSlots = 128;   // PE heap entries kept in shared memory
 constexpr int kMaxDiffs = 32767;
 constexpr int kCand = 4;            // candidates per lane per compare chunk (tight bound; 2 under a loose bound)
+constexpr int kLogCap = 128;          // survivor-log entries per pass (specific -> sensitive reuse)
+constexpr int kLogMaxLen = 1023;     // reads longer than this do not use the log (9-bit offset field)
 constexpr int kTbLanesSm = 8;       // traceback words of lanes < 8 (band <= 16) stay in shared memory
 constexpr int kTbCacheMaxCands = 4; // record traceback while scoring when a set has at most this many candidates
 
@@ -64,6 +66,9 @@ struct IndexDev {
   const uint64_t *genome;
   const uint32_t *counter, *counter_t, *counter_a;
   const uint32_t *index, *index_t, *index_a;
+  // bit k set <=> bucket k of the table is non-empty (counter[k+1] != counter[k]); small enough to stay in L2.
+  // A null pointer means "probe the counters directly" (dense tables, where the bitmap would save nothing).
+  const uint32_t *bits, *bits_t, *bits_a;
   uint32_t max_candidates;
 };
 
@@ -160,8 +165,8 @@ static_assert(sizeof(KernelParams) <= kParamBytes, "KernelParams must fit its sh
 __host__ __device__ __forceinline__ uint32_t tb_sm_words(uint32_t ml) { return (ml + 64u + 32u + 15u) / 16u; }
 
 struct WarpLayout {
-  uint32_t o_packed, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_base, o_qcode, o_refb, total;
-  uint32_t plane_words;
+  uint32_t o_packed, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, total;
+  uint32_t plane_words, elig_words;
 };
 
 __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool paired) {
@@ -179,6 +184,11 @@ __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool pai
   o += (uint32_t)sizeof(WarpScalars);
   L.o_tb = o;
   o += 2u * tb_sm_words(ml) * kTbLanesSm * 8u;  // traceback words of 2 slots
+  L.o_log = o;
+  o += 2u * kLogCap * 4u;                    // survivor log: positions + packed (d, pm, table, offset)
+  L.elig_words = ml / 64u + 1u;              // specific offsets are < readlen / 2
+  L.o_elig = o;
+  o += 2u * L.elig_words * 4u;
   L.plane_words = ml / 32u + 2u;
   L.o_planes = o;
   o += 3u * L.plane_words * 4u;
@@ -223,6 +233,9 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   __device__ __forceinline__ uint8_t *base(int e) const { return base_ptr + L.o_base + (size_t)e * params().ml; }
   __device__ __forceinline__ uint8_t *qcode(int e) const { return base_ptr + L.o_qcode + (size_t)e * (params().ml + 32u); }
   __device__ __forceinline__ uint8_t *refb() const { return base_ptr + L.o_refb; }
+  __device__ __forceinline__ uint32_t *log_pos() const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_log); }
+  __device__ __forceinline__ uint32_t *log_meta() const { return log_pos() + kLogCap; }
+  __device__ __forceinline__ uint32_t *elig(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_elig) + k * L.elig_words; }
   __device__ __forceinline__ size_t slot() const { return (size_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); }
   __device__ __forceinline__ uint64_t *tb_gm(int s) const {
     const KernelParams &P = params();
@@ -587,11 +600,10 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
                                               const uint64_t *packed, int n_words, int bound, uint32_t c0,
                                               uint32_t total, uint32_t base_off, uint32_t incl, uint32_t tot,
                                               uint32_t n2, uint32_t s2, uint32_t s3, int lane, int (&d)[KC],
-                                              int (&pm)[KC], uint32_t (&the_pos)[KC],
+                                              int (&pm)[KC], uint32_t (&the_pos)[KC], uint32_t (&sub)[KC],
                                               unsigned long long &n_entry,
                                               unsigned long long &n_word) {
   bool valid[KC];
-  uint32_t sub[KC];
   // ---- owners + index gathers (KC independent loads per lane) ----
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
@@ -616,10 +628,11 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
       entry = (r < o_n2) ? __ldg(ix.index + o_s2 + r) : __ldg(index3 + o_s3 + (r - o_n2));
     }
     the_pos[k] = entry;
-    sub[k] = base_off + (uint32_t)o;
+    // seed offset of the candidate; bit 31 = it came from the three-letter bucket
+    sub[k] = (base_off + (uint32_t)o) | ((valid[k] && cidx - (o_incl - o_tot) >= o_n2) ? 0x80000000u : 0u);
   }
 #pragma unroll
-  for (int k = 0; k < KC; ++k) the_pos[k] -= sub[k];
+  for (int k = 0; k < KC; ++k) the_pos[k] -= sub[k] & 0x7fffffffu;
 
   // ---- stage 0: S0 + 1 genome words per candidate, all gathers issued before any use ----
   uint64_t g[KC][S0 + 1];
@@ -679,6 +692,60 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
   }
 }
 
+// Ordered replay of the survivors of one compare round against candidate set `set_id`
+// (check_hits' `if (diffs <= res.cutoff) res.update(...)`, abismal.cpp:1146-1147, in bucket order).
+// Kept out of line: survivors are rare, and the heap code must not bloat the gather loop.
+__device__ __noinline__ void replay_hits(int set_id, uint32_t strand_code, unsigned mask, int d, int pm, uint32_t pos) {
+  const Warp W;
+  CandSet res;
+  res.load(W, set_id);
+  while (mask != 0u && !res.sure_ambig) {
+    const int l = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int dd = __shfl_sync(FULL, d, l);
+    const int mm = __shfl_sync(FULL, pm, l);
+    const uint32_t pp = __shfl_sync(FULL, pos, l);
+    if (mm <= res.cutoff) res.update(true, dd, strand_code, pp);  // check_hits<.., true> in both phases
+  }
+  res.store(W, set_id);
+}
+
+// survivor-log entry: d (11 bits) | pm (11 bits) | three-letter table (1 bit) | seed offset (9 bits)
+__device__ __forceinline__ uint32_t log_pack(int d, int pm, uint32_t is3, uint32_t off) {
+  return (uint32_t)d | ((uint32_t)pm << 11) | (is3 << 22) | (off << 23);
+}
+
+// Sensitive phase for the seed offsets the specific phase has already examined: every candidate of a
+// sensitive-eligible bucket at those offsets whose distance is within the (looser) sensitive cutoff was logged,
+// in canonical order, by the specific phase; replay them instead of gathering the same words again.
+__device__ __noinline__ void replay_log(int set_id, uint32_t strand_code, int n_log) {
+  const Warp W;
+  const uint32_t *lp = W.log_pos(), *lm = W.log_meta();
+  const uint32_t *e2 = W.elig(0), *e3 = W.elig(1);
+  CandSet res;
+  res.load(W, set_id);
+  for (int k = 0; k < n_log && !res.sure_ambig; ++k) {
+    const uint32_t m = lm[k];
+    const uint32_t off = m >> 23, is3 = (m >> 22) & 1u;
+    const uint32_t ew = (is3 ? e3 : e2)[off >> 5];
+    if (((ew >> (off & 31u)) & 1u) == 0u) continue;  // bucket not examined by the sensitive phase
+    const int d = (int)(m & 2047u), pm = (int)((m >> 11) & 2047u);
+    if (pm <= res.cutoff) res.update(true, d, strand_code, lp[k]);
+  }
+  res.store(W, set_id);
+}
+
+// 2 adjacent counters of bucket k; the L2-resident emptiness bitmap (when present) filters out empty buckets
+// without touching HBM.
+__device__ __forceinline__ void probe(const uint32_t *__restrict__ counter, const uint32_t *__restrict__ bits,
+                                      uint32_t k, uint32_t &s, uint32_t &e) {
+  s = 0;
+  e = 0;
+  if (bits != nullptr && ((__ldg(bits + (k >> 5)) >> (k & 31u)) & 1u) == 0u) return;
+  s = __ldg(counter + k);
+  e = __ldg(counter + k + 1);
+}
+
 // process_seeds (abismal.cpp:1269-1375) for pass `strand_code` of `end` into candidate set `set_id`
 __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_code) {
   const Warp W;
@@ -695,38 +762,56 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
   const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
   const uint32_t *counter3 = g_to_a ? ix.counter_a : ix.counter_t;
   const uint32_t *index3 = g_to_a ? ix.index_a : ix.index_t;
+  const uint32_t *bits3 = g_to_a ? ix.bits_a : ix.bits_t;
   const uint32_t maxc = P.max_candidates;
   const int n_words = (int)((readlen + 15) / 16);
   unsigned long long c_lookup = 0, c_entry = 0, c_word = 0;
-
-  CandSet res;
-  res.load(W, set_id);
+  volatile CandState *st = W.cs(set_id);  // the set's scalar state stays in shared memory
+  const volatile uint64_t *heap0 = heap_of(W, set_id).sm;
+  uint32_t *log_pos = W.log_pos(), *log_meta = W.log_meta();
+  uint32_t *elig2 = W.elig(0), *elig3 = W.elig(1);
 
   const uint32_t specific_len = min(readlen - 20u, readlen >> 1);
   const uint32_t specific_lim = max(20u, readlen >> 1);
   const uint32_t lim_two = readlen - 25u + 1u;
+  int n_log = 0;
+  bool log_ok = readlen <= (uint32_t)kLogMaxLen;
 
   for (int phase = 0; phase < 2; ++phase) {
     const bool specific = phase == 0;
-    if (specific) res.set_specific();
-    else {
-      if (!res.should_do_sensitive()) break;
-      res.set_sensitive();
+    uint32_t first_off = 0;
+    {
+      CandSet res;
+      res.load(W, set_id);
+      if (specific) res.set_specific();
+      else {
+        if (!res.should_do_sensitive()) break;
+        res.set_sensitive();
+      }
+      res.store(W, set_id);
+    }
+    if (!specific && log_ok) {
+      if (n_log > 0) replay_log(set_id, strand_code, n_log);
+      first_off = specific_lim;
     }
     const uint32_t n_off = specific ? specific_lim : lim_two;
-    for (uint32_t base_off = 0; base_off < n_off && !res.sure_ambig; base_off += 32) {
+    for (uint32_t base_off = first_off; base_off < n_off && !st->sure_ambig; base_off += 32) {
       const uint32_t i = base_off + lane;
       const bool active = i < n_off;
       uint32_t s2 = 0, e2 = 0, s3 = 0, e3 = 0, n2 = 0, n3 = 0;
+      bool el2 = false, el3 = false;
       if (active) {
         // get_1bit_hash / get_base_3_hash at offset i (rolling == direct), AbismalIndex.hpp:285-305
         const uint32_t k = __brev(plane_window(p2, i)) >> 7;
         const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
         const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
-        s2 = __ldg(ix.counter + k);
-        e2 = __ldg(ix.counter + k + 1);
-        s3 = __ldg(counter3 + k3);
-        e3 = __ldg(counter3 + k3 + 1);
+        probe(ix.counter, ix.bits, k, s2, e2);
+        probe(counter3, bits3, k3, s3, e3);
+        {  // the sensitive phase's bucket rule (abismal.cpp:1351-1370), on the raw bucket sizes
+          const uint32_t d_two = e2 - s2, d_three = e3 - s3;
+          el2 = d_two != 0u && d_two <= maxc && (d_three == 0u || d_two <= 10u * d_three);
+          el3 = d_three != 0u && d_three <= maxc;
+        }
         if (specific) {
           uint32_t l_two = 25, l_three = 16;
           if (e2 - s2 > maxc || e2 == s2) {
@@ -746,60 +831,100 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
           n3 = (d_three <= maxc || l_three >= specific_len) ? d_three : 0u;
         }
         else {
-          const uint32_t d_two = e2 - s2, d_three = e3 - s3;
-          n2 = (d_two != 0u && d_two <= maxc && (d_three == 0u || d_two <= 10u * d_three)) ? d_two : 0u;
-          n3 = (d_three != 0u && d_three <= maxc) ? d_three : 0u;
+          n2 = el2 ? e2 - s2 : 0u;
+          n3 = el3 ? e3 - s3 : 0u;
         }
         c_lookup += 2;
       }
       __syncwarp();
+      if (specific) {
+        const unsigned m2 = __ballot_sync(FULL, el2), m3 = __ballot_sync(FULL, el3);
+        if (lane == 0) {
+          elig2[base_off >> 5] = m2;
+          elig3[base_off >> 5] = m3;
+        }
+      }
       const uint32_t tot = n2 + n3;
       const uint32_t incl = warp_incl_scan_add(tot, lane);
       const uint32_t total = __shfl_sync(FULL, incl, 31);
-      for (uint32_t c0 = 0; c0 < total && !res.sure_ambig;) {
-        int d[kCand], pm[kCand];
-        uint32_t the_pos[kCand];
-        const int bound = res.cutoff;
-        // tight bound (specific phase): most candidates die within 2 words -> 4 candidates x 3 words per lane;
-        // loose bound (sensitive phase, ~6 words per candidate): 2 candidates x 5 words per lane
-        int kc;
-        if (bound >= 30) {
-          int d2[2], pm2[2];
-          uint32_t pos2[2];
-          compare_chunk<2, 4>(ix, index3, packed, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3, lane,
-                              d2, pm2, pos2, c_entry, c_word);
-#pragma unroll
-          for (int k = 0; k < kCand; ++k) {
-            d[k] = k < 2 ? d2[k & 1] : 0;
-            pm[k] = k < 2 ? pm2[k & 1] : (1 << 30);
-            the_pos[k] = k < 2 ? pos2[k & 1] : 0u;
+      bool stop = false;
+      for (uint32_t c0 = 0; c0 < total && !stop;) {
+        const int cutoff = st->cutoff;
+        // In the specific phase compare against the looser bound the sensitive phase may use later (the heap
+        // top only ever decreases) and log what survives it, unless the set is already full (then the
+        // sensitive phase is unlikely to run and deep compares would be wasted).
+        bool deep = false;
+        int bound = cutoff;
+        if (specific && log_ok) {
+          const int cap_now = st->is_pe ? (int)st->capacity : (int)kSeMax;
+          if (st->sz == cap_now) log_ok = false;
+          else {
+            deep = true;
+            bound = Hit(heap0[0]).diffs();
           }
-          kc = 2;
+        }
+        if (bound >= 30) {
+          int d[2], pm[2];
+          uint32_t the_pos[2];
+          uint32_t sub[2];
+          compare_chunk<2, 6>(ix, index3, packed, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3, lane,
+                              d, pm, the_pos, sub, c_entry, c_word);
+          c0 += 64u;
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (deep) {
+              const unsigned ml = __ballot_sync(FULL, pm[k] <= bound);
+              if (ml != 0u) {
+                const int at = n_log + __popc(ml & ((1u << lane) - 1u));
+                n_log += __popc(ml);
+                if (n_log > kLogCap) log_ok = false;
+                else if (pm[k] <= bound) {
+                  log_pos[at] = the_pos[k];
+                  log_meta[at] = log_pack(d[k], pm[k], sub[k] >> 31, sub[k] & 0x7fffffffu);
+                }
+              }
+            }
+            const unsigned mask = __ballot_sync(FULL, pm[k] <= cutoff);
+            if (mask != 0u && !stop) {
+              replay_hits(set_id, strand_code, mask, d[k], pm[k], the_pos[k]);
+              stop = st->sure_ambig != 0;
+            }
+          }
         }
         else {
+          int d[kCand], pm[kCand];
+          uint32_t the_pos[kCand];
+          uint32_t sub[kCand];
           compare_chunk<kCand, 2>(ix, index3, packed, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3,
-                                  lane, d, pm, the_pos, c_entry, c_word);
-          kc = kCand;
-        }
-        c0 += 32u * kc;
-        __syncwarp();
+                                  lane, d, pm, the_pos, sub, c_entry, c_word);
+          c0 += 32u * kCand;
+          __syncwarp();
 #pragma unroll
-        for (int k = 0; k < kCand; ++k) {
-          if (k >= kc) break;
-          unsigned mask = __ballot_sync(FULL, pm[k] <= bound);
-          while (mask != 0u && !res.sure_ambig) {
-            const int l = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int dd = __shfl_sync(FULL, d[k], l);
-            const int mm = __shfl_sync(FULL, pm[k], l);
-            const uint32_t pp = __shfl_sync(FULL, the_pos[k], l);
-            if (mm <= res.cutoff) res.update(true, dd, strand_code, pp);  // check_hits<.., true> in both phases
+          for (int k = 0; k < kCand; ++k) {
+            if (deep) {
+              const unsigned ml = __ballot_sync(FULL, pm[k] <= bound);
+              if (ml != 0u) {
+                const int at = n_log + __popc(ml & ((1u << lane) - 1u));
+                n_log += __popc(ml);
+                if (n_log > kLogCap) log_ok = false;
+                else if (pm[k] <= bound) {
+                  log_pos[at] = the_pos[k];
+                  log_meta[at] = log_pack(d[k], pm[k], sub[k] >> 31, sub[k] & 0x7fffffffu);
+                }
+              }
+            }
+            const unsigned mask = __ballot_sync(FULL, pm[k] <= cutoff);
+            if (mask != 0u && !stop) {
+              replay_hits(set_id, strand_code, mask, d[k], pm[k], the_pos[k]);
+              stop = st->sure_ambig != 0;
+            }
           }
         }
       }
     }
+    __syncwarp();
   }
-  res.store(W, set_id);
   if (P.counters != nullptr) {
     unsigned long long *cnt = W.scal()->cnt;
     for (int d = 16; d >= 1; d >>= 1) {
@@ -1406,6 +1531,22 @@ __device__ __forceinline__ void reset_set(const Warp &W, int id, int kind, uint3
     s.reset_se_noarg();
   }
   s.store(W, id);
+}
+
+// bit k of `bits` = bucket k is non-empty; *n_set += number of non-empty buckets (n = counter_size)
+__global__ void bucket_bitmap_kernel(const uint32_t *__restrict__ counter, uint64_t n, uint32_t *bits,
+                                     unsigned long long *n_set) {
+  const uint64_t n_round = (n + 31) & ~(uint64_t)31;
+  unsigned long long local = 0;
+  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_round; k += (uint64_t)gridDim.x * blockDim.x) {
+    const bool nonempty = k < n && counter[k + 1] != counter[k];
+    const unsigned m = __ballot_sync(FULL, nonempty);
+    if ((threadIdx.x & 31) == 0) {
+      bits[k >> 5] = m;
+      local += __popc(m);
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_set, local);
 }
 
 // MINB = resident CTAs per SM the register allocation is bounded for (2: <=128 regs, 3: <=80, 4: <=64)
