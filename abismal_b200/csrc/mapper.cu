@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int kDefaultMinB = 3;
+constexpr int kDefaultMinB = 2;
 
 thread_local std::string g_err;
 

@@ -293,17 +293,27 @@ def main():
             o.close()
             ms_per_launch = dev_ms / launches
             achieved = bytes_per_pair * b1.n / (ms_per_launch / 1e3) / 1e9
-            traffic = None
+            traffic, gather = None, None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
+                    tj = json.load(f)
+                # ncu --set full capture of the same kernel on a 262144-pair batch of the same reads,
+                # scaled to this launch's batch (the kernel's work is linear in the number of pairs)
+                traffic = float(tj["dram_bytes_per_pair"]) * b1.n
+                sect_s = float(tj["l1_miss_sectors_per_pair"]) * b1.n / (ms_per_launch / 1e3) / 1e9
+                gather = {"achieved_gsectors_per_s": sect_s,
+                          "ceiling_gsectors_per_s": float(tj["random_gather_ceiling_gsectors_per_s"]),
+                          "frac": sect_s / float(tj["random_gather_ceiling_gsectors_per_s"]),
+                          "note": "32-byte L1-miss sectors per second vs the random-gather ceiling measured with "
+                                  "tools/micro/gather_bench.cu; this, not streaming bandwidth, bounds the kernel"}
             except Exception:
                 pass
             out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                                "algorithmic_bytes_per_pair": bytes_per_pair,
                                "kernel": "map_reads_kernel", "ms_per_launch": ms_per_launch,
-                               "counters_from": "CPU oracle on the first %d pairs of the batch" % n_o}
+                               "counters_from": "CPU oracle on the first %d pairs of the batch" % n_o,
+                               "random_gather": gather}
             n_s = min(args.cpu_sample_pairs, b1.n)
             s1, s2 = prefix + "_sample_1.fq", prefix + "_sample_2.fq"
             sample_fastq(fq1, s1, n_s)
