@@ -2,6 +2,7 @@
 identical data contract in oracle/abismal_oracle.h)."""
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -99,8 +100,47 @@ def load_library():
     lib.abg_mapper_launches_per_run.argtypes = [C.c_void_p]
     lib.abg_mapper_launches_per_run.restype = C.c_uint32
     lib.abg_mapper_get_counters.argtypes = [C.c_void_p, C.POINTER(abg_work_counters)]
+    lib.abg_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.abg_host_free.argtypes = [C.c_void_p]
+    lib.abg_host_free.restype = None
+    lib.abg_mapper_chunk.argtypes = [C.c_void_p]
+    lib.abg_mapper_chunk.restype = C.c_uint32
     _lib = lib
     return lib
+
+
+class _PinnedBlock:
+    """Page-locked host memory from abg_host_alloc; freed when the last array viewing it dies."""
+
+    def __init__(self, nbytes):
+        self.lib = load_library()
+        self.ptr = C.c_void_p()
+        if self.lib.abg_host_alloc(max(int(nbytes), 1), C.byref(self.ptr)) != 0:
+            raise AbgError(self.lib.abg_last_error().decode())
+        self.buf = (C.c_char * max(int(nbytes), 1)).from_address(self.ptr.value)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.abg_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_zeros(shape, dtype):
+    """numpy array over page-locked memory (DMA'd in place by abg_map_batch)."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if not np.isscalar(shape) else int(shape)
+    blk = _PinnedBlock(n * dt.itemsize)
+    root = np.frombuffer(blk.buf, dtype=dt, count=n)  # every view keeps `root` alive through .base
+    root[...] = np.zeros((), dt)
+    _keep[id(blk)] = blk
+    weakref.finalize(root, _keep.pop, id(blk), None)
+    return root.reshape(shape)
+
+
+_keep = {}
 
 
 def _ptr(a):
@@ -143,17 +183,18 @@ def make_params(mode=0, allow_ambig=False, min_dist=32, max_dist=3000, valid_fra
 class Results:
     """Host result arrays for one batch (numpy, caller owned)."""
 
-    def __init__(self, n, paired, stride):
+    def __init__(self, n, paired, stride, pinned=False):
         self.n, self.paired, self.stride = n, paired, stride
-        self.se1 = np.zeros(n, HIT_DTYPE)
-        self.cigar1 = np.zeros((n, stride), np.uint32)
-        self.n_cigar1 = np.zeros(n, np.uint32)
+        zeros = pinned_zeros if pinned else np.zeros
+        self.se1 = zeros(n, HIT_DTYPE)
+        self.cigar1 = zeros((n, stride), np.uint32)
+        self.n_cigar1 = zeros(n, np.uint32)
         if paired:
-            self.pe_r1 = np.zeros(n, HIT_DTYPE)
-            self.pe_r2 = np.zeros(n, HIT_DTYPE)
-            self.se2 = np.zeros(n, HIT_DTYPE)
-            self.cigar2 = np.zeros((n, stride), np.uint32)
-            self.n_cigar2 = np.zeros(n, np.uint32)
+            self.pe_r1 = zeros(n, HIT_DTYPE)
+            self.pe_r2 = zeros(n, HIT_DTYPE)
+            self.se2 = zeros(n, HIT_DTYPE)
+            self.cigar2 = zeros((n, stride), np.uint32)
+            self.n_cigar2 = zeros(n, np.uint32)
         else:
             self.pe_r1 = self.pe_r2 = self.se2 = self.cigar2 = self.n_cigar2 = None
 
@@ -163,12 +204,18 @@ class Results:
             setattr(r, k, _ptr(getattr(self, k)))
         return r
 
-    def d2h_bytes(self):
+    def d2h_bytes(self, inline_ops=16):
+        """Bytes abg_map_batch copies device -> host: hit records, CIGAR lengths and the first
+        `inline_ops` operations of every CIGAR row (longer CIGARs are fetched singly)."""
         tot = 0
-        for k in ("pe_r1", "pe_r2", "se1", "se2", "cigar1", "cigar2", "n_cigar1", "n_cigar2"):
+        for k in ("pe_r1", "pe_r2", "se1", "se2", "n_cigar1", "n_cigar2"):
             a = getattr(self, k)
             if a is not None:
                 tot += a.nbytes
+        for k in ("cigar1", "cigar2"):
+            a = getattr(self, k)
+            if a is not None:
+                tot += a.shape[0] * min(inline_ops, a.shape[1]) * 4
         return tot
 
     def cigars(self, end):

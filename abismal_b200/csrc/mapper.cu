@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "abismal_b200.h"
 #include "mapper_kernels.cuh"
@@ -75,13 +76,19 @@ struct abg_index {
   uint32_t *bits = nullptr, *bits_t = nullptr, *bits_a = nullptr;
 };
 
+constexpr uint32_t kInlineOps = 16;   // CIGAR ops per read copied back with the batch; longer ones are fetched afterwards
+constexpr uint32_t kMaxChunks = 256;  // sub-batches one abg_map_batch call is pipelined over
+
 struct abg_mapper {
   abg_index *idx = nullptr;
   abg_params params{};
-  uint32_t max_batch = 0, max_read_len = 0, ml = 0;
+  uint32_t max_batch = 0, max_read_len = 0, ml = 0, chunk = 0;
   bool paired = false, count_work = false;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr;                       // upload / run / download (split API)
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;       // pipelined abg_map_batch
+  cudaStream_t s_run[2] = {nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_start = nullptr;
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_out[kMaxChunks] = {};
   float last_ms = 0.f;
   // launch shape
   int grid = 0, minb = 0;
@@ -94,23 +101,201 @@ struct abg_mapper {
   // device results
   abg_hit *d_pe_r1 = nullptr, *d_pe_r2 = nullptr, *d_se[2] = {nullptr, nullptr};
   uint32_t *d_cigar[2] = {nullptr, nullptr}, *d_ncigar[2] = {nullptr, nullptr};
+  uint32_t *d_cigar_inline[2] = {nullptr, nullptr};  // [max_batch][inline_ops]
   // scratch
   uint64_t *d_pe_overflow = nullptr;
   int16_t *d_mem_scr = nullptr;
   uint64_t *d_tb = nullptr;
   uint32_t tb_words = 0;
-  unsigned int *d_work = nullptr;   // [0] work counter, [1] error flag
+  unsigned int *d_work = nullptr;   // [0] error flag, [1 + j] work counter of chunk j
   unsigned long long *d_counters = nullptr;
-  // pinned staging
+  // pinned staging (used when the caller's buffers are pageable)
   char *h_seq[2] = {nullptr, nullptr};
   uint32_t *h_off[2] = {nullptr, nullptr};
   abg_hit *h_pe_r1 = nullptr, *h_pe_r2 = nullptr, *h_se[2] = {nullptr, nullptr};
-  uint32_t *h_cigar[2] = {nullptr, nullptr}, *h_ncigar[2] = {nullptr, nullptr};
+  uint32_t *h_cigar[2] = {nullptr, nullptr}, *h_ncigar[2] = {nullptr, nullptr};  // h_cigar: kInlineOps per read
   unsigned int *h_flags = nullptr;
   abg_work_counters counters{};
   uint32_t cur_n = 0;
   bool timed = false;  // ev0/ev1 have been recorded
 };
+
+namespace {
+
+bool is_pinned(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Offsets of reads [c0, c1] rebased to the start of the batch, with the ReadLoader contract checked.
+int stage_offsets(abg_mapper *m, const uint32_t *off, uint32_t c0, uint32_t c1, uint32_t *dst) {
+  const uint32_t base = off[0];
+  for (uint32_t i = c0; i < c1; ++i) {
+    const uint32_t len = off[i + 1] - off[i];
+    if (len > m->max_read_len) return fail(ABG_ERR_TOO_LONG, "abg_map_batch: read longer than max_read_len");
+    if (len != 0 && len < 44)
+      return fail(ABG_ERR_INVALID, "abg_map_batch: reads shorter than 44 bases must be passed as empty");
+    dst[i] = off[i] - base;
+  }
+  dst[c1] = off[c1] - base;
+  return ABG_OK;
+}
+
+void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint32_t n, unsigned int *work) {
+  std::memset(&P, 0, sizeof P);
+  P.ix = m->idx->dev;
+  P.n = n;
+  const uint32_t stride = m->params.cigar_stride;
+  for (int e = 0; e < 2; ++e) {
+    P.seq[e] = m->d_seq[e];
+    P.off[e] = m->d_off[e] ? m->d_off[e] + c0 : nullptr;
+    P.se[e] = m->d_se[e] ? m->d_se[e] + c0 : nullptr;
+    P.cigar[e] = m->d_cigar[e] ? m->d_cigar[e] + (size_t)c0 * stride : nullptr;
+    P.n_cigar[e] = m->d_ncigar[e] ? m->d_ncigar[e] + c0 : nullptr;
+    P.cigar_inline[e] = m->d_cigar_inline[e] ? m->d_cigar_inline[e] + (size_t)c0 * std::min(kInlineOps, stride) : nullptr;
+  }
+  P.inline_ops = std::min(kInlineOps, stride);
+  P.pe_r1 = m->d_pe_r1 ? m->d_pe_r1 + c0 : nullptr;
+  P.pe_r2 = m->d_pe_r2 ? m->d_pe_r2 + c0 : nullptr;
+  P.cigar_stride = stride;
+  P.mode = m->params.mode;
+  P.allow_ambig = m->params.allow_ambig;
+  P.min_dist = m->params.min_dist;
+  P.max_dist = m->params.max_dist;
+  P.max_candidates = m->params.max_candidates ? m->params.max_candidates : m->idx->dev.max_candidates;
+  P.valid_frac = m->params.valid_frac;
+  P.ml = m->ml;
+  P.pe_overflow = m->d_pe_overflow;
+  P.mem_scr = m->d_mem_scr;
+  P.tb = m->d_tb;
+  P.tb_words = m->tb_words;
+  P.work_counter = work;
+  P.error_flag = m->d_work;
+  P.counters = m->d_counters;
+}
+
+int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st) {
+  if (P.n == 0) return ABG_OK;
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid, ((uint64_t)P.n + ab2dev::kWarpsPerBlock - 1) / ab2dev::kWarpsPerBlock);
+  void *args[] = {&P};
+  ABG_CUDA(cudaLaunchKernel(m->kernel, dim3(grid), dim3(ab2dev::kThreadsPerBlock), args, m->smem, st));
+  return ABG_OK;
+}
+
+struct ResultDst {  // where hit records and CIGAR lengths land: the caller's buffers when pinned, else staging
+  abg_hit *pe_r1, *pe_r2, *se[2];
+  uint32_t *ncig[2];
+  bool direct;
+};
+
+ResultDst pick_result_dst(abg_mapper *m, const abg_results *r) {
+  ResultDst d{};
+  bool direct = is_pinned(r->se1) && is_pinned(r->n_cigar1);
+  if (m->paired) direct = direct && is_pinned(r->pe_r1) && is_pinned(r->pe_r2) && is_pinned(r->se2) && is_pinned(r->n_cigar2);
+  d.direct = direct;
+  if (direct) {
+    d.pe_r1 = r->pe_r1;
+    d.pe_r2 = r->pe_r2;
+    d.se[0] = r->se1;
+    d.se[1] = r->se2;
+    d.ncig[0] = r->n_cigar1;
+    d.ncig[1] = r->n_cigar2;
+  }
+  else {
+    d.pe_r1 = m->h_pe_r1;
+    d.pe_r2 = m->h_pe_r2;
+    for (int e = 0; e < 2; ++e) {
+      d.se[e] = m->h_se[e];
+      d.ncig[e] = m->h_ncigar[e];
+    }
+  }
+  return d;
+}
+
+// Device -> host copy of the results of reads [c0, c0 + n): hit records, CIGAR lengths and the compact
+// [n][inline_ops] array holding the first operations of every CIGAR (into the mapper's pinned staging).
+int copy_results_async(abg_mapper *m, const ResultDst &d, uint32_t c0, uint32_t n, cudaStream_t st) {
+  if (n == 0) return ABG_OK;
+  const uint32_t w = std::min(kInlineOps, m->params.cigar_stride);
+  const int n_ends = m->paired ? 2 : 1;
+  for (int e = 0; e < n_ends; ++e) {
+    ABG_CUDA(cudaMemcpyAsync(d.se[e] + c0, m->d_se[e] + c0, (size_t)n * sizeof(abg_hit), cudaMemcpyDeviceToHost, st));
+    ABG_CUDA(cudaMemcpyAsync(d.ncig[e] + c0, m->d_ncigar[e] + c0, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    ABG_CUDA(cudaMemcpyAsync(m->h_cigar[e] + (size_t)c0 * w, m->d_cigar_inline[e] + (size_t)c0 * w, (size_t)n * w * 4,
+                             cudaMemcpyDeviceToHost, st));
+  }
+  if (m->paired) {
+    ABG_CUDA(cudaMemcpyAsync(d.pe_r1 + c0, m->d_pe_r1 + c0, (size_t)n * sizeof(abg_hit), cudaMemcpyDeviceToHost, st));
+    ABG_CUDA(cudaMemcpyAsync(d.pe_r2 + c0, m->d_pe_r2 + c0, (size_t)n * sizeof(abg_hit), cudaMemcpyDeviceToHost, st));
+  }
+  return ABG_OK;
+}
+
+// Host side of reads [c0, c0 + n) once their copies have landed: staging -> caller for pageable result
+// buffers, and the used part of every CIGAR row scattered into the caller's cigar_stride rows.
+void scatter_results(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t c0, uint32_t n) {
+  const uint32_t stride = m->params.cigar_stride;
+  const uint32_t w = std::min(kInlineOps, stride);
+  const int n_ends = m->paired ? 2 : 1;
+  abg_hit *const u_se[2] = {r->se1, r->se2};
+  uint32_t *const u_cig[2] = {r->cigar1, r->cigar2};
+  uint32_t *const u_ncig[2] = {r->n_cigar1, r->n_cigar2};
+  for (int e = 0; e < n_ends; ++e) {
+    if (!d.direct) {
+      std::memcpy(u_se[e] + c0, d.se[e] + c0, (size_t)n * sizeof(abg_hit));
+      std::memcpy(u_ncig[e] + c0, d.ncig[e] + c0, (size_t)n * 4);
+    }
+    if (u_cig[e]) {
+      const uint32_t *nc = d.ncig[e] + c0;
+      const uint32_t *src = m->h_cigar[e] + (size_t)c0 * w;
+      uint32_t *dst = u_cig[e] + (size_t)c0 * stride;
+      for (uint32_t i = 0; i < n; ++i, src += w, dst += stride) {
+        const uint32_t k = std::min(nc[i], w);
+        for (uint32_t t = 0; t < k; ++t) dst[t] = src[t];
+      }
+    }
+  }
+  if (m->paired && !d.direct) {
+    std::memcpy(r->pe_r1 + c0, d.pe_r1 + c0, (size_t)n * sizeof(abg_hit));
+    std::memcpy(r->pe_r2 + c0, d.pe_r2 + c0, (size_t)n * sizeof(abg_hit));
+  }
+}
+
+// After everything has landed: error flag, CIGARs longer than kInlineOps (rare, fetched one by one).
+int finish_results(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t n) {
+  if (m->h_flags[0] != 0u)
+    return fail(ABG_ERR_CIGAR_OVERFLOW, "abg_map_batch: a CIGAR needed more than cigar_stride operations");
+  const uint32_t stride = m->params.cigar_stride;
+  const uint32_t w = std::min(kInlineOps, stride);
+  uint32_t *const u_cig[2] = {r->cigar1, r->cigar2};
+  for (int e = 0; e < (m->paired ? 2 : 1); ++e) {
+    if (!u_cig[e]) continue;
+    const uint32_t *nc = d.ncig[e];
+    size_t n_long = 0;
+    for (uint32_t i = 0; i < n; ++i) n_long += nc[i] > w;
+    if (n_long == 0) continue;
+    if (n_long <= 256) {
+      for (uint32_t i = 0; i < n; ++i)
+        if (nc[i] > w)
+          ABG_CUDA(cudaMemcpy(u_cig[e] + (size_t)i * stride, m->d_cigar[e] + (size_t)i * stride, (size_t)nc[i] * 4,
+                              cudaMemcpyDeviceToHost));
+    }
+    else {  // many long CIGARs (long reads, high indel rates): one bulk copy of the full-stride rows
+      std::vector<uint32_t> tmp((size_t)n * stride);
+      ABG_CUDA(cudaMemcpy(tmp.data(), m->d_cigar[e], tmp.size() * 4, cudaMemcpyDeviceToHost));
+      for (uint32_t i = 0; i < n; ++i)
+        if (nc[i] > w) std::memcpy(u_cig[e] + (size_t)i * stride, tmp.data() + (size_t)i * stride, (size_t)nc[i] * 4);
+    }
+  }
+  return ABG_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -190,6 +375,17 @@ void abg_index_destroy(abg_index *ix) {
 
 uint64_t abg_index_device_bytes(const abg_index *ix) { return ix ? ix->bytes : 0; }
 
+int abg_host_alloc(size_t bytes, void **out) {
+  if (!out) return fail(ABG_ERR_INVALID, "abg_host_alloc: null argument");
+  *out = nullptr;
+  ABG_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return ABG_OK;
+}
+
+void abg_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, uint32_t max_read_len,
                       int count_work, abg_mapper **out) {
   if (!ix || !p || !out || max_batch == 0) return fail(ABG_ERR_INVALID, "abg_mapper_create: bad argument");
@@ -208,6 +404,14 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   m->count_work = count_work != 0;
   const int n_ends = m->paired ? 2 : 1;
   const uint32_t stride = p->cigar_stride;
+  {
+    // sub-batch size of the pipelined abg_map_batch (copies of chunk j+1 overlap the kernel of chunk j)
+    const char *e = std::getenv("ABISMAL_B200_CHUNK");
+    const long v = e ? std::atol(e) : 0;
+    uint32_t c = v > 0 ? (uint32_t)v : 32768u;
+    const uint32_t min_c = (max_batch + kMaxChunks - 1) / kMaxChunks;
+    m->chunk = std::max(c, std::max(min_c, 1u));
+  }
 
 #define ABG_M(call)                                                                         \
   do {                                                                                      \
@@ -219,8 +423,18 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   } while (0)
 
   ABG_M(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  ABG_M(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
+  ABG_M(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+  ABG_M(cudaStreamCreateWithFlags(&m->s_run[0], cudaStreamNonBlocking));
+  ABG_M(cudaStreamCreateWithFlags(&m->s_run[1], cudaStreamNonBlocking));
   ABG_M(cudaEventCreate(&m->ev0));
   ABG_M(cudaEventCreate(&m->ev1));
+  ABG_M(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+  for (uint32_t k = 0; k < kMaxChunks; ++k) {
+    ABG_M(cudaEventCreateWithFlags(&m->ev_in[k], cudaEventDisableTiming));
+    ABG_M(cudaEventCreateWithFlags(&m->ev_k[k], cudaEventDisableTiming));
+    ABG_M(cudaEventCreateWithFlags(&m->ev_out[k], cudaEventDisableTiming));
+  }
 
   // launch shape: persistent grid, as many CTAs per SM as shared memory/registers allow
   m->smem = ab2dev::block_smem_bytes(m->ml, m->paired);
@@ -242,19 +456,22 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     return fail(ABG_ERR_CUDA, "abg_mapper_create: kernel does not fit on an SM");
   }
   m->grid = n_sm * per_sm;
-  const size_t slots = (size_t)m->grid * ab2dev::kWarpsPerBlock;
+  // two scratch sets: consecutive chunks run on alternating streams and may overlap at their tails
+  const size_t slots = (size_t)m->grid * ab2dev::kWarpsPerBlock * 2;
 
   m->seq_cap = (size_t)max_batch * max_read_len;
+  const uint32_t w = std::min(kInlineOps, stride);
   for (int e = 0; e < n_ends; ++e) {
     ABG_M(cudaMalloc(&m->d_seq[e], m->seq_cap + 16));
     ABG_M(cudaMalloc(&m->d_off[e], ((size_t)max_batch + 1) * 4));
     ABG_M(cudaMalloc(&m->d_se[e], (size_t)max_batch * sizeof(abg_hit)));
     ABG_M(cudaMalloc(&m->d_cigar[e], (size_t)max_batch * stride * 4));
     ABG_M(cudaMalloc(&m->d_ncigar[e], (size_t)max_batch * 4));
+    ABG_M(cudaMalloc(&m->d_cigar_inline[e], (size_t)max_batch * w * 4));
     ABG_M(cudaMallocHost(&m->h_seq[e], m->seq_cap + 16));
     ABG_M(cudaMallocHost(&m->h_off[e], ((size_t)max_batch + 1) * 4));
     ABG_M(cudaMallocHost(&m->h_se[e], (size_t)max_batch * sizeof(abg_hit)));
-    ABG_M(cudaMallocHost(&m->h_cigar[e], (size_t)max_batch * stride * 4));
+    ABG_M(cudaMallocHost(&m->h_cigar[e], (size_t)max_batch * w * 4));
     ABG_M(cudaMallocHost(&m->h_ncigar[e], (size_t)max_batch * 4));
   }
   if (m->paired) {
@@ -267,7 +484,7 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   }
   m->tb_words = ab2dev::tb_sm_words(m->ml);
   ABG_M(cudaMalloc(&m->d_tb, slots * 2 * m->tb_words * 32 * sizeof(uint64_t)));
-  ABG_M(cudaMalloc(&m->d_work, 2 * sizeof(unsigned int)));
+  ABG_M(cudaMalloc(&m->d_work, (kMaxChunks + 2) * sizeof(unsigned int)));
   ABG_M(cudaMallocHost(&m->h_flags, 2 * sizeof(unsigned int)));
   if (m->count_work) ABG_M(cudaMalloc(&m->d_counters, 6 * sizeof(unsigned long long)));
 #undef ABG_M
@@ -278,13 +495,14 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
 void abg_mapper_destroy(abg_mapper *m) {
   if (!m) return;
   cudaSetDevice(m->idx->device);
-  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaDeviceSynchronize();
   for (int e = 0; e < 2; ++e) {
     cudaFree(m->d_seq[e]);
     cudaFree(m->d_off[e]);
     cudaFree(m->d_se[e]);
     cudaFree(m->d_cigar[e]);
     cudaFree(m->d_ncigar[e]);
+    cudaFree(m->d_cigar_inline[e]);
     cudaFreeHost(m->h_seq[e]);
     cudaFreeHost(m->h_off[e]);
     cudaFreeHost(m->h_se[e]);
@@ -303,14 +521,38 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFreeHost(m->h_flags);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->ev_start) cudaEventDestroy(m->ev_start);
+  for (uint32_t k = 0; k < kMaxChunks; ++k) {
+    if (m->ev_in[k]) cudaEventDestroy(m->ev_in[k]);
+    if (m->ev_k[k]) cudaEventDestroy(m->ev_k[k]);
+    if (m->ev_out[k]) cudaEventDestroy(m->ev_out[k]);
+  }
   if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->s_h2d) cudaStreamDestroy(m->s_h2d);
+  if (m->s_d2h) cudaStreamDestroy(m->s_d2h);
+  if (m->s_run[0]) cudaStreamDestroy(m->s_run[0]);
+  if (m->s_run[1]) cudaStreamDestroy(m->s_run[1]);
   delete m;
 }
 
+namespace {
+
+int check_batch(const abg_mapper *m, const abg_batch *b, const char *who) {
+  if (!m || !b || !b->seq1 || !b->off1) return fail(ABG_ERR_INVALID, std::string(who) + ": null argument");
+  if (b->n > m->max_batch) return fail(ABG_ERR_INVALID, std::string(who) + ": batch larger than max_batch");
+  if (m->paired && (!b->seq2 || !b->off2)) return fail(ABG_ERR_INVALID, std::string(who) + ": paired mode needs two ends");
+  const uint32_t *offs[2] = {b->off1, b->off2};
+  for (int e = 0; e < (m->paired ? 2 : 1); ++e)
+    if ((size_t)(offs[e][b->n] - offs[e][0]) > m->seq_cap)
+      return fail(ABG_ERR_TOO_LONG, std::string(who) + ": batch sequence bytes exceed capacity");
+  return ABG_OK;
+}
+
+}  // namespace
+
 int abg_mapper_upload(abg_mapper *m, const abg_batch *b) {
-  if (!m || !b || !b->seq1 || !b->off1) return fail(ABG_ERR_INVALID, "abg_mapper_upload: null argument");
-  if (b->n > m->max_batch) return fail(ABG_ERR_INVALID, "abg_mapper_upload: batch larger than max_batch");
-  if (m->paired && (!b->seq2 || !b->off2)) return fail(ABG_ERR_INVALID, "abg_mapper_upload: paired mode needs two ends");
+  int rc;
+  if ((rc = check_batch(m, b, "abg_mapper_upload")) != ABG_OK) return rc;
   ABG_CUDA(cudaSetDevice(m->idx->device));
   const int n_ends = m->paired ? 2 : 1;
   const char *seqs[2] = {b->seq1, b->seq2};
@@ -318,17 +560,13 @@ int abg_mapper_upload(abg_mapper *m, const abg_batch *b) {
   for (int e = 0; e < n_ends; ++e) {
     const uint32_t *off = offs[e];
     const size_t bytes = off[b->n] - off[0];
-    if (bytes > m->seq_cap) return fail(ABG_ERR_TOO_LONG, "abg_mapper_upload: batch sequence bytes exceed capacity");
-    for (uint32_t i = 0; i < b->n; ++i) {
-      const uint32_t len = off[i + 1] - off[i];
-      if (len > m->max_read_len) return fail(ABG_ERR_TOO_LONG, "abg_mapper_upload: read longer than max_read_len");
-      if (len != 0 && len < 44)
-        return fail(ABG_ERR_INVALID, "abg_mapper_upload: reads shorter than 44 bases must be passed as empty");
-      m->h_off[e][i] = off[i] - off[0];
+    if ((rc = stage_offsets(m, off, 0, b->n, m->h_off[e])) != ABG_OK) return rc;
+    const char *src = seqs[e] + off[0];
+    if (!is_pinned(src)) {
+      std::memcpy(m->h_seq[e], src, bytes);
+      src = m->h_seq[e];
     }
-    m->h_off[e][b->n] = off[b->n] - off[0];
-    std::memcpy(m->h_seq[e], seqs[e] + off[0], bytes);
-    ABG_CUDA(cudaMemcpyAsync(m->d_seq[e], m->h_seq[e], bytes, cudaMemcpyHostToDevice, m->stream));
+    ABG_CUDA(cudaMemcpyAsync(m->d_seq[e], src, bytes, cudaMemcpyHostToDevice, m->stream));
     ABG_CUDA(cudaMemcpyAsync(m->d_off[e], m->h_off[e], ((size_t)b->n + 1) * 4, cudaMemcpyHostToDevice, m->stream));
   }
   m->cur_n = b->n;
@@ -339,41 +577,12 @@ int abg_mapper_run(abg_mapper *m) {
   if (!m) return fail(ABG_ERR_INVALID, "abg_mapper_run: null mapper");
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ab2dev::KernelParams P;
-  std::memset(&P, 0, sizeof P);
-  P.ix = m->idx->dev;
-  P.n = m->cur_n;
-  for (int e = 0; e < 2; ++e) {
-    P.seq[e] = m->d_seq[e];
-    P.off[e] = m->d_off[e];
-    P.se[e] = m->d_se[e];
-    P.cigar[e] = m->d_cigar[e];
-    P.n_cigar[e] = m->d_ncigar[e];
-  }
-  P.pe_r1 = m->d_pe_r1;
-  P.pe_r2 = m->d_pe_r2;
-  P.cigar_stride = m->params.cigar_stride;
-  P.mode = m->params.mode;
-  P.allow_ambig = m->params.allow_ambig;
-  P.min_dist = m->params.min_dist;
-  P.max_dist = m->params.max_dist;
-  P.max_candidates = m->params.max_candidates ? m->params.max_candidates : m->idx->dev.max_candidates;
-  P.valid_frac = m->params.valid_frac;
-  P.ml = m->ml;
-  P.pe_overflow = m->d_pe_overflow;
-  P.mem_scr = m->d_mem_scr;
-  P.tb = m->d_tb;
-  P.tb_words = m->tb_words;
-  P.work_counter = m->d_work;
-  P.error_flag = m->d_work + 1;
-  P.counters = m->d_counters;
+  fill_params(m, P, 0, m->cur_n, m->d_work + 1);
   ABG_CUDA(cudaMemsetAsync(m->d_work, 0, 2 * sizeof(unsigned int), m->stream));
   if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->stream));
   ABG_CUDA(cudaEventRecord(m->ev0, m->stream));
-  if (P.n > 0) {
-    const int grid = (int)std::min<uint64_t>((uint64_t)m->grid, ((uint64_t)P.n + ab2dev::kWarpsPerBlock - 1) / ab2dev::kWarpsPerBlock);
-    void *args[] = {&P};
-    ABG_CUDA(cudaLaunchKernel(m->kernel, dim3(grid), dim3(ab2dev::kThreadsPerBlock), args, m->smem, m->stream));
-  }
+  int rc;
+  if ((rc = launch(m, P, m->stream)) != ABG_OK) return rc;
   ABG_CUDA(cudaEventRecord(m->ev1, m->stream));
   m->timed = true;
   return ABG_OK;
@@ -391,21 +600,15 @@ int abg_mapper_sync(abg_mapper *m) {
 }
 
 int abg_mapper_download(abg_mapper *m, abg_results *r) {
-  if (!m || !r || !r->se1) return fail(ABG_ERR_INVALID, "abg_mapper_download: null argument");
+  if (!m || !r || !r->se1 || !r->n_cigar1) return fail(ABG_ERR_INVALID, "abg_mapper_download: null argument");
+  if (m->paired && (!r->pe_r1 || !r->pe_r2 || !r->se2 || !r->n_cigar2))
+    return fail(ABG_ERR_INVALID, "abg_mapper_download: paired results need pe_r1/pe_r2/se2/n_cigar2");
   ABG_CUDA(cudaSetDevice(m->idx->device));
   const uint32_t n = m->cur_n;
-  const uint32_t stride = m->params.cigar_stride;
-  const int n_ends = m->paired ? 2 : 1;
-  for (int e = 0; e < n_ends; ++e) {
-    ABG_CUDA(cudaMemcpyAsync(m->h_se[e], m->d_se[e], (size_t)n * sizeof(abg_hit), cudaMemcpyDeviceToHost, m->stream));
-    ABG_CUDA(cudaMemcpyAsync(m->h_cigar[e], m->d_cigar[e], (size_t)n * stride * 4, cudaMemcpyDeviceToHost, m->stream));
-    ABG_CUDA(cudaMemcpyAsync(m->h_ncigar[e], m->d_ncigar[e], (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
-  }
-  if (m->paired) {
-    ABG_CUDA(cudaMemcpyAsync(m->h_pe_r1, m->d_pe_r1, (size_t)n * sizeof(abg_hit), cudaMemcpyDeviceToHost, m->stream));
-    ABG_CUDA(cudaMemcpyAsync(m->h_pe_r2, m->d_pe_r2, (size_t)n * sizeof(abg_hit), cudaMemcpyDeviceToHost, m->stream));
-  }
-  ABG_CUDA(cudaMemcpyAsync(m->h_flags, m->d_work, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, m->stream));
+  const ResultDst d = pick_result_dst(m, r);
+  int rc;
+  if ((rc = copy_results_async(m, d, 0, n, m->stream)) != ABG_OK) return rc;
+  ABG_CUDA(cudaMemcpyAsync(m->h_flags, m->d_work, sizeof(unsigned int), cudaMemcpyDeviceToHost, m->stream));
   if (m->d_counters)
     ABG_CUDA(cudaMemcpyAsync(&m->counters, m->d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              m->stream));
@@ -414,31 +617,88 @@ int abg_mapper_download(abg_mapper *m, abg_results *r) {
     m->last_ms = 0.f;
     (void)cudaGetLastError();  // do not leave a stale error behind
   }
-  if (m->h_flags[1] != 0u)
-    return fail(ABG_ERR_CIGAR_OVERFLOW, "abg_map_batch: a CIGAR needed more than cigar_stride operations");
-  std::memcpy(r->se1, m->h_se[0], (size_t)n * sizeof(abg_hit));
-  if (r->cigar1) std::memcpy(r->cigar1, m->h_cigar[0], (size_t)n * stride * 4);
-  if (r->n_cigar1) std::memcpy(r->n_cigar1, m->h_ncigar[0], (size_t)n * 4);
-  if (m->paired) {
-    if (!r->pe_r1 || !r->pe_r2 || !r->se2) return fail(ABG_ERR_INVALID, "abg_mapper_download: paired results need pe_r1/pe_r2/se2");
-    std::memcpy(r->pe_r1, m->h_pe_r1, (size_t)n * sizeof(abg_hit));
-    std::memcpy(r->pe_r2, m->h_pe_r2, (size_t)n * sizeof(abg_hit));
-    std::memcpy(r->se2, m->h_se[1], (size_t)n * sizeof(abg_hit));
-    if (r->cigar2) std::memcpy(r->cigar2, m->h_cigar[1], (size_t)n * stride * 4);
-    if (r->n_cigar2) std::memcpy(r->n_cigar2, m->h_ncigar[1], (size_t)n * 4);
-  }
-  return ABG_OK;
+  scatter_results(m, d, r, 0, n);
+  return finish_results(m, d, r, n);
 }
 
+// Host buffers in, host buffers out.  The batch is cut into sub-batches that flow through three streams:
+// H2D copy of chunk j+1 | kernel of chunk j | D2H copy of chunk j-1, so that only the first copy in and the
+// last copy out are exposed.  Pinned caller buffers (abg_host_alloc) are used in place; pageable ones are
+// staged through the mapper's pinned buffers chunk by chunk, which overlaps too.
 int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
   int rc;
-  if ((rc = abg_mapper_upload(m, b)) != ABG_OK) return rc;
-  if ((rc = abg_mapper_run(m)) != ABG_OK) return rc;
-  return abg_mapper_download(m, r);
+  if ((rc = check_batch(m, b, "abg_map_batch")) != ABG_OK) return rc;
+  if (!r || !r->se1 || !r->n_cigar1) return fail(ABG_ERR_INVALID, "abg_map_batch: null results");
+  if (m->paired && (!r->pe_r1 || !r->pe_r2 || !r->se2 || !r->n_cigar2))
+    return fail(ABG_ERR_INVALID, "abg_map_batch: paired results need pe_r1/pe_r2/se2/n_cigar2");
+  ABG_CUDA(cudaSetDevice(m->idx->device));
+  const uint32_t n = b->n;
+  m->cur_n = n;
+  m->timed = false;
+  const int n_ends = m->paired ? 2 : 1;
+  const char *seqs[2] = {b->seq1, b->seq2};
+  const uint32_t *offs[2] = {b->off1, b->off2};
+  bool seq_pinned[2] = {is_pinned(b->seq1), m->paired && is_pinned(b->seq2)};
+  const ResultDst d = pick_result_dst(m, r);
+  const uint32_t chunk = std::max(m->chunk, (n + kMaxChunks - 1) / kMaxChunks);
+  const uint32_t n_chunks = n ? (n + chunk - 1) / chunk : 0;
+
+  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, (kMaxChunks + 2) * sizeof(unsigned int), m->s_h2d));
+  if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->s_h2d));
+  const size_t slot_sets = (size_t)m->grid * ab2dev::kWarpsPerBlock;
+  for (uint32_t j = 0; j < n_chunks; ++j) {
+    const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
+    for (int e = 0; e < n_ends; ++e) {
+      const uint32_t *off = offs[e];
+      if ((rc = stage_offsets(m, off, c0, c1, m->h_off[e])) != ABG_OK) {
+        cudaDeviceSynchronize();
+        return rc;
+      }
+      const size_t o0 = off[c0] - off[0], bytes = off[c1] - off[c0];
+      const char *src = seqs[e] + off[c0];
+      if (!seq_pinned[e]) {
+        std::memcpy(m->h_seq[e] + o0, src, bytes);
+        src = m->h_seq[e] + o0;
+      }
+      if (bytes) ABG_CUDA(cudaMemcpyAsync(m->d_seq[e] + o0, src, bytes, cudaMemcpyHostToDevice, m->s_h2d));
+      ABG_CUDA(cudaMemcpyAsync(m->d_off[e] + c0, m->h_off[e] + c0, ((size_t)(c1 - c0) + 1) * 4, cudaMemcpyHostToDevice,
+                               m->s_h2d));
+    }
+    ABG_CUDA(cudaEventRecord(m->ev_in[j], m->s_h2d));
+    cudaStream_t sr = m->s_run[j & 1];
+    ABG_CUDA(cudaStreamWaitEvent(sr, m->ev_in[j], 0));
+    ab2dev::KernelParams P;
+    fill_params(m, P, c0, c1 - c0, m->d_work + 1 + j);
+    // scratch set of this stream
+    if (j & 1) {
+      if (P.pe_overflow) P.pe_overflow += slot_sets * 2 * ab2dev::kPeLarge;
+      if (P.mem_scr) P.mem_scr += slot_sets * ab2dev::kPeLarge;
+      P.tb += slot_sets * 2 * m->tb_words * 32;
+    }
+    if ((rc = launch(m, P, sr)) != ABG_OK) return rc;
+    ABG_CUDA(cudaEventRecord(m->ev_k[j], sr));
+    ABG_CUDA(cudaStreamWaitEvent(m->s_d2h, m->ev_k[j], 0));
+    if ((rc = copy_results_async(m, d, c0, c1 - c0, m->s_d2h)) != ABG_OK) return rc;
+    ABG_CUDA(cudaEventRecord(m->ev_out[j], m->s_d2h));
+  }
+  if (n_chunks == 0) ABG_CUDA(cudaStreamSynchronize(m->s_h2d));
+  ABG_CUDA(cudaMemcpyAsync(m->h_flags, m->d_work, sizeof(unsigned int), cudaMemcpyDeviceToHost, m->s_d2h));
+  if (m->d_counters)
+    ABG_CUDA(cudaMemcpyAsync(&m->counters, m->d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             m->s_d2h));
+  // host side of each sub-batch as it lands, while the GPU works on the later ones
+  for (uint32_t j = 0; j < n_chunks; ++j) {
+    const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
+    ABG_CUDA(cudaEventSynchronize(m->ev_out[j]));
+    scatter_results(m, d, r, c0, c1 - c0);
+  }
+  ABG_CUDA(cudaStreamSynchronize(m->s_d2h));
+  return finish_results(m, d, r, n);
 }
 
 float abg_mapper_last_kernel_ms(const abg_mapper *m) { return m ? m->last_ms : 0.f; }
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m) { return (m && m->cur_n) ? 1u : 0u; }
+uint32_t abg_mapper_chunk(const abg_mapper *m) { return m ? m->chunk : 0u; }
 
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out) {
   if (!m || !out) return fail(ABG_ERR_INVALID, "abg_mapper_get_counters: null argument");

@@ -82,7 +82,8 @@ struct KernelParams {
   abg_hit *pe_r1, *pe_r2, *se[2];
   uint32_t *cigar[2];
   uint32_t *n_cigar[2];
-  uint32_t cigar_stride;
+  uint32_t *cigar_inline[2];  // [n][inline_ops]: the first operations of every CIGAR, the part copied back in bulk
+  uint32_t cigar_stride, inline_ops;
   // params
   uint32_t mode, allow_ambig, min_dist, max_dist, max_candidates;
   double valid_frac;
@@ -1627,6 +1628,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) map_reads_kernel(const
         P.n_cigar[0][item] = cg_n;
         if (cg_n > P.cigar_stride) atomicExch(P.error_flag, 1u);
       }
+      __syncwarp();
+      if ((uint32_t)lane < P.inline_ops)
+        P.cigar_inline[0][(size_t)item * P.inline_ops + lane] = P.cigar[0][(size_t)item * P.cigar_stride + lane];
     }
     else {
       // map_paired_ended<conv> / map_paired_ended_rand (abismal.cpp:1887-2185)
@@ -1705,6 +1709,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) map_reads_kernel(const
         P.n_cigar[0][item] = cg[0].n;
         P.n_cigar[1][item] = cg[1].n;
         if (cg[0].n > cg[0].stride || cg[1].n > cg[1].stride) atomicExch(P.error_flag, 1u);
+      }
+      __syncwarp();
+      if ((uint32_t)lane < P.inline_ops) {
+        P.cigar_inline[0][(size_t)item * P.inline_ops + lane] = cg[0].ops[lane];
+        P.cigar_inline[1][(size_t)item * P.inline_ops + lane] = cg[1].ops[lane];
       }
     }
     __syncwarp();

@@ -26,6 +26,17 @@ class ReadBatch:
         b.max_len = int(np.diff(self.off[lo:hi + 1].astype(np.int64)).max()) if hi > lo else 0
         return b
 
+    def to_pinned(self):
+        """Copy of this batch whose arrays live in page-locked memory (abg_host_alloc)."""
+        from .capi import pinned_zeros
+        b = ReadBatch.__new__(ReadBatch)
+        b.names, b.n, b.max_len = self.names, self.n, self.max_len
+        b.off = pinned_zeros(self.off.shape, np.uint32)
+        b.off[...] = self.off
+        b.seq = pinned_zeros(self.seq.shape, np.uint8)
+        b.seq[...] = self.seq
+        return b
+
     def sequence(self, i):
         return self.seq[int(self.off[i]):int(self.off[i + 1])].tobytes().decode()
 

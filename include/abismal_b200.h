@@ -150,8 +150,19 @@ int abg_mapper_create(abg_index *idx, const abg_params *params, uint32_t max_bat
                       uint32_t max_read_len, int count_work, abg_mapper **out);
 void abg_mapper_destroy(abg_mapper *m);
 
-/* Host buffers in, host buffers out (H2D copy, kernels, D2H copy, sync). */
+/* Page-locked host memory for batch and result buffers.  Buffers from here are
+ * DMA'd in place; pageable buffers work too but are staged through the
+ * mapper's own pinned memory (one extra host copy). */
+int abg_host_alloc(size_t bytes, void **out);
+void abg_host_free(void *p);
+
+/* Host buffers in, host buffers out.  Internally the batch is cut into
+ * sub-batches (abg_mapper_chunk reads) pipelined over three streams, so the
+ * H2D copy of one sub-batch, the kernel of the previous and the D2H copy of the
+ * one before overlap.  Of every CIGAR only the operations actually used are
+ * written to results->cigar*; the rest of each cigar_stride row is untouched. */
 int abg_map_batch(abg_mapper *m, const abg_batch *batch, abg_results *results);
+uint32_t abg_mapper_chunk(const abg_mapper *m);
 
 /* Split form used to time the device part alone: upload once, run many. */
 int abg_mapper_upload(abg_mapper *m, const abg_batch *batch);

@@ -169,3 +169,30 @@ def test_cli_small_gpu_batches_and_gz(workspace, gpu):
                                                         "tests/rep_pe_1.fq.gz", "tests/rep_pe_2.fq.gz"])
     assert helpers.sam_body(a)[3:] == helpers.sam_body(b)[3:]
     assert open(ast_).read() == open(bst).read()
+
+
+def test_pipelined_chunks_and_pinned_buffers(workspace, rep_index, gpu, monkeypatch):
+    """abg_map_batch pipelines sub-batches over three streams; results must not depend on the
+    sub-batch size nor on whether the caller's buffers are pinned (DMA in place) or pageable (staged)."""
+    from abismal_b200 import Mapper
+    from abismal_b200.capi import Results
+    ixf, ix = rep_index
+    b1, b2 = _fq(workspace, "rep_pe_1.fq"), _fq(workspace, "rep_pe_2.fq")
+    m = Mapper(ix, mode=1, max_batch=b1.n, max_read_len=160)
+    want = m.map_batch(b1, b2)
+    m.close()
+    monkeypatch.setenv("ABISMAL_B200_CHUNK", "777")
+    mc = Mapper(ix, mode=1, max_batch=b1.n, max_read_len=160)
+    assert mc.lib.abg_mapper_chunk(mc._h) == 777
+    got = mc.map_batch(b1, b2)
+    helpers.assert_results_equal(got, want, True)
+    p1, p2 = b1.to_pinned(), b2.to_pinned()
+    res = Results(b1.n, True, mc.stride, pinned=True)
+    for _ in range(2):
+        mc.map_batch(p1, p2, res)
+    helpers.assert_results_equal(res, want, True)
+    # split API on the same mapper
+    mc.upload(p1, p2)
+    mc.run()
+    helpers.assert_results_equal(mc.download(b1.n), want, True)
+    mc.close()
