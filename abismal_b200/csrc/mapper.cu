@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int kDefaultMinB = 2;
+constexpr int kDefaultMinB = 3;
 
 thread_local std::string g_err;
 
@@ -69,11 +69,13 @@ int upload(const T *host, uint64_t n, uint64_t n_alloc, T **dev) {
 struct abg_index {
   int device = 0;
   ab2dev::IndexDev dev{};
-  uint64_t bytes = 0;
+  uint64_t bytes = 0, bytes_extra = 0;
   uint64_t *genome = nullptr;
   uint32_t *counter = nullptr, *counter_t = nullptr, *counter_a = nullptr;
   uint32_t *index = nullptr, *index_t = nullptr, *index_a = nullptr;
   uint32_t *bits = nullptr, *bits_t = nullptr, *bits_a = nullptr;
+  uint64_t *g2 = nullptr;
+  uint32_t *gx = nullptr;
 };
 
 constexpr uint32_t kInlineOps = 16;   // CIGAR ops per read copied back with the batch; longer ones are fetched afterwards
@@ -340,6 +342,26 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
     abg_index_destroy(ix);
     return rc;
   }
+  {  // 2-bit genome copy + exception bitmap for the candidate compare
+    const uint64_t n2 = (v->genome_words + 1) / 2 + 8;  // spare zero words: look-ahead of the last windows
+    const uint64_t nx = (n2 * 32 / 256 + 31) / 32 + 2;
+    cudaError_t e1 = cudaMalloc(reinterpret_cast<void **>(&ix->g2), n2 * 8);
+    cudaError_t e2 = cudaMalloc(reinterpret_cast<void **>(&ix->gx), nx * 4);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      abg_index_destroy(ix);
+      return fail(ABG_ERR_CUDA, "abg_index_create: out of device memory for the 2-bit genome");
+    }
+    cudaMemset(ix->gx, 0, nx * 4);
+    ab2dev::pack_genome2_kernel<<<148 * 8, 256>>>(ix->genome, v->genome_words + 4, n2, ix->g2, ix->gx);
+    const cudaError_t e3 = cudaDeviceSynchronize();
+    if (e3 != cudaSuccess) {
+      abg_index_destroy(ix);
+      return fail(ABG_ERR_CUDA, std::string("pack_genome2_kernel: ") + cudaGetErrorString(e3));
+    }
+    ix->dev.g2 = ix->g2;
+    ix->dev.gx = ix->gx;
+    ix->bytes_extra = n2 * 8 + nx * 4;
+  }
   ix->dev.bits = ix->bits;
   ix->dev.bits_t = ix->bits_t;
   ix->dev.bits_a = ix->bits_a;
@@ -370,10 +392,12 @@ void abg_index_destroy(abg_index *ix) {
   cudaFree(ix->bits);
   cudaFree(ix->bits_t);
   cudaFree(ix->bits_a);
+  cudaFree(ix->g2);
+  cudaFree(ix->gx);
   delete ix;
 }
 
-uint64_t abg_index_device_bytes(const abg_index *ix) { return ix ? ix->bytes : 0; }
+uint64_t abg_index_device_bytes(const abg_index *ix) { return ix ? ix->bytes + ix->bytes_extra : 0; }
 
 int abg_host_alloc(size_t bytes, void **out) {
   if (!out) return fail(ABG_ERR_INVALID, "abg_host_alloc: null argument");

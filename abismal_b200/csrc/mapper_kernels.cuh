@@ -56,7 +56,8 @@ constexpr int kPeSmall = 32;        // pe_candidates::max_size_small
 constexpr int kPeLarge = 32 << 10;  // pe_candidates::max_size_large
 constexpr int kPeSmemSlots = 128;   // PE heap entries kept in shared memory
 constexpr int kMaxDiffs = 32767;
-constexpr int kCand = 4;            // candidates per lane per compare chunk (tight bound; 2 under a loose bound)
+constexpr int kCand = 1;            // candidates per lane per compare round (the memory system saturates at ~120
+                                    // sectors in flight per SM: one 5-word gather per lane is plenty)
 constexpr int kLogCap = 128;          // survivor-log entries per pass (specific -> sensitive reuse)
 constexpr int kLogMaxLen = 1023;     // reads longer than this do not use the log (9-bit offset field)
 constexpr int kTbLanesSm = 8;       // traceback words of lanes < 8 (band <= 16) stay in shared memory
@@ -69,6 +70,12 @@ struct IndexDev {
   // bit k set <=> bucket k of the table is non-empty (counter[k+1] != counter[k]); small enough to stay in L2.
   // A null pointer means "probe the counters directly" (dense tables, where the bitmap would save nothing).
   const uint32_t *bits, *bits_t, *bits_a;
+  // 2-bit copy of the genome for the candidate compare: word w holds bases 32w..32w+31, bit j of the low half =
+  // code bit 0 and of the high half = code bit 1 of base 32w+j (A0 C1 G2 T3; anything else reads as A and is
+  // flagged).  gx: bit b set <=> the 256-base block b holds a base that is not A/C/G/T (N, IUPAC); candidates
+  // whose window touches a flagged block take the exact 4-bit compare instead.
+  const uint64_t *g2;
+  const uint32_t *gx;
   uint32_t max_candidates;
 };
 
@@ -166,8 +173,8 @@ static_assert(sizeof(KernelParams) <= kParamBytes, "KernelParams must fit its sh
 __host__ __device__ __forceinline__ uint32_t tb_sm_words(uint32_t ml) { return (ml + 64u + 32u + 15u) / 16u; }
 
 struct WarpLayout {
-  uint32_t o_packed, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, total;
-  uint32_t plane_words, elig_words;
+  uint32_t o_packed, o_masks, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, total;
+  uint32_t plane_words, elig_words, mask_words;
 };
 
 __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool paired) {
@@ -190,6 +197,9 @@ __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool pai
   L.elig_words = ml / 64u + 1u;              // specific offsets are < readlen / 2
   L.o_elig = o;
   o += 2u * L.elig_words * 4u;
+  L.mask_words = ml / 32u + 1u;
+  L.o_masks = o;
+  o += 4u * L.mask_words * 4u;               // read-vs-{A,C,G,T} match masks per 32-base chunk
   L.plane_words = ml / 32u + 2u;
   L.o_planes = o;
   o += 3u * L.plane_words * 4u;
@@ -234,6 +244,7 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   __device__ __forceinline__ uint8_t *base(int e) const { return base_ptr + L.o_base + (size_t)e * params().ml; }
   __device__ __forceinline__ uint8_t *qcode(int e) const { return base_ptr + L.o_qcode + (size_t)e * (params().ml + 32u); }
   __device__ __forceinline__ uint8_t *refb() const { return base_ptr + L.o_refb; }
+  __device__ __forceinline__ uint32_t *masks(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_masks) + k * L.mask_words; }
   __device__ __forceinline__ uint32_t *log_pos() const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_log); }
   __device__ __forceinline__ uint32_t *log_meta() const { return log_pos() + kLogCap; }
   __device__ __forceinline__ uint32_t *elig(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_elig) + k * L.elig_words; }
@@ -491,6 +502,24 @@ __device__ __noinline__ void build_packed(int end, uint32_t flags) {
       p3b[w] = mb;
     }
   }
+  // match masks against the 2-bit genome: bit j of masks(X)[c] <=> read base 32c+j matches genome base X
+  // (code & one-hot(X)); the 0xF tail of the last packed word matches everything, positions past it nothing.
+  {
+    uint32_t *mA = W.masks(0), *mC = W.masks(1), *mG = W.masks(2), *mT = W.masks(3);
+    const uint32_t n_tail = 16u * nw;
+    for (uint32_t c = 0; c < W.L.mask_words; ++c) {
+      const uint32_t i = 32 * c + W.lane;
+      const uint32_t code = i < n ? q[i] : (i < n_tail ? 0xFu : 0u);
+      const unsigned a = __ballot_sync(FULL, code & 1u), cc = __ballot_sync(FULL, code & 2u);
+      const unsigned g = __ballot_sync(FULL, code & 4u), t = __ballot_sync(FULL, code & 8u);
+      if (W.lane == 0) {
+        mA[c] = a;
+        mC[c] = cc;
+        mG[c] = g;
+        mT[c] = t;
+      }
+    }
+  }
   if (W.lane == 0) S->packed_key = key;
   __syncwarp();
 }
@@ -591,20 +620,51 @@ __device__ __forceinline__ uint64_t window_word(uint64_t g0, uint64_t g1, uint32
   return (g0 >> off) | ((g1 << (63u - off)) << 1);
 }
 
-// One compare chunk: kCand candidates per lane, candidate (k, lane) = canonical index c0 + 32k + lane.
-// S0 = packed words compared in the first stage (S0 + 1 genome words gathered at once per candidate).
-// full_compare (abismal.cpp:1105-1122) stops at the first word after which the running distance exceeds the
-// cutoff; a word can contribute a NEGATIVE amount (multi-bit IUPAC genome codes give popcounts > 16), so a
-// candidate is accepted iff the MAXIMUM prefix sum pm is <= the cutoff, and then d is the full sum.
-template <int KC, int S0>
+// full_compare (abismal.cpp:1105-1122) on the 4-bit genome, word by word.  It stops at the first word after
+// which the running distance exceeds the cutoff, and a word can contribute a NEGATIVE amount (multi-bit IUPAC
+// genome codes give popcounts > 16): a candidate is accepted iff the MAXIMUM prefix sum pm is <= the cutoff,
+// and then d is the full sum.  Used only for candidates whose window holds a base that is not A/C/G/T.
+__device__ __noinline__ int exact_compare(uint32_t the_pos, int n_words, int bound, int *pm_out) {
+  const Warp W;
+  const uint64_t *packed = W.packed();
+  const uint64_t *g = params().ix.genome + (the_pos >> 4);
+  const uint32_t off = (the_pos & 15u) << 2;
+  int d = 0, pm = 0;
+  uint64_t cur = __ldg(g);
+  for (int w = 0; w < n_words && pm <= bound; ++w) {
+    const uint64_t nxt = __ldg(g + w + 1);
+    d += 16 - __popcll(packed[w] & window_word(cur, nxt, off));
+    pm = max(pm, d);
+    cur = nxt;
+  }
+  *pm_out = pm;
+  return d;
+}
+
+// 32 match bits of chunk c: genome code planes (lo, hi) of the 32 bases select among the read's four masks
+__device__ __forceinline__ uint32_t match_bits(uint32_t lo, uint32_t hi, uint32_t mA, uint32_t mC, uint32_t mG,
+                                               uint32_t mT) {
+  const uint32_t x0 = (lo & mC) | (~lo & mA);  // hi == 0: A or C
+  const uint32_t x1 = (lo & mT) | (~lo & mG);  // hi == 1: G or T
+  return (hi & x1) | (~hi & x0);
+}
+
+// One compare chunk: KC candidates per lane, candidate (k, lane) = canonical index c0 + 32k + lane, compared
+// against the 2-bit genome.  NC0 = 32-base chunks compared in the first stage (NC0 + 1 words gathered at once
+// per candidate, all before any use); later stages add two chunks at a time while the distance is within the
+// bound.  Every base pair contributes 0 or 1 here, so the running distance is monotone and pm == d.
+template <int KC, int NC0>
 __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
-                                              const uint64_t *packed, int n_words, int bound, uint32_t c0,
+                                              const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
+                                              const uint32_t *mT, int n_words, int bound, uint32_t c0,
                                               uint32_t total, uint32_t base_off, uint32_t incl, uint32_t tot,
                                               uint32_t n2, uint32_t s2, uint32_t s3, int lane, int (&d)[KC],
                                               int (&pm)[KC], uint32_t (&the_pos)[KC], uint32_t (&sub)[KC],
                                               unsigned long long &n_entry,
                                               unsigned long long &n_word) {
   bool valid[KC];
+  const int n_bases = 16 * n_words;          // compared positions incl. the 0xF tail of the last packed word
+  const int n_chunks = (n_bases + 31) >> 5;
   // ---- owners + index gathers (KC independent loads per lane) ----
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
@@ -635,62 +695,84 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
 #pragma unroll
   for (int k = 0; k < KC; ++k) the_pos[k] -= sub[k] & 0x7fffffffu;
 
-  // ---- stage 0: S0 + 1 genome words per candidate, all gathers issued before any use ----
-  uint64_t g[KC][S0 + 1];
+  // ---- stage 0: NC0 + 1 words of the 2-bit genome per candidate + its exception bits ----
+  uint64_t g[KC][NC0 + 1];
+  bool exc[KC];
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
-    const uint64_t *gp = ix.genome + (the_pos[k] >> 4);
+    const uint64_t *gp = ix.g2 + (the_pos[k] >> 5);
 #pragma unroll
-    for (int j = 0; j <= S0; ++j) g[k][j] = (valid[k] && j <= n_words) ? __ldg(gp + j) : 0ull;
+    for (int j = 0; j <= NC0; ++j) g[k][j] = (valid[k] && j <= n_chunks) ? __ldg(gp + j) : 0ull;
+    exc[k] = false;
+    if (valid[k]) {
+      const uint32_t b0 = the_pos[k] >> 8, b1 = (the_pos[k] + (uint32_t)n_bases - 1u) >> 8;
+      if (b1 - b0 <= 1u && (b0 >> 5) == (b1 >> 5))  // the usual case: one probe of the (L2-resident) bitmap
+        exc[k] = ((__ldg(ix.gx + (b0 >> 5)) >> (b0 & 31u)) & (1u | (1u << (b1 - b0)))) != 0u;
+      else
+        for (uint32_t b = b0; b <= b1; ++b) exc[k] = exc[k] || ((__ldg(ix.gx + (b >> 5)) >> (b & 31u)) & 1u);
+    }
   }
   uint64_t carry[KC];
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
-    const uint32_t off = (the_pos[k] & 15u) << 2;
-    int dd = 0, mx = 0;
+    const uint32_t sh = the_pos[k] & 31u;
+    int dd = 0;
 #pragma unroll
-    for (int j = 0; j < S0; ++j)
-      if (j < n_words) {
-        dd += 16 - __popcll(packed[j] & window_word(g[k][j], g[k][j + 1], off));
-        mx = max(mx, dd);
+    for (int c = 0; c < NC0; ++c)
+      if (c < n_chunks) {
+        const uint32_t lo = __funnelshift_r((uint32_t)g[k][c], (uint32_t)g[k][c + 1], sh);
+        const uint32_t hi = __funnelshift_r((uint32_t)(g[k][c] >> 32), (uint32_t)(g[k][c + 1] >> 32), sh);
+        dd += min(32, n_bases - 32 * c) - __popc(match_bits(lo, hi, mA[c], mC[c], mG[c], mT[c]));
       }
     d[k] = dd;
-    pm[k] = valid[k] ? mx : (1 << 30);
-    carry[k] = g[k][S0];
+    pm[k] = valid[k] ? dd : (1 << 30);
+    carry[k] = g[k][NC0];
     if (valid[k]) {
       n_entry += 1;
-      n_word += (unsigned long long)min(S0, n_words);
+      n_word += (unsigned long long)min(NC0, n_chunks);
     }
   }
-  // ---- later stages: two more words for every candidate still within the bound ----
-  for (int w = S0; w < n_words; w += 2) {
+  // ---- later stages: two more chunks for every candidate still within the bound ----
+  for (int c = NC0; c < n_chunks; c += 2) {
     uint64_t a[KC], b[KC];
     bool alive[KC], any = false;
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-      alive[k] = pm[k] <= bound;
+      alive[k] = pm[k] <= bound && !exc[k];
       any = any || alive[k];
-      const uint64_t *gp = ix.genome + (the_pos[k] >> 4) + w;
+      const uint64_t *gp = ix.g2 + (the_pos[k] >> 5) + c;
       a[k] = alive[k] ? __ldg(gp + 1) : 0ull;
-      b[k] = (alive[k] && w + 1 < n_words) ? __ldg(gp + 2) : 0ull;
+      b[k] = (alive[k] && c + 1 < n_chunks) ? __ldg(gp + 2) : 0ull;
     }
     if (!any) break;
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
       if (alive[k]) {
-        const uint32_t off = (the_pos[k] & 15u) << 2;
-        int dd = d[k] + 16 - __popcll(packed[w] & window_word(carry[k], a[k], off));
-        pm[k] = max(pm[k], dd);
-        if (w + 1 < n_words) {
-          dd += 16 - __popcll(packed[w + 1] & window_word(a[k], b[k], off));
-          pm[k] = max(pm[k], dd);
+        const uint32_t sh = the_pos[k] & 31u;
+        uint32_t lo = __funnelshift_r((uint32_t)carry[k], (uint32_t)a[k], sh);
+        uint32_t hi = __funnelshift_r((uint32_t)(carry[k] >> 32), (uint32_t)(a[k] >> 32), sh);
+        int dd = d[k] + min(32, n_bases - 32 * c) - __popc(match_bits(lo, hi, mA[c], mC[c], mG[c], mT[c]));
+        if (c + 1 < n_chunks) {
+          lo = __funnelshift_r((uint32_t)a[k], (uint32_t)b[k], sh);
+          hi = __funnelshift_r((uint32_t)(a[k] >> 32), (uint32_t)(b[k] >> 32), sh);
+          dd += min(32, n_bases - 32 * (c + 1)) -
+                __popc(match_bits(lo, hi, mA[c + 1], mC[c + 1], mG[c + 1], mT[c + 1]));
         }
         d[k] = dd;
+        pm[k] = dd;
         carry[k] = b[k];
-        n_word += (w + 1 < n_words) ? 2ull : 1ull;
+        n_word += (c + 1 < n_chunks) ? 2ull : 1ull;
       }
     }
   }
+  // ---- windows holding N / IUPAC bases: the exact 4-bit compare (rare) ----
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+    if (exc[k]) {
+      int mx = 0;
+      d[k] = exact_compare(the_pos[k], n_words, bound, &mx);
+      pm[k] = mx;
+    }
 }
 
 // Ordered replay of the survivors of one compare round against candidate set `set_id`
@@ -757,7 +839,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
   build_packed(end, strand_code);
   const uint32_t readlen = W.scal()->len[end];
   const uint8_t *qcode = W.qcode(end);
-  const uint64_t *packed = W.packed();
+  const uint32_t *mA = W.masks(0), *mC = W.masks(1), *mG = W.masks(2), *mT = W.masks(3);
   const uint32_t *p2 = W.plane(0), *p3a = W.plane(1), *p3b = W.plane(2);
   const uint32_t *T3 = tab3();
   const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
@@ -849,7 +931,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
       const uint32_t incl = warp_incl_scan_add(tot, lane);
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       bool stop = false;
-      for (uint32_t c0 = 0; c0 < total && !stop;) {
+      for (uint32_t c0 = 0; c0 < total && !stop; c0 += 32u * kCand) {
         const int cutoff = st->cutoff;
         // In the specific phase compare against the looser bound the sensitive phase may use later (the heap
         // top only ever decreases) and log what survives it, unless the set is already full (then the
@@ -864,62 +946,30 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
             bound = Hit(heap0[0]).diffs();
           }
         }
-        if (bound >= 30) {
-          int d[2], pm[2];
-          uint32_t the_pos[2];
-          uint32_t sub[2];
-          compare_chunk<2, 6>(ix, index3, packed, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3, lane,
-                              d, pm, the_pos, sub, c_entry, c_word);
-          c0 += 64u;
-          __syncwarp();
+        int d[kCand], pm[kCand];
+        uint32_t the_pos[kCand];
+        uint32_t sub[kCand];
+        compare_chunk<kCand, 4>(ix, index3, mA, mC, mG, mT, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3,
+                                lane, d, pm, the_pos, sub, c_entry, c_word);
+        __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            if (deep) {
-              const unsigned ml = __ballot_sync(FULL, pm[k] <= bound);
-              if (ml != 0u) {
-                const int at = n_log + __popc(ml & ((1u << lane) - 1u));
-                n_log += __popc(ml);
-                if (n_log > kLogCap) log_ok = false;
-                else if (pm[k] <= bound) {
-                  log_pos[at] = the_pos[k];
-                  log_meta[at] = log_pack(d[k], pm[k], sub[k] >> 31, sub[k] & 0x7fffffffu);
-                }
+        for (int k = 0; k < kCand; ++k) {
+          if (deep) {
+            const unsigned ml = __ballot_sync(FULL, pm[k] <= bound);
+            if (ml != 0u) {
+              const int at = n_log + __popc(ml & ((1u << lane) - 1u));
+              n_log += __popc(ml);
+              if (n_log > kLogCap) log_ok = false;
+              else if (pm[k] <= bound) {
+                log_pos[at] = the_pos[k];
+                log_meta[at] = log_pack(d[k], pm[k], sub[k] >> 31, sub[k] & 0x7fffffffu);
               }
-            }
-            const unsigned mask = __ballot_sync(FULL, pm[k] <= cutoff);
-            if (mask != 0u && !stop) {
-              replay_hits(set_id, strand_code, mask, d[k], pm[k], the_pos[k]);
-              stop = st->sure_ambig != 0;
             }
           }
-        }
-        else {
-          int d[kCand], pm[kCand];
-          uint32_t the_pos[kCand];
-          uint32_t sub[kCand];
-          compare_chunk<kCand, 2>(ix, index3, packed, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3,
-                                  lane, d, pm, the_pos, sub, c_entry, c_word);
-          c0 += 32u * kCand;
-          __syncwarp();
-#pragma unroll
-          for (int k = 0; k < kCand; ++k) {
-            if (deep) {
-              const unsigned ml = __ballot_sync(FULL, pm[k] <= bound);
-              if (ml != 0u) {
-                const int at = n_log + __popc(ml & ((1u << lane) - 1u));
-                n_log += __popc(ml);
-                if (n_log > kLogCap) log_ok = false;
-                else if (pm[k] <= bound) {
-                  log_pos[at] = the_pos[k];
-                  log_meta[at] = log_pack(d[k], pm[k], sub[k] >> 31, sub[k] & 0x7fffffffu);
-                }
-              }
-            }
-            const unsigned mask = __ballot_sync(FULL, pm[k] <= cutoff);
-            if (mask != 0u && !stop) {
-              replay_hits(set_id, strand_code, mask, d[k], pm[k], the_pos[k]);
-              stop = st->sure_ambig != 0;
-            }
+          const unsigned mask = __ballot_sync(FULL, pm[k] <= cutoff);
+          if (mask != 0u && !stop) {
+            replay_hits(set_id, strand_code, mask, d[k], pm[k], the_pos[k]);
+            stop = st->sure_ambig != 0;
           }
         }
       }
@@ -1548,6 +1598,32 @@ __global__ void bucket_bitmap_kernel(const uint32_t *__restrict__ counter, uint6
     }
   }
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_set, local);
+}
+
+// 2-bit copy of the 4-bit genome + exception bits (see IndexDev::g2 / gx).  One thread per 32 bases.
+__global__ void pack_genome2_kernel(const uint64_t *__restrict__ genome, uint64_t n_words4, uint64_t n_words2,
+                                    uint64_t *g2, uint32_t *gx) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words2; w += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = 0;
+    bool bad = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t x = (2 * w + h) < n_words4 ? genome[2 * w + h] : 0ull;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t nib = (uint32_t)(x >> (4 * j)) & 15u;
+        uint32_t code = 0;
+        if (nib == 2u) code = 1;
+        else if (nib == 4u) code = 2;
+        else if (nib == 8u) code = 3;
+        else if (nib != 1u) bad = true;
+        lo |= (code & 1u) << (16 * h + j);
+        hi |= (code >> 1) << (16 * h + j);
+      }
+    }
+    g2[w] = (uint64_t)lo | ((uint64_t)hi << 32);
+    if (bad) atomicOr(gx + (w >> 8), 1u << ((w >> 3) & 31u));  // block = (32 w) >> 8 = w >> 3
+  }
 }
 
 // MINB = resident CTAs per SM the register allocation is bounded for (2: <=128 regs, 3: <=80, 4: <=64)
