@@ -6,12 +6,14 @@
 // through the very same host code.
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <ctime>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -19,8 +21,11 @@
 #include <vector>
 
 #include "abismal_b200.h"
+#include "bam_writer.hpp"
+#include "genome_prep.hpp"
 #include "index_file.hpp"
 #include "options.hpp"
+#include "pipeline.hpp"
 #include "read_loader.hpp"
 #include "sam_format.hpp"
 #ifdef ABISMAL_ENGINE_ORACLE
@@ -45,8 +50,10 @@ std::string fmt_secs(double s) {
 }
 
 struct ResultBuffers {
-  std::vector<abg_hit> pe_r1, pe_r2, se1, se2;
-  std::vector<uint32_t> cigar1, cigar2, n_cigar1, n_cigar2;
+  // hit records and CIGAR lengths are DMA'd straight into these (page-locked in the GPU build)
+  ab2::pinned_vector<abg_hit> pe_r1, pe_r2, se1, se2;
+  ab2::pinned_vector<uint32_t> n_cigar1, n_cigar2;
+  std::vector<uint32_t> cigar1, cigar2;
   uint32_t stride = 0;
   void resize(uint32_t n, uint32_t cigar_stride, bool paired) {
     stride = cigar_stride;
@@ -133,12 +140,250 @@ ab2::ReadView make_view(const ab2::ReadBatch &b, uint32_t i, const uint32_t *cig
   return v;
 }
 
+// One batch travelling through the pipeline.
+struct WorkItem {
+  uint64_t seq_no = 0;
+  ab2::ReadBatch b1, b2;
+  ResultBuffers rb;
+};
+
+struct StageClock {  // busy seconds of one pipeline stage (reported with -v)
+  std::atomic<uint64_t> ns{0};
+  struct Scope {
+    StageClock &c;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Scope(StageClock &cc) : c(cc) {}
+    ~Scope() {
+      c.ns += static_cast<uint64_t>(
+        std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+    }
+  };
+  double secs() const { return static_cast<double>(ns.load()) * 1e-9; }
+};
+
+struct MapConfig {
+  bool paired_end = false, allow_ambig = false, write_bam = false, verbose = false;
+  uint32_t batch_size = 0, n_threads = 1;
+  int bam_level = -1;
+  std::vector<int> devices;
+  abg_params params{};
+};
+
+// FASTQ readers -> mapper (one per GPU) -> formatter pool -> ordered writer.
+// Output order is input order, i.e. the reference's `-t 1` order.
+class MapPipeline {
+public:
+  MapPipeline(const MapConfig &cfg, const ab2::IndexFile &index, const std::string &fq1, const std::string &fq2,
+              FILE *out)
+    : cfg_(cfg), index_(index), out_(out), rl1_(fq1), free_(kItems), q12_(kItems), to_map_(kItems),
+      to_out_(kItems), pool_(cfg.n_threads) {
+    if (cfg.paired_end) rl2_.reset(new ab2::FastqReader(fq2));
+    items_.resize(kItems);
+    for (WorkItem &it : items_) free_.push(&it);
+  }
+
+  void run() {
+    std::vector<std::thread> th;
+    th.emplace_back([this] { guarded([this] { read_end1(); }); });
+    if (cfg_.paired_end) th.emplace_back([this] { guarded([this] { read_end2(); }); });
+    n_mappers_live_ = static_cast<int>(cfg_.devices.size());
+    for (int dev : cfg_.devices) th.emplace_back([this, dev] { guarded([this, dev] { map_on(dev); }); });
+    th.emplace_back([this] { guarded([this] { write_out(); }); });
+    for (std::thread &t : th) t.join();
+    if (error_) std::rethrow_exception(error_);
+  }
+
+  ab2::SeStats se_stats;
+  ab2::PeStats pe_stats;
+  uint64_t n_done = 0;
+  StageClock t_read1, t_read2, t_map, t_format, t_write;
+
+private:
+  static constexpr size_t kItems = 6;
+
+  template <class F>
+  void guarded(F f) {
+    try {
+      f();
+    }
+    catch (...) {
+      {
+        std::lock_guard<std::mutex> lk(err_mu_);
+        if (!error_) error_ = std::current_exception();
+      }
+      failed_ = true;
+      free_.close();
+      q12_.close();
+      to_map_.close();
+      to_out_.close();
+    }
+  }
+
+  // abismal.cpp:1549-1555 / :1947-1955: `while (rl1 && rl2) { load; load; compare sizes; ... }`
+  void read_end1() {
+    uint64_t k = 0;
+    while (!failed_ && !stop_reading_) {
+      WorkItem *it = nullptr;
+      if (!free_.pop(it)) break;
+      bool last;
+      {
+        StageClock::Scope sc(t_read1);
+        it->seq_no = k++;
+        rl1_.load_reads(it->b1, cfg_.batch_size);
+        last = !rl1_.good();
+      }
+      if (!(cfg_.paired_end ? q12_ : to_map_).push(it)) break;
+      if (last) break;
+    }
+    (cfg_.paired_end ? q12_ : to_map_).close();
+  }
+
+  void read_end2() {
+    WorkItem *it = nullptr;
+    while (!failed_ && q12_.pop(it)) {
+      {
+        StageClock::Scope sc(t_read2);
+        rl2_->load_reads(it->b2, cfg_.batch_size);
+      }
+      if (it->b1.size() != it->b2.size())
+        throw std::runtime_error("paired-end batch sizes differ. Batch 1: " + std::to_string(it->b1.size()) +
+                                 ", batch 2: " + std::to_string(it->b2.size()) +
+                                 ". Are you sure your paired-end inputs have the same number of reads?");
+      const bool last = !rl2_->good();
+      if (!to_map_.push(it)) break;
+      if (last) {
+        stop_reading_ = true;  // the reference's loop ends as soon as either file is exhausted
+        break;
+      }
+    }
+    q12_.close();  // unblocks reader 1 if it ran ahead
+    to_map_.close();
+  }
+
+  void map_on(int device) {
+    std::unique_ptr<Engine> engine;
+    uint32_t engine_max_len = 0;
+    const abg_index_view view = index_.view();
+    WorkItem *it = nullptr;
+    while (!failed_ && to_map_.pop(it)) {
+      const uint32_t n = it->b1.size();
+      if (n != 0) {
+        StageClock::Scope sc(t_map);
+        const uint32_t max_len = std::max(it->b1.max_read_len(), cfg_.paired_end ? it->b2.max_read_len() : 0u);
+        if (!engine || max_len > engine_max_len) {
+          engine.reset();
+          engine_max_len = std::max<uint32_t>(256, max_len);
+          engine.reset(new Engine(view, cfg_.params, cfg_.batch_size, engine_max_len, device));
+        }
+        it->rb.resize(n, cfg_.params.cigar_stride, cfg_.paired_end);
+        abg_batch batch;
+        std::memset(&batch, 0, sizeof batch);
+        batch.n = n;
+        batch.seq1 = it->b1.seq.data();
+        batch.off1 = it->b1.seq_off.data();
+        if (cfg_.paired_end) {
+          batch.seq2 = it->b2.seq.data();
+          batch.off2 = it->b2.seq_off.data();
+        }
+        abg_results res = it->rb.view(cfg_.paired_end);
+        engine->map(batch, res);
+      }
+      if (!to_out_.push(it)) break;
+    }
+    if (--n_mappers_live_ == 0) to_out_.close();
+  }
+
+  // Formats reads [i0, i1) of the item into `bytes` (SAM text or BGZF-framed BAM records).
+  void format_slice(WorkItem &w, uint32_t i0, uint32_t i1, std::string &bytes, ab2::SeStats &ss, ab2::PeStats &ps) {
+    const bool allow_ambig = cfg_.allow_ambig;
+    ab2::Emitter em;
+    ab2::BgzfRecordPacker packer(bytes, cfg_.bam_level);
+    if (cfg_.write_bam) em.bam = &packer;
+    else em.sam = &bytes;
+    ResultBuffers &rb = w.rb;
+    if (!cfg_.paired_end) {
+      for (uint32_t i = i0; i < i1; ++i) {
+        const ab2::ReadView r = make_view(w.b1, i, rb.cigar1.data(), rb.n_cigar1.data(), rb.stride);
+        abg_hit &best = rb.se1[i];
+        if (r.seq_len != 0) {
+          if (ab2::format_se(allow_ambig, best, index_.cl, r, em) == ab2::map_unmapped) ab2::hit_reset(best);
+        }
+        ss.update(allow_ambig, r, best);
+      }
+    }
+    else {
+      for (uint32_t i = i0; i < i1; ++i) {
+        const ab2::ReadView r1 = make_view(w.b1, i, rb.cigar1.data(), rb.n_cigar1.data(), rb.stride);
+        const ab2::ReadView r2 = make_view(w.b2, i, rb.cigar2.data(), rb.n_cigar2.data(), rb.stride);
+        ab2::select_output(allow_ambig, index_.cl, r1, r2, rb.pe_r1[i], rb.pe_r2[i], rb.se1[i], rb.se2[i], em);
+        ps.update(allow_ambig, r1, r2, rb.pe_r1[i], rb.pe_r2[i], rb.se1[i], rb.se2[i]);
+      }
+    }
+    if (cfg_.write_bam) packer.finish();
+  }
+
+  void write_out() {
+    std::map<uint64_t, WorkItem *> waiting;  // multi-GPU: batches finish out of order
+    uint64_t next = 0;
+    const unsigned n_slices = std::max(1u, pool_.size() * 2);
+    std::vector<std::string> bytes(n_slices);
+    std::vector<ab2::SeStats> ss(n_slices);
+    std::vector<ab2::PeStats> ps(n_slices);
+    WorkItem *in = nullptr;
+    while (!failed_ && to_out_.pop(in)) {
+      waiting[in->seq_no] = in;
+      while (!waiting.empty() && waiting.begin()->first == next) {
+        WorkItem *w = waiting.begin()->second;
+        waiting.erase(waiting.begin());
+        ++next;
+        const uint32_t n = w->b1.size();
+        if (n != 0) {
+          {
+            StageClock::Scope sc(t_format);
+            pool_.run(n_slices, [&](unsigned k) {
+              const uint32_t i0 = static_cast<uint32_t>(static_cast<uint64_t>(n) * k / n_slices);
+              const uint32_t i1 = static_cast<uint32_t>(static_cast<uint64_t>(n) * (k + 1) / n_slices);
+              bytes[k].clear();
+              ss[k] = ab2::SeStats();
+              ps[k] = ab2::PeStats();
+              format_slice(*w, i0, i1, bytes[k], ss[k], ps[k]);
+            });
+          }
+          StageClock::Scope sc(t_write);
+          for (unsigned k = 0; k < n_slices; ++k) {
+            if (!bytes[k].empty() && std::fwrite(bytes[k].data(), 1, bytes[k].size(), out_) != bytes[k].size())
+              throw std::runtime_error("failed to write bam");
+            se_stats.add(ss[k]);
+            pe_stats.add(ps[k]);
+          }
+          n_done += n;
+        }
+        free_.push(w);
+      }
+    }
+    free_.close();
+  }
+
+  const MapConfig &cfg_;
+  const ab2::IndexFile &index_;
+  FILE *out_;
+  ab2::FastqReader rl1_;
+  std::unique_ptr<ab2::FastqReader> rl2_;
+  std::vector<WorkItem> items_;
+  ab2::BoundedQueue<WorkItem *> free_, q12_, to_map_, to_out_;
+  ab2::WorkerPool pool_;
+  std::atomic<bool> failed_{false}, stop_reading_{false};
+  std::atomic<int> n_mappers_live_{0};
+  std::mutex err_mu_;
+  std::exception_ptr error_;
+};
+
 int map_main(int argc, char *argv[]) {
   try {
     bool verbose = false, g_to_a_conversion = false, allow_ambig = false, pbat_mode = false;
     bool random_pbat = false, write_bam_fmt = false, stats_as_json = false, help = false, about = false;
-    uint32_t max_candidates = 0, n_threads = 1, min_dist = 32, max_dist = 3000;
-    uint32_t batch_size = 1u << 16, device = 0;
+    uint32_t max_candidates = 0, n_threads = 0, min_dist = 32, max_dist = 3000;
+    uint32_t batch_size = 1u << 17, device = 0, n_gpus = 1;
     double valid_frac = 0.1;
     std::string index_file, genome_file, outfile, stats_outfile;
 
@@ -159,11 +404,12 @@ int map_main(int argc, char *argv[]) {
     opt.add("pbat", 'P', "input follows the PBAT protocol", false, pbat_mode);
     opt.add("random-pbat", 'R', "input follows random PBAT protocol", false, random_pbat);
     opt.add("a-rich", 'A', "indicates reads are a-rich (se mode)", false, g_to_a_conversion);
-    opt.add("threads", 't', "number of threads", false, n_threads);
+    opt.add("threads", 't', "number of host threads (0: all cores, at most 32)", false, n_threads);
     opt.add("verbose", 'v', "print more run info", false, verbose);
     // extras of this implementation (not in the reference)
     opt.add("gpu-batch", '\0', "reads (or pairs) per GPU batch", false, batch_size);
-    opt.add("device", '\0', "CUDA device ordinal", false, device);
+    opt.add("device", '\0', "first CUDA device ordinal", false, device);
+    opt.add("gpus", '\0', "number of GPUs to shard batches over (index replicated)", false, n_gpus);
     const std::vector<std::string> leftover = opt.parse(argc, argv);
 
     const std::string usage = opt.help_message(argv[0], "<reads-fq1> [<reads-fq2>]");
@@ -179,10 +425,12 @@ int map_main(int argc, char *argv[]) {
       std::cerr << usage << '\n';
       return EXIT_SUCCESS;
     }
-    if (n_threads == 0 || n_threads > 1024) {
+    if (n_threads > 1024) {
       std::cerr << "Please choose a valid number of threads" << '\n';
       return EXIT_SUCCESS;
     }
+    if (n_threads == 0) n_threads = std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    n_threads = std::min(n_threads, std::max(1u, std::thread::hardware_concurrency()));  // abismal.cpp:2398-2400
     if (index_file.empty() == genome_file.empty()) {
       std::cerr << "Select one of index file (-i) or genome file (-g)\n";
       return EXIT_SUCCESS;
@@ -201,26 +449,37 @@ int map_main(int argc, char *argv[]) {
         return EXIT_FAILURE;
       }
     }
-    if (!genome_file.empty())
-      throw std::runtime_error("on-the-fly indexing (-g) is not part of the GPU map path; "
-                               "build the index with `abismal idx` and pass it with -i");
-    if (write_bam_fmt)
-      throw std::runtime_error("BAM output (-B) is not implemented yet; write SAM and convert");
     if (batch_size == 0) batch_size = 1;
+    if (n_gpus == 0) n_gpus = 1;
 
     if (verbose) {
       log_msg(paired_end ? "input (PE): " + reads_file + ", " + reads_file2 : "input (SE): " + reads_file);
-      log_msg("output (SAM): " + outfile);
+      log_msg(std::string("output (") + (write_bam_fmt ? "BAM" : "SAM") + "): " + outfile);
       if (!stats_outfile.empty()) log_msg("map statistics: " + stats_outfile);
     }
 
+#ifndef ABISMAL_ENGINE_ORACLE
+    ab2::host_mem_hooks().alloc = abg_host_alloc;
+    ab2::host_mem_hooks().release = abg_host_free;
+#endif
+
     ab2::IndexFile index;
     const auto t0 = std::chrono::steady_clock::now();
-    if (verbose) log_msg("loading index " + index_file);
-    index.read(index_file);
-    if (verbose)
-      log_msg("loading time: " +
-              fmt_secs(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+    if (!index_file.empty()) {
+      if (verbose) log_msg("loading index " + index_file);
+      index.read(index_file);
+      if (verbose)
+        log_msg("loading time: " +
+                fmt_secs(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+    }
+    else {
+      // abismal.cpp:2439-2446: index the genome on the fly
+      if (verbose) log_msg("indexing genome " + genome_file);
+      build_index_from_fasta(genome_file, static_cast<int>(device), index);
+      if (verbose)
+        log_msg("indexing time: " +
+                fmt_secs(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+    }
     if (max_candidates != 0) log_msg("manually setting max_candidates to " + std::to_string(max_candidates));
 
     FILE *out = outfile == "-" ? stdout : std::fopen(outfile.c_str(), "w");
@@ -235,10 +494,29 @@ int map_main(int argc, char *argv[]) {
       }
     } closer{out};
 
-    const std::string hdr = ab2::make_sam_header(index.cl, argc, argv, kVersion);
-    if (std::fwrite(hdr.data(), 1, hdr.size(), out) != hdr.size()) throw std::runtime_error("error writing header");
+    MapConfig cfg;
+    cfg.paired_end = paired_end;
+    cfg.allow_ambig = allow_ambig;
+    cfg.write_bam = write_bam_fmt;
+    cfg.verbose = verbose;
+    cfg.batch_size = batch_size;
+    cfg.n_threads = n_threads;
+    if (const char *e = std::getenv("ABISMAL_B200_BAM_LEVEL")) cfg.bam_level = std::atoi(e);
+    for (uint32_t g = 0; g < n_gpus; ++g) cfg.devices.push_back(static_cast<int>(device + g));
 
-    abg_params params;
+    const std::string hdr = ab2::make_sam_header(index.cl, argc, argv, kVersion);
+    {
+      std::string bytes;
+      if (write_bam_fmt) {
+        const std::string bh = ab2::make_bam_header(index.cl, hdr);
+        ab2::bgzf_append(bh.data(), bh.size(), cfg.bam_level, bytes);
+      }
+      else bytes = hdr;
+      if (std::fwrite(bytes.data(), 1, bytes.size(), out) != bytes.size())
+        throw std::runtime_error("error writing header");
+    }
+
+    abg_params &params = cfg.params;
     std::memset(&params, 0, sizeof params);
     params.mode = (paired_end ? ABG_MODE_PAIRED : 0u) | (random_pbat ? ABG_MODE_RANDOM_PBAT : 0u);
     // abismal.cpp:2468-2483: SE a-rich for -A or -P; PE a-rich for -P.  -R selects
@@ -251,85 +529,28 @@ int map_main(int argc, char *argv[]) {
     params.max_candidates = max_candidates;
     params.cigar_stride = 64;
 
-    ab2::FastqReader rl1(reads_file);
-    std::unique_ptr<ab2::FastqReader> rl2;
-    if (paired_end) rl2.reset(new ab2::FastqReader(reads_file2));
-
-    std::unique_ptr<Engine> engine;
-    uint32_t engine_max_len = 0;
-    const abg_index_view view = index.view();
-
-    ab2::ReadBatch b1, b2;
-    ResultBuffers rb;
-    ab2::SeStats se_stats;
-    ab2::PeStats pe_stats;
-    std::string sam;
     const auto t_map = std::chrono::steady_clock::now();
-    uint64_t n_done = 0;
-
-    while (rl1.good() && (!paired_end || rl2->good())) {
-      rl1.load_reads(b1, batch_size);
-      if (paired_end) {
-        rl2->load_reads(b2, batch_size);
-        if (b1.size() != b2.size())
-          throw std::runtime_error("paired-end batch sizes differ. Batch 1: " + std::to_string(b1.size()) +
-                                   ", batch 2: " + std::to_string(b2.size()) +
-                                   ". Are you sure your paired-end inputs have the same number of reads?");
-      }
-      const uint32_t n = b1.size();
-      if (n == 0) continue;
-      const uint32_t max_len = std::max(b1.max_read_len(), paired_end ? b2.max_read_len() : 0u);
-      if (!engine || max_len > engine_max_len) {
-        engine.reset();
-        engine_max_len = std::max<uint32_t>(256, max_len);
-        engine.reset(new Engine(view, params, batch_size, engine_max_len, static_cast<int>(device)));
-      }
-      rb.resize(n, params.cigar_stride, paired_end);
-      abg_batch batch;
-      std::memset(&batch, 0, sizeof batch);
-      batch.n = n;
-      batch.seq1 = b1.seq.data();
-      batch.off1 = b1.seq_off.data();
-      if (paired_end) {
-        batch.seq2 = b2.seq.data();
-        batch.off2 = b2.seq_off.data();
-      }
-      abg_results res = rb.view(paired_end);
-      engine->map(batch, res);
-
-      sam.clear();
-      if (!paired_end) {
-        for (uint32_t i = 0; i < n; ++i) {
-          const ab2::ReadView r = make_view(b1, i, rb.cigar1.data(), rb.n_cigar1.data(), rb.stride);
-          abg_hit &best = rb.se1[i];
-          if (r.seq_len != 0) {
-            if (ab2::format_se(allow_ambig, best, index.cl, r, sam) == ab2::map_unmapped) ab2::hit_reset(best);
-          }
-          se_stats.update(allow_ambig, r, best);
-        }
-      }
-      else {
-        for (uint32_t i = 0; i < n; ++i) {
-          const ab2::ReadView r1 = make_view(b1, i, rb.cigar1.data(), rb.n_cigar1.data(), rb.stride);
-          const ab2::ReadView r2 = make_view(b2, i, rb.cigar2.data(), rb.n_cigar2.data(), rb.stride);
-          ab2::select_output(allow_ambig, index.cl, r1, r2, rb.pe_r1[i], rb.pe_r2[i], rb.se1[i], rb.se2[i], sam);
-          pe_stats.update(allow_ambig, r1, r2, rb.pe_r1[i], rb.pe_r2[i], rb.se1[i], rb.se2[i]);
-        }
-      }
-      if (std::fwrite(sam.data(), 1, sam.size(), out) != sam.size()) throw std::runtime_error("failed to write bam");
-      n_done += n;
+    MapPipeline pipe(cfg, index, reads_file, reads_file2, out);
+    pipe.run();
+    if (write_bam_fmt) {
+      const std::string &eof = ab2::bgzf_eof_marker();
+      if (std::fwrite(eof.data(), 1, eof.size(), out) != eof.size()) throw std::runtime_error("failed to write bam");
     }
     if (verbose) {
       const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_map).count();
-      log_msg("reads mapped: " + std::to_string(n_done));
+      log_msg("reads mapped: " + std::to_string(pipe.n_done));
       log_msg("total mapping time: " + fmt_secs(secs));
+      log_msg("stage busy time: read1 " + fmt_secs(pipe.t_read1.secs()) + ", read2 " + fmt_secs(pipe.t_read2.secs()) +
+              ", map (" + std::to_string(cfg.devices.size()) + " GPU) " + fmt_secs(pipe.t_map.secs()) + ", format (" +
+              std::to_string(n_threads) + " threads) " + fmt_secs(pipe.t_format.secs()) + ", write " +
+              fmt_secs(pipe.t_write.secs()));
     }
 
     if (!stats_outfile.empty()) {
       std::ofstream statout(stats_outfile);
       if (statout) {
-        if (stats_as_json) statout << (paired_end ? pe_stats.tojson() : se_stats.tojson());
-        else statout << (paired_end ? pe_stats.tostring(allow_ambig) : se_stats.tostring("read1"));
+        if (stats_as_json) statout << (paired_end ? pipe.pe_stats.tojson() : pipe.se_stats.tojson());
+        else statout << (paired_end ? pipe.pe_stats.tostring(allow_ambig) : pipe.se_stats.tostring("read1"));
       }
       else std::cerr << "failed to open stats out file: " << stats_outfile << '\n';
     }
@@ -341,14 +562,70 @@ int map_main(int argc, char *argv[]) {
   return EXIT_SUCCESS;
 }
 
+// `abismal-b200 idx`: the reference's abismalidx (src/abismalidx.cpp:30-120) with the index built on the GPU.
+int idx_main(int argc, char *argv[]) {
+  try {
+    bool verbose = false, help = false, about = false;
+    uint32_t n_threads = 1, device = 0;
+    std::string target_regions_file;
+    ab2::Options opt;
+    opt.add("help", '?', "print this help message", false, help);
+    opt.add("about", '\0', "print about message", false, about);
+    opt.add("targets", 'A', "target regions", false, target_regions_file);
+    opt.add("threads", 't', "number of threads", false, n_threads);
+    opt.add("verbose", 'v', "print more run info", false, verbose);
+    opt.add("device", '\0', "CUDA device ordinal", false, device);
+    const std::vector<std::string> leftover = opt.parse(argc, argv);
+    const std::string usage = opt.help_message(argv[0], "<genome-fasta> <abismal-index-file>");
+    if (argc == 1 || help || about) {
+      std::cerr << usage << '\n';
+      return EXIT_SUCCESS;
+    }
+    if (leftover.size() != 2) {
+      std::cerr << usage << '\n';
+      return EXIT_SUCCESS;
+    }
+    if (!target_regions_file.empty())
+      throw std::runtime_error("target regions (-A) are not supported by the GPU index builder");
+    const auto t0 = std::chrono::steady_clock::now();
+    if (verbose) log_msg("indexing genome " + leftover.front());
+    ab2::IndexFile index;
+    build_index_from_fasta(leftover.front(), static_cast<int>(device), index);
+    if (verbose) log_msg("writing index file " + leftover.back());
+    ab2::write_index_file(index, leftover.back());
+    if (verbose)
+      log_msg("total indexing time: " +
+              fmt_secs(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
+  }
+  catch (const std::exception &e) {
+    std::cerr << e.what() << '\n';
+    return EXIT_FAILURE;
+  }
+  return EXIT_SUCCESS;
+}
+
 }  // namespace
 
+void build_index_from_fasta(const std::string &fasta_path, int device, ab2::IndexFile &out) {
+#ifdef ABISMAL_ENGINE_ORACLE
+  (void)fasta_path;
+  (void)device;
+  (void)out;
+  throw std::runtime_error("index construction is not part of the oracle test tool; pass an index with -i");
+#else
+  ab2::PreparedGenome g;
+  ab2::prepare_genome(fasta_path, g);
+  ab2::build_index(std::move(g), device, out);
+#endif
+}
+
 int main(int argc, char *argv[]) {
-  // same dispatch shape as the reference's abismal_main.cpp: `<prog> map ...`
-  if (argc < 2 || std::strcmp(argv[1], "map") != 0) {
-    std::cerr << "usage: " << argv[0] << " map [OPTIONS] <reads-fq1> [<reads-fq2>]\n"
-              << "(only the `map` command is provided; use the reference's `abismal idx` to build an index)\n";
-    return argc < 2 ? EXIT_SUCCESS : EXIT_FAILURE;
-  }
-  return map_main(argc - 1, argv + 1);
+  // same dispatch shape as the reference's abismal_main.cpp: `<prog> <command> ...`
+  if (argc >= 2 && std::strcmp(argv[1], "map") == 0) return map_main(argc - 1, argv + 1);
+  if (argc >= 2 && std::strcmp(argv[1], "idx") == 0) return idx_main(argc - 1, argv + 1);
+  std::cerr << "usage: " << argv[0] << " <command> [OPTIONS]\n"
+            << "commands:\n  idx   make an index for a reference genome (on the GPU)\n"
+            << "  map   map bisulfite converted reads (on the GPU)\n"
+            << "(`sim` is not provided; use the reference's `abismal sim`)\n";
+  return argc < 2 ? EXIT_SUCCESS : EXIT_FAILURE;
 }

@@ -1,0 +1,141 @@
+// Host-side plumbing of the `map` front end: a bounded queue between pipeline
+// stages, a fork-join worker pool for the per-batch host work (SAM/BAM
+// formatting, statistics) and an allocator that puts batch and result buffers
+// in page-locked memory so that the mapper DMAs them in place.
+//
+// The reference runs N symmetric OpenMP threads that each load, map and write
+// a 1000-read batch under two mutexes (src/abismal.cpp:1541-1596); here the
+// GPU does the mapping, so `-t N` host threads are spent on the stages either
+// side of it: FASTQ readers -> mapper (one per GPU) -> formatters -> writer.
+#ifndef ABISMAL_B200_PIPELINE_HPP
+#define ABISMAL_B200_PIPELINE_HPP
+
+#include <condition_variable>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <deque>
+#include <exception>
+#include <functional>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <utility>
+#include <vector>
+
+namespace ab2 {
+
+// ---- page-locked memory hook -------------------------------------------------
+// Set once by main() before any buffer exists (abg_host_alloc/abg_host_free in
+// the GPU build, left null in the oracle test tool => plain malloc).
+struct HostMemHooks {
+  int (*alloc)(size_t, void **) = nullptr;
+  void (*release)(void *) = nullptr;
+};
+HostMemHooks &host_mem_hooks();
+
+template <class T>
+struct PinnedAlloc {
+  using value_type = T;
+  PinnedAlloc() = default;
+  template <class U>
+  PinnedAlloc(const PinnedAlloc<U> &) {}
+  T *allocate(size_t n) {
+    void *p = nullptr;
+    const HostMemHooks &h = host_mem_hooks();
+    if (h.alloc) {
+      if (h.alloc(n * sizeof(T), &p) != 0 || !p) throw std::bad_alloc();
+    }
+    else {
+      p = std::malloc(n * sizeof(T) ? n * sizeof(T) : 1);
+      if (!p) throw std::bad_alloc();
+    }
+    return static_cast<T *>(p);
+  }
+  void deallocate(T *p, size_t) {
+    const HostMemHooks &h = host_mem_hooks();
+    if (h.release) h.release(p);
+    else std::free(p);
+  }
+  // leave elements uninitialised on resize(): these are plain buffers the GPU fills
+  template <class U, class... Args>
+  void construct(U *p, Args &&...args) {
+    if constexpr (sizeof...(Args) == 0) (void)p;
+    else ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...);
+  }
+  template <class U>
+  bool operator==(const PinnedAlloc<U> &) const { return true; }
+  template <class U>
+  bool operator!=(const PinnedAlloc<U> &) const { return false; }
+};
+
+template <class T>
+using pinned_vector = std::vector<T, PinnedAlloc<T>>;
+
+// ---- bounded multi-producer multi-consumer queue ---------------------------------
+template <class T>
+class BoundedQueue {
+public:
+  explicit BoundedQueue(size_t cap) : cap_(cap) {}
+  // false when the queue was closed before the item could be queued
+  bool push(T v) {
+    std::unique_lock<std::mutex> lk(mu_);
+    not_full_.wait(lk, [&] { return q_.size() < cap_ || closed_; });
+    if (closed_) return false;
+    q_.push_back(std::move(v));
+    not_empty_.notify_one();
+    return true;
+  }
+  // false when the queue is closed and drained
+  bool pop(T &out) {
+    std::unique_lock<std::mutex> lk(mu_);
+    not_empty_.wait(lk, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    out = std::move(q_.front());
+    q_.pop_front();
+    not_full_.notify_one();
+    return true;
+  }
+  void close() {
+    std::lock_guard<std::mutex> lk(mu_);
+    closed_ = true;
+    not_full_.notify_all();
+    not_empty_.notify_all();
+  }
+
+private:
+  std::mutex mu_;
+  std::condition_variable not_full_, not_empty_;
+  std::deque<T> q_;
+  size_t cap_;
+  bool closed_ = false;
+};
+
+// ---- fork-join pool -----------------------------------------------------------
+// run(n, f) calls f(k) for k in [0, n) on the pool's threads plus the caller
+// and returns when all are done; the first exception is rethrown.
+class WorkerPool {
+public:
+  explicit WorkerPool(unsigned n_threads);
+  ~WorkerPool();
+  WorkerPool(const WorkerPool &) = delete;
+  WorkerPool &operator=(const WorkerPool &) = delete;
+  unsigned size() const { return static_cast<unsigned>(threads_.size()) + 1; }
+  void run(unsigned n, const std::function<void(unsigned)> &f);
+
+private:
+  void worker();
+  void drain(std::unique_lock<std::mutex> &lk);
+
+  std::vector<std::thread> threads_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable wake_, done_;
+  const std::function<void(unsigned)> *job_ = nullptr;
+  unsigned next_ = 0, total_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+  std::exception_ptr error_;
+  bool stop_ = false;
+};
+
+}  // namespace ab2
+#endif

@@ -82,6 +82,9 @@ bool FastqReader::getline(const char *&line, size_t &len) {
 
 void FastqReader::load_reads(ReadBatch &out, size_t max_reads) {
   out.clear();
+  // one allocation up front (page-locked memory is slow to allocate); also keeps seq.data() non-null for
+  // batches whose reads are all empty
+  if (out.seq.capacity() == 0) out.seq.reserve(std::max<size_t>(64, std::min<size_t>(max_reads, 1u << 22) * 160));
   if (eof_) return;
   size_t line_count = 0;
   const size_t num_lines_to_read = 4 * max_reads;

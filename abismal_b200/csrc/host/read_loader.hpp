@@ -7,12 +7,14 @@
 #include <string>
 #include <vector>
 
+#include "pipeline.hpp"
+
 namespace ab2 {
 
 // Reads of one batch in flat arrays: read i is seq[seq_off[i] .. seq_off[i+1]),
 // its name is names[name_off[i] .. name_off[i+1]).
 struct ReadBatch {
-  std::vector<char> seq;
+  pinned_vector<char> seq;  // page-locked in the GPU build: DMA'd in place by abg_map_batch
   std::vector<uint32_t> seq_off{0};
   std::vector<char> names;
   std::vector<uint32_t> name_off{0};

@@ -30,6 +30,7 @@ inline void put_int(std::string &o, int64_t v) {
 struct Nt16 {
   char fwd[256];  // normalised base
   char rc[256];   // normalised revcomp base (revcomp_inplace: A<->T, C<->G, else N)
+  unsigned char code[256];  // seq_nt16_table
   Nt16() {
     static const char dec[] = "=ACMGRSVTWYHKDBN";
     for (int c = 0; c < 256; ++c) {
@@ -53,6 +54,7 @@ struct Nt16 {
         default: code = 15;
       }
       fwd[c] = dec[code];
+      this->code[c] = static_cast<unsigned char>(code);
       rc[c] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
     }
   }
@@ -93,8 +95,8 @@ void put_rname(std::string &o, const ChromLookup &cl, int32_t tid) {
   else o += '*';
 }
 
-void put_record(std::string &o, const ChromLookup &cl, const ReadView &r, bool revcomp, uint16_t flag,
-                int32_t tid, uint32_t pos, int32_t mtid, int64_t mpos, int64_t isize, int nm, char cv) {
+void put_sam_record(std::string &o, const ChromLookup &cl, const ReadView &r, bool revcomp, uint16_t flag,
+                    int32_t tid, uint32_t pos, int32_t mtid, int64_t mpos, int64_t isize, int nm, char cv) {
   o.append(r.name, r.name_len);
   o += '\t';
   put_uint(o, flag);
@@ -119,6 +121,107 @@ void put_record(std::string &o, const ChromLookup &cl, const ReadView &r, bool r
   o += "\tCV:A:";
   o += cv;
   o += '\n';
+}
+
+inline void le16(std::string &o, uint32_t v) {
+  o += static_cast<char>(v & 0xff);
+  o += static_cast<char>((v >> 8) & 0xff);
+}
+inline void le32(std::string &o, uint32_t v) {
+  le16(o, v & 0xffff);
+  le16(o, v >> 16);
+}
+
+// UCSC binning scheme (SAM spec 5.3), the value bam_set1 stores in core.bin
+inline uint32_t reg2bin(int64_t beg, int64_t end) {
+  --end;
+  if (beg >> 14 == end >> 14) return static_cast<uint32_t>(((1 << 15) - 1) / 7 + (beg >> 14));
+  if (beg >> 17 == end >> 17) return static_cast<uint32_t>(((1 << 12) - 1) / 7 + (beg >> 17));
+  if (beg >> 20 == end >> 20) return static_cast<uint32_t>(((1 << 9) - 1) / 7 + (beg >> 20));
+  if (beg >> 23 == end >> 23) return static_cast<uint32_t>(((1 << 6) - 1) / 7 + (beg >> 23));
+  if (beg >> 26 == end >> 26) return static_cast<uint32_t>(((1 << 3) - 1) / 7 + (beg >> 26));
+  return 0;
+}
+
+// The record bam_set1 + bam_aux_update_int("NM") + bam_aux_append("CV", 'A') build
+// (abismal.cpp:511-542, :710-770), in the on-disk BAM layout (SAM spec 4.2).
+void put_bam_record(std::string &o, const ReadView &r, bool revcomp, uint16_t flag, int32_t tid, uint32_t pos,
+                    int32_t mtid, int64_t mpos, int64_t isize, int nm, char cv) {
+  o.clear();
+  le32(o, 0);  // block_size, patched below
+  le32(o, static_cast<uint32_t>(tid));
+  le32(o, pos);
+  uint32_t rlen = cigar_rseq_ops(r.cigar, r.n_cigar);
+  if (rlen == 0) rlen = 1;
+  const uint32_t l_name = r.name_len + 1;
+  o += static_cast<char>(l_name & 0xff);
+  o += static_cast<char>(255);  // MAPQ
+  le16(o, reg2bin(pos, static_cast<int64_t>(pos) + rlen));
+  le16(o, r.n_cigar);
+  le16(o, flag);
+  le32(o, r.seq_len);
+  le32(o, static_cast<uint32_t>(mtid));
+  le32(o, static_cast<uint32_t>(static_cast<int32_t>(mpos)));
+  le32(o, static_cast<uint32_t>(static_cast<int32_t>(isize)));
+  o.append(r.name, r.name_len);
+  o += '\0';
+  for (uint32_t i = 0; i < r.n_cigar; ++i) le32(o, r.cigar[i]);
+  {
+    const size_t at = o.size();
+    o.resize(at + (r.seq_len + 1) / 2, '\0');
+    unsigned char *d = reinterpret_cast<unsigned char *>(&o[at]);
+    for (uint32_t i = 0; i < r.seq_len; ++i) {
+      const unsigned char ch = revcomp ? static_cast<unsigned char>(nt16.rc[static_cast<unsigned char>(r.seq[r.seq_len - 1 - i])])
+                                       : static_cast<unsigned char>(r.seq[i]);
+      const unsigned code = nt16.code[ch];
+      d[i >> 1] |= static_cast<unsigned char>((i & 1) ? code : code << 4);
+    }
+  }
+  o.append(r.seq_len, static_cast<char>(0xff));  // no qualities
+  // NM: the smallest integer type that holds the value (bam_aux_update_int)
+  o += "NM";
+  if (nm >= 0) {
+    if (nm <= 0xff) {
+      o += 'C';
+      o += static_cast<char>(nm);
+    }
+    else if (nm <= 0xffff) {
+      o += 'S';
+      le16(o, static_cast<uint32_t>(nm));
+    }
+    else {
+      o += 'I';
+      le32(o, static_cast<uint32_t>(nm));
+    }
+  }
+  else if (nm >= -128) {
+    o += 'c';
+    o += static_cast<char>(nm);
+  }
+  else if (nm >= -32768) {
+    o += 's';
+    le16(o, static_cast<uint32_t>(nm) & 0xffffu);
+  }
+  else {
+    o += 'i';
+    le32(o, static_cast<uint32_t>(nm));
+  }
+  o += "CVA";
+  o += cv;
+  const uint32_t block_size = static_cast<uint32_t>(o.size() - 4);
+  o[0] = static_cast<char>(block_size & 0xff);
+  o[1] = static_cast<char>((block_size >> 8) & 0xff);
+  o[2] = static_cast<char>((block_size >> 16) & 0xff);
+  o[3] = static_cast<char>((block_size >> 24) & 0xff);
+}
+
+void put_record(Emitter &em, const ChromLookup &cl, const ReadView &r, bool revcomp, uint16_t flag, int32_t tid,
+                uint32_t pos, int32_t mtid, int64_t mpos, int64_t isize, int nm, char cv) {
+  if (em.bam) {
+    put_bam_record(em.scratch, r, revcomp, flag, tid, pos, mtid, mpos, isize, nm, cv);
+    em.bam->add(em.scratch.data(), em.scratch.size());
+  }
+  else put_sam_record(*em.sam, cl, r, revcomp, flag, tid, pos, mtid, mpos, isize, nm, cv);
 }
 
 bool chrom_and_posn(const ChromLookup &cl, const ReadView &r, uint32_t p, uint32_t &r_p, uint32_t &r_e,
@@ -165,7 +268,7 @@ std::string make_sam_header(const ChromLookup &cl, int argc, char *const argv[],
 }
 
 MapType format_se(bool allow_ambig, const abg_hit &res, const ChromLookup &cl, const ReadView &r,
-                  std::string &out) {
+                  Emitter &out) {
   const bool ambig = hit_ambig(res);
   const bool valid = !hit_empty(res);
   if (!allow_ambig && ambig) return map_ambig;
@@ -181,7 +284,7 @@ MapType format_se(bool allow_ambig, const abg_hit &res, const ChromLookup &cl, c
 }
 
 MapType format_pe(bool allow_ambig, const abg_hit &p1, const abg_hit &p2, const ChromLookup &cl,
-                  const ReadView &r1, const ReadView &r2, std::string &out) {
+                  const ReadView &r1, const ReadView &r2, Emitter &out) {
   if (hit_empty(p1)) return map_unmapped;
   const bool ambig = hit_ambig(p1);
   if (!allow_ambig && ambig) return map_ambig;
@@ -216,7 +319,7 @@ MapType format_pe(bool allow_ambig, const abg_hit &p1, const abg_hit &p2, const 
 }
 
 void select_output(bool allow_ambig, const ChromLookup &cl, const ReadView &r1, const ReadView &r2,
-                   abg_hit &pe1, abg_hit &pe2, abg_hit &se1, abg_hit &se2, std::string &out) {
+                   abg_hit &pe1, abg_hit &pe2, abg_hit &se1, abg_hit &se2, Emitter &out) {
   const MapType pe_map_type = format_pe(allow_ambig, pe1, pe2, cl, r1, r2, out);
   const bool should_report = !hit_empty(pe1) && (allow_ambig || !hit_ambig(pe1));
   if (!should_report || pe_map_type == map_unmapped) {

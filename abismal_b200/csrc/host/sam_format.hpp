@@ -9,6 +9,7 @@
 #include <string>
 
 #include "abismal_b200.h"
+#include "bam_writer.hpp"
 #include "index_file.hpp"
 
 namespace ab2 {
@@ -22,6 +23,13 @@ struct ReadView {
   uint32_t seq_len;
   const uint32_t *cigar;
   uint32_t n_cigar;
+};
+
+// Where records go: SAM text appended to *sam, or BAM records handed to *bam.
+struct Emitter {
+  std::string *sam = nullptr;
+  BgzfRecordPacker *bam = nullptr;
+  std::string scratch;  // one BAM record under construction
 };
 
 inline bool hit_empty(const abg_hit &h) { return h.pos == 0; }
@@ -38,15 +46,15 @@ uint32_t cigar_rseq_ops(const uint32_t *cigar, uint32_t n);
 // argv/argc are those seen by the `map` subcommand (program name included).
 std::string make_sam_header(const ChromLookup &cl, int argc, char *const argv[], const char *version);
 
-// Appends zero or one record to `out`.
+// Emits zero or one record.
 MapType format_se(bool allow_ambig, const abg_hit &res, const ChromLookup &cl, const ReadView &r,
-                  std::string &out);
-// Appends zero or two records to `out`.
+                  Emitter &out);
+// Emits zero or two records.
 MapType format_pe(bool allow_ambig, const abg_hit &p1, const abg_hit &p2, const ChromLookup &cl,
-                  const ReadView &r1, const ReadView &r2, std::string &out);
+                  const ReadView &r1, const ReadView &r2, Emitter &out);
 // select_output: may reset pe (both ends) / se1 / se2 exactly as the reference does.
 void select_output(bool allow_ambig, const ChromLookup &cl, const ReadView &r1, const ReadView &r2,
-                   abg_hit &pe1, abg_hit &pe2, abg_hit &se1, abg_hit &se2, std::string &out);
+                   abg_hit &pe1, abg_hit &pe2, abg_hit &se1, abg_hit &se2, Emitter &out);
 
 struct SeStats {  // single_end_mapping_statistics
   uint64_t total_reads = 0, reads_mapped_unique = 0, reads_mapped_ambiguous = 0, reads_skipped = 0;

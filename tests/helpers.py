@@ -159,3 +159,78 @@ def assert_results_equal(a, b, paired):
         for i, (p, q) in enumerate(zip(ca, cb)):
             if not np.array_equal(p, q):
                 raise AssertionError("cigar%d differs at record %d: %r vs %r" % (e, i, p, q))
+
+
+# ---- BAM -> SAM text (decoder used to check `-B` output record by record) -------------
+def bam_to_sam_lines(path):
+    """Decode a BAM file (BGZF blocks + BAM records, SAM spec 4.1/4.2) to SAM text lines.
+    Also checks the BGZF framing: BC subfield, BSIZE, CRC32, ISIZE and the EOF marker."""
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    assert raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"), "no BGZF EOF marker"
+    data = bytearray()
+    at = 0
+    while at < len(raw):
+        assert raw[at:at + 4] == b"\x1f\x8b\x08\x04", "bad BGZF block header at %d" % at
+        xlen = struct.unpack_from("<H", raw, at + 10)[0]
+        assert raw[at + 12:at + 16] == b"BC\x02\x00" and xlen == 6
+        bsize = struct.unpack_from("<H", raw, at + 16)[0] + 1
+        body = raw[at + 18:at + bsize - 8]
+        crc, isize = struct.unpack_from("<II", raw, at + bsize - 8)
+        blk = zlib.decompress(body, -15)
+        assert len(blk) == isize and (zlib.crc32(blk) & 0xffffffff) == crc and isize <= 0xff00
+        data += blk
+        at += bsize
+    data = bytes(data)
+    assert data[:4] == b"BAM\x01"
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    text = data[8:8 + l_text].decode()
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, p)[0]
+    p += 4
+    refs = []
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", data, p)[0]
+        name = data[p + 4:p + 4 + l_name - 1].decode()
+        l_ref = struct.unpack_from("<i", data, p + 4 + l_name)[0]
+        refs.append((name, l_ref))
+        p += 8 + l_name
+    lines = [ln + "\n" for ln in text.split("\n") if ln]
+    sq = [ln.rstrip("\n").split("\t") for ln in lines if ln.startswith("@SQ")]
+    assert [(f[1][3:], int(f[2][3:])) for f in sq] == refs
+    nt16 = "=ACMGRSVTWYHKDBN"
+    ops = "MIDNSHP=X"
+    while p < len(data):
+        block_size = struct.unpack_from("<i", data, p)[0]
+        rec = data[p + 4:p + 4 + block_size]
+        p += 4 + block_size
+        tid, pos, l_name, mapq, _bin, n_cig, flag, l_seq, mtid, mpos, tlen = struct.unpack_from("<iiBBHHHiiii", rec, 0)
+        q = 32
+        name = rec[q:q + l_name - 1].decode()
+        q += l_name
+        cig = struct.unpack_from("<%dI" % n_cig, rec, q)
+        q += 4 * n_cig
+        sb = rec[q:q + (l_seq + 1) // 2]
+        q += (l_seq + 1) // 2
+        seq = "".join(nt16[(sb[i >> 1] >> (0 if i & 1 else 4)) & 15] for i in range(l_seq))
+        qual = rec[q:q + l_seq]
+        q += l_seq
+        assert all(b == 0xff for b in qual)
+        tags = []
+        while q < len(rec):
+            tag, typ = rec[q:q + 2].decode(), chr(rec[q + 2])
+            q += 3
+            if typ == "A":
+                tags.append("%s:A:%s" % (tag, chr(rec[q])))
+                q += 1
+            else:
+                fmt = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I"}[typ]
+                tags.append("%s:i:%d" % (tag, struct.unpack_from(fmt, rec, q)[0]))
+                q += struct.calcsize(fmt)
+        rname = refs[tid][0] if tid >= 0 else "*"
+        rnext = "*" if mtid < 0 else ("=" if mtid == tid else refs[mtid][0])
+        cigar = "".join("%d%s" % (c >> 4, ops[c & 15]) for c in cig) or "*"
+        lines.append("\t".join([name, str(flag), rname, str(pos + 1), str(mapq), cigar, rnext, str(mpos + 1), str(tlen),
+                                seq or "*", "*"] + tags) + "\n")
+    return lines

@@ -99,3 +99,37 @@ def test_pe_count_mismatch_is_an_error(workspace):
     _write_fq(workspace.path("mm_2.fq"), recs[:7])
     p = run_tool(["map", "-i", "tests/tRex1.idx", "-o", "tests/mm.sam", "tests/mm_1.fq", "tests/mm_2.fq"], workspace.dir)
     assert p.returncode == 1 and "paired-end batch sizes differ" in p.stderr
+
+
+def test_bam_output_decodes_to_the_sam_records(workspace):
+    """-B: BGZF framing is valid and every BAM record decodes to the SAM line of the same run (SE and PE)."""
+    workspace.need_trex()
+    for tag, args in (("bam_se", ["tests/reads_1.fq"]), ("bam_pe", ["tests/reads_pe_1.fq", "tests/reads_pe_2.fq"])):
+        sam = workspace.map_with(helpers.ORACLE_MAP, tag, ["-i", "tests/tRex1.idx"] + args)
+        bam = workspace.map_with(helpers.ORACLE_MAP, tag + "_b", ["-i", "tests/tRex1.idx"] + args, pre=["-B"])
+        want = helpers.sam_body(sam[0])
+        got = [ln for ln in helpers.bam_to_sam_lines(bam[0]) if not ln.startswith("@PG")]
+        assert len(got) > 1000 and got == want
+        assert open(sam[1]).read() == open(bam[1]).read()
+
+
+def test_pipeline_batching_threads_and_sharding_do_not_change_the_output(workspace):
+    """Small batches, several formatter threads and two mapper workers (the multi-GPU path of the front end,
+    here two CPU engines) give byte-identical SAM and stats in input order."""
+    workspace.need_trex()
+    args = ["-i", "tests/tRex1.idx", "tests/reads_pe_1.fq", "tests/reads_pe_2.fq"]
+    base = workspace.map_with(helpers.ORACLE_MAP, "pipe_a", args, pre=["-t", "1"])
+    for k, pre in enumerate((["-t", "4", "-gpu-batch", "37"], ["-t", "3", "-gpu-batch", "501", "-gpus", "2"],
+                             ["-gpu-batch", "10000"], ["-gpu-batch", "1", "-t", "2", "-gpus", "3"])):
+        if k == 3:  # one read per batch: keep it short
+            for e in (1, 2):
+                with open(workspace.path("reads_pe_%d.fq" % e)) as f, open(workspace.path("few_%d.fq" % e), "w") as g:
+                    g.writelines(f.readlines()[:4 * 300])
+            few = ["-i", "tests/tRex1.idx", "tests/few_1.fq", "tests/few_2.fq"]
+            a = workspace.map_with(helpers.ORACLE_MAP, "pipe_few_a", few)
+            b = workspace.map_with(helpers.ORACLE_MAP, "pipe_few_b", few, pre=pre)
+            assert helpers.sam_body(a[0]) == helpers.sam_body(b[0]) and open(a[1]).read() == open(b[1]).read()
+            continue
+        got = workspace.map_with(helpers.ORACLE_MAP, "pipe_%d" % k, args, pre=pre)
+        assert helpers.sam_body(got[0]) == helpers.sam_body(base[0])
+        assert open(got[1]).read() == open(base[1]).read()
