@@ -261,18 +261,19 @@ private:
   }
 
   void map_on(int device) {
-    std::unique_ptr<Engine> engine;
-    uint32_t engine_max_len = 0;
+    // The engine (index upload to HBM, scratch, streams) is created while the readers parse the first batch.
     const abg_index_view view = index_.view();
+    uint32_t engine_max_len = 256;
+    std::unique_ptr<Engine> engine(new Engine(view, cfg_.params, cfg_.batch_size, engine_max_len, device));
     WorkItem *it = nullptr;
     while (!failed_ && to_map_.pop(it)) {
       const uint32_t n = it->b1.size();
       if (n != 0) {
         StageClock::Scope sc(t_map);
         const uint32_t max_len = std::max(it->b1.max_read_len(), cfg_.paired_end ? it->b2.max_read_len() : 0u);
-        if (!engine || max_len > engine_max_len) {
+        if (max_len > engine_max_len) {
           engine.reset();
-          engine_max_len = std::max<uint32_t>(256, max_len);
+          engine_max_len = max_len;
           engine.reset(new Engine(view, cfg_.params, cfg_.batch_size, engine_max_len, device));
         }
         it->rb.resize(n, cfg_.params.cigar_stride, cfg_.paired_end);

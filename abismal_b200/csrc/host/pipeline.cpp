@@ -7,6 +7,26 @@ HostMemHooks &host_mem_hooks() {
   return h;
 }
 
+void *host_buf_alloc(size_t bytes) {
+  void *p = nullptr;
+  const HostMemHooks &h = host_mem_hooks();
+  if (h.alloc) {
+    if (h.alloc(bytes ? bytes : 1, &p) != 0 || !p) throw std::bad_alloc();
+  }
+  else {
+    p = std::malloc(bytes ? bytes : 1);
+    if (!p) throw std::bad_alloc();
+  }
+  return p;
+}
+
+void host_buf_free(void *p) {
+  if (!p) return;
+  const HostMemHooks &h = host_mem_hooks();
+  if (h.release) h.release(p);
+  else std::free(p);
+}
+
 WorkerPool::WorkerPool(unsigned n_threads) {
   const unsigned extra = n_threads > 1 ? n_threads - 1 : 0;  // the caller of run() works too
   threads_.reserve(extra);

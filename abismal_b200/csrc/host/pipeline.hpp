@@ -14,6 +14,8 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <algorithm>
 #include <deque>
 #include <exception>
 #include <functional>
@@ -34,43 +36,49 @@ struct HostMemHooks {
 };
 HostMemHooks &host_mem_hooks();
 
-template <class T>
-struct PinnedAlloc {
-  using value_type = T;
-  PinnedAlloc() = default;
-  template <class U>
-  PinnedAlloc(const PinnedAlloc<U> &) {}
-  T *allocate(size_t n) {
-    void *p = nullptr;
-    const HostMemHooks &h = host_mem_hooks();
-    if (h.alloc) {
-      if (h.alloc(n * sizeof(T), &p) != 0 || !p) throw std::bad_alloc();
-    }
-    else {
-      p = std::malloc(n * sizeof(T) ? n * sizeof(T) : 1);
-      if (!p) throw std::bad_alloc();
-    }
-    return static_cast<T *>(p);
-  }
-  void deallocate(T *p, size_t) {
-    const HostMemHooks &h = host_mem_hooks();
-    if (h.release) h.release(p);
-    else std::free(p);
-  }
-  // leave elements uninitialised on resize(): these are plain buffers the GPU fills
-  template <class U, class... Args>
-  void construct(U *p, Args &&...args) {
-    if constexpr (sizeof...(Args) == 0) (void)p;
-    else ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...);
-  }
-  template <class U>
-  bool operator==(const PinnedAlloc<U> &) const { return true; }
-  template <class U>
-  bool operator!=(const PinnedAlloc<U> &) const { return false; }
-};
+void *host_buf_alloc(size_t bytes);  // page-locked when the hooks are set, malloc otherwise; throws std::bad_alloc
+void host_buf_free(void *p);
 
+// Growable array of trivially-copyable T in (possibly page-locked) host memory; elements are never
+// value-initialised: these are plain buffers the parser or the GPU fills.
 template <class T>
-using pinned_vector = std::vector<T, PinnedAlloc<T>>;
+class pinned_vector {
+public:
+  pinned_vector() = default;
+  pinned_vector(const pinned_vector &) = delete;
+  pinned_vector &operator=(const pinned_vector &) = delete;
+  pinned_vector(pinned_vector &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr; o.n_ = o.cap_ = 0; }
+  ~pinned_vector() { host_buf_free(p_); }
+  T *data() { return p_; }
+  const T *data() const { return p_; }
+  size_t size() const { return n_; }
+  size_t capacity() const { return cap_; }
+  bool empty() const { return n_ == 0; }
+  T &operator[](size_t i) { return p_[i]; }
+  const T &operator[](size_t i) const { return p_[i]; }
+  void clear() { n_ = 0; }
+  void reserve(size_t cap) {
+    if (cap <= cap_) return;
+    T *q = static_cast<T *>(host_buf_alloc(cap * sizeof(T)));
+    if (n_) std::memcpy(q, p_, n_ * sizeof(T));
+    host_buf_free(p_);
+    p_ = q;
+    cap_ = cap;
+  }
+  void resize(size_t n) {
+    if (n > cap_) reserve(std::max(n, cap_ + cap_ / 2));
+    n_ = n;
+  }
+  void append(const T *src, size_t n) {
+    if (n_ + n > cap_) reserve(std::max(n_ + n, cap_ + cap_ / 2));
+    std::memcpy(p_ + n_, src, n * sizeof(T));
+    n_ += n;
+  }
+
+private:
+  T *p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+};
 
 // ---- bounded multi-producer multi-consumer queue ---------------------------------
 template <class T>

@@ -46,6 +46,9 @@ public:
 private:
   bool getline(const char *&line, size_t &len);  // bgzf_getline semantics
   bool fill();
+  bool fill_more();
+  bool fast_record(ReadBatch &out);
+  void push_read(ReadBatch &out, const char *name, size_t name_len, const char *line, size_t len);
 
   std::string filename_;
   void *file_ = nullptr;  // gzFile

@@ -17,14 +17,6 @@ inline void put_uint(std::string &o, uint64_t v) {
   } while (v);
   while (n) o += tmp[--n];
 }
-inline void put_int(std::string &o, int64_t v) {
-  if (v < 0) {
-    o += '-';
-    put_uint(o, static_cast<uint64_t>(-v));
-  }
-  else put_uint(o, static_cast<uint64_t>(v));
-}
-
 // SEQ passes through BAM's 4-bit alphabet in htslib (bam_set1 encodes,
 // sam_format1 decodes): upper-cases, keeps IUPAC codes, anything else -> N.
 struct Nt16 {
@@ -61,66 +53,85 @@ struct Nt16 {
 };
 const Nt16 nt16;
 
-void put_seq(std::string &o, const ReadView &r, bool revcomp) {
-  if (r.seq_len == 0) {
-    o += '*';
-    return;
-  }
-  const size_t at = o.size();
-  o.resize(at + r.seq_len);
-  char *d = &o[at];
-  if (!revcomp)
-    for (uint32_t i = 0; i < r.seq_len; ++i) d[i] = nt16.fwd[static_cast<unsigned char>(r.seq[i])];
-  else
-    for (uint32_t i = 0; i < r.seq_len; ++i)
-      d[i] = nt16.rc[static_cast<unsigned char>(r.seq[r.seq_len - 1 - i])];
+// raw-pointer writers for the SAM text (one reservation per record instead of a capacity check per byte)
+inline char *wr_uint(char *p, uint64_t v) {
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = static_cast<char>('0' + v % 10);
+    v /= 10;
+  } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
 }
-
-void put_cigar(std::string &o, const uint32_t *cig, uint32_t n) {
-  static const char ops[] = "MIDNSHP=XB??????";
-  if (n == 0) {
-    o += '*';
-    return;
+inline char *wr_int(char *p, int64_t v) {
+  if (v < 0) {
+    *p++ = '-';
+    return wr_uint(p, static_cast<uint64_t>(-v));
   }
-  for (uint32_t i = 0; i < n; ++i) {
-    put_uint(o, cig[i] >> 4);
-    o += ops[cig[i] & 15u];
-  }
+  return wr_uint(p, static_cast<uint64_t>(v));
 }
-
-// real chromosomes are names[1 .. n-2]; tid = chrom_idx - 1
-void put_rname(std::string &o, const ChromLookup &cl, int32_t tid) {
+inline char *wr_str(char *p, const char *s, size_t n) {
+  std::memcpy(p, s, n);
+  return p + n;
+}
+inline const std::string *rname_of(const ChromLookup &cl, int32_t tid) {
   const int64_t n_real = static_cast<int64_t>(cl.names.size()) - 2;
-  if (tid >= 0 && tid < n_real) o += cl.names[static_cast<size_t>(tid) + 1];
-  else o += '*';
+  return (tid >= 0 && tid < n_real) ? &cl.names[static_cast<size_t>(tid) + 1] : nullptr;
 }
 
 void put_sam_record(std::string &o, const ChromLookup &cl, const ReadView &r, bool revcomp, uint16_t flag,
                     int32_t tid, uint32_t pos, int32_t mtid, int64_t mpos, int64_t isize, int nm, char cv) {
-  o.append(r.name, r.name_len);
-  o += '\t';
-  put_uint(o, flag);
-  o += '\t';
-  put_rname(o, cl, tid);
-  o += '\t';
-  put_uint(o, static_cast<uint64_t>(pos) + 1);
-  o += "\t255\t";
-  put_cigar(o, r.cigar, r.n_cigar);
-  o += '\t';
-  if (mtid < 0) o += '*';
-  else if (mtid == tid) o += '=';
-  else put_rname(o, cl, mtid);
-  o += '\t';
-  put_int(o, mpos + 1);
-  o += '\t';
-  put_int(o, isize);
-  o += '\t';
-  put_seq(o, r, revcomp);
-  o += "\t*\tNM:i:";
-  put_int(o, nm);
-  o += "\tCV:A:";
-  o += cv;
-  o += '\n';
+  const std::string *rn = rname_of(cl, tid);
+  const std::string *mn = (mtid >= 0 && mtid != tid) ? rname_of(cl, mtid) : nullptr;
+  const size_t at = o.size();
+  const size_t max_len = static_cast<size_t>(r.name_len) + r.seq_len + 12u * r.n_cigar + (rn ? rn->size() : 1) +
+                         (mn ? mn->size() : 1) + 160;
+  o.resize(at + max_len);
+  char *p = &o[at];
+  p = wr_str(p, r.name, r.name_len);
+  *p++ = '\t';
+  p = wr_uint(p, flag);
+  *p++ = '\t';
+  if (rn) p = wr_str(p, rn->data(), rn->size());
+  else *p++ = '*';
+  *p++ = '\t';
+  p = wr_uint(p, static_cast<uint64_t>(pos) + 1);
+  p = wr_str(p, "\t255\t", 5);
+  if (r.n_cigar == 0) *p++ = '*';
+  else {
+    static const char ops[] = "MIDNSHP=XB??????";
+    for (uint32_t i = 0; i < r.n_cigar; ++i) {
+      p = wr_uint(p, r.cigar[i] >> 4);
+      *p++ = ops[r.cigar[i] & 15u];
+    }
+  }
+  *p++ = '\t';
+  if (mtid < 0) *p++ = '*';
+  else if (mtid == tid) *p++ = '=';
+  else if (mn) p = wr_str(p, mn->data(), mn->size());
+  else *p++ = '*';
+  *p++ = '\t';
+  p = wr_int(p, mpos + 1);
+  *p++ = '\t';
+  p = wr_int(p, isize);
+  *p++ = '\t';
+  if (r.seq_len == 0) *p++ = '*';
+  else if (!revcomp) {
+    for (uint32_t i = 0; i < r.seq_len; ++i) p[i] = nt16.fwd[static_cast<unsigned char>(r.seq[i])];
+    p += r.seq_len;
+  }
+  else {
+    const char *s = r.seq + r.seq_len - 1;
+    for (uint32_t i = 0; i < r.seq_len; ++i) p[i] = nt16.rc[static_cast<unsigned char>(s[-static_cast<int64_t>(i)])];
+    p += r.seq_len;
+  }
+  p = wr_str(p, "\t*\tNM:i:", 8);
+  p = wr_int(p, nm);
+  p = wr_str(p, "\tCV:A:", 6);
+  *p++ = cv;
+  *p++ = '\n';
+  o.resize(static_cast<size_t>(p - o.data()));
 }
 
 inline void le16(std::string &o, uint32_t v) {
