@@ -1,5 +1,10 @@
 #include "index_file.hpp"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -43,7 +48,11 @@ bool ChromLookup::chrom_idx_and_offset(uint32_t pos, uint32_t ref_len, int32_t &
   return pos + ref_len <= starts[chrom_idx + 1];
 }
 
-void IndexFile::read(const std::string &path) {
+IndexFile::~IndexFile() {
+  if (map_base_) munmap(map_base_, map_len_);
+}
+
+void IndexFile::read(const std::string &path, bool map_file) {
   static const char *error_msg = "failed loading index file";
   FILE *in = std::fopen(path.c_str(), "rb");
   if (!in) throw std::runtime_error("cannot open input file " + path);
@@ -81,6 +90,48 @@ void IndexFile::read(const std::string &path) {
   read_array(in, cl.starts, static_cast<uint64_t>(n_chroms) + 1, cl_msg);
 
   const uint64_t genome_words = (static_cast<uint64_t>(cl.genome_size()) + 15) / 16;
+  if (map_file) {
+    // header parsed; everything from here on is fixed-size arrays: map the file and point into it
+    const long at = std::ftell(in);
+    struct stat st;
+    if (at < 0 || fstat(fileno(in), &st) != 0) throw std::runtime_error(error_msg);
+    const size_t len = static_cast<size_t>(st.st_size);
+    void *base = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fileno(in), 0);
+    if (base == MAP_FAILED) throw std::runtime_error(error_msg);
+    map_base_ = base;
+    map_len_ = len;
+    const unsigned char *p = static_cast<const unsigned char *>(base) + at, *end = static_cast<const unsigned char *>(base) + len;
+    const auto take = [&](uint64_t bytes) {
+      if (static_cast<uint64_t>(end - p) < bytes) throw std::runtime_error(error_msg);
+      const unsigned char *q = p;
+      p += bytes;
+      return q;
+    };
+    const auto pod32 = [&]() { uint32_t v; std::memcpy(&v, take(4), 4); return v; };
+    const auto pod64 = [&]() { uint64_t v; std::memcpy(&v, take(8), 8); return v; };
+    std::memset(&mapped_, 0, sizeof mapped_);
+    mapped_.genome = reinterpret_cast<const uint64_t *>(take(genome_words * 8));
+    mapped_.genome_words = genome_words;
+    mapped_.genome_size = cl.genome_size();
+    max_candidates = pod32();
+    counter_size = pod64();
+    counter_size_three = pod64();
+    index_size = pod64();
+    index_size_three = pod64();
+    if (counter_size != (1ull << 25) || counter_size_three != 43046721ull) throw std::runtime_error(error_msg);
+    mapped_.counter = reinterpret_cast<const uint32_t *>(take((counter_size + 1) * 4));
+    mapped_.counter_t = reinterpret_cast<const uint32_t *>(take((counter_size_three + 1) * 4));
+    mapped_.counter_a = reinterpret_cast<const uint32_t *>(take((counter_size_three + 1) * 4));
+    mapped_.index = reinterpret_cast<const uint32_t *>(take(index_size * 4));
+    mapped_.index_t = reinterpret_cast<const uint32_t *>(take(index_size_three * 4));
+    mapped_.index_a = reinterpret_cast<const uint32_t *>(take(index_size_three * 4));
+    mapped_.counter_size = counter_size;
+    mapped_.counter_size_three = counter_size_three;
+    mapped_.index_size = index_size;
+    mapped_.index_size_three = index_size_three;
+    mapped_.max_candidates = max_candidates;
+    return;
+  }
   // one spare zero word: the look-ahead word of a compare at the very end
   read_array(in, genome, genome_words, error_msg);
   genome.push_back(0);
@@ -102,6 +153,7 @@ void IndexFile::read(const std::string &path) {
 }
 
 abg_index_view IndexFile::view() const {
+  if (map_base_) return mapped_;
   abg_index_view v;
   std::memset(&v, 0, sizeof(v));
   v.genome = genome.data();

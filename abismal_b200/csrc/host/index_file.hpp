@@ -29,9 +29,21 @@ struct IndexFile {
   std::vector<uint64_t> genome;
   std::vector<uint32_t> counter, counter_t, counter_a, index, index_t, index_a;
 
-  // throws std::runtime_error with the reference's messages
-  void read(const std::string &path);
+  IndexFile() = default;
+  IndexFile(const IndexFile &) = delete;
+  IndexFile &operator=(const IndexFile &) = delete;
+  ~IndexFile();
+
+  // throws std::runtime_error with the reference's messages.  map_file: leave the arrays in a read-only
+  // mapping of the file instead of copying them into the vectors (they are only read once, by the upload
+  // to HBM); view() then points into the mapping.
+  void read(const std::string &path, bool map_file = false);
   abg_index_view view() const;
+
+private:
+  void *map_base_ = nullptr;
+  size_t map_len_ = 0;
+  abg_index_view mapped_{};
 };
 
 }  // namespace ab2

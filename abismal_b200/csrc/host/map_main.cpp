@@ -12,6 +12,7 @@
 #include <cstring>
 #include <ctime>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -85,45 +86,64 @@ struct ResultBuffers {
   }
 };
 
-// The mapping engine behind the C ABI.
-class Engine {
+// The index resident on one device (HBM in the product, host memory in the oracle test tool); shared by the
+// mapper workers of that device.
+class DeviceIndex {
 public:
-  Engine(const abg_index_view &view, const abg_params &params, uint32_t max_batch, uint32_t max_len,
-         int device)
-    : params_(params) {
+  DeviceIndex(const abg_index_view &view, int device) {
 #ifdef ABISMAL_ENGINE_ORACLE
-    (void)max_batch;
-    (void)max_len;
     (void)device;
     if (abo_index_create(&view, &oidx_) != 0) throw std::runtime_error(abo_last_error());
 #else
     if (abg_index_create(&view, device, &idx_) != 0) throw std::runtime_error(abg_last_error());
-    if (abg_mapper_create(idx_, &params, max_batch, max_len, 0, &mapper_) != 0)
+#endif
+  }
+  ~DeviceIndex() {
+#ifdef ABISMAL_ENGINE_ORACLE
+    abo_index_destroy(oidx_);
+#else
+    abg_index_destroy(idx_);
+#endif
+  }
+  DeviceIndex(const DeviceIndex &) = delete;
+  DeviceIndex &operator=(const DeviceIndex &) = delete;
+#ifdef ABISMAL_ENGINE_ORACLE
+  abo_index *oidx_ = nullptr;
+#else
+  abg_index *idx_ = nullptr;
+#endif
+};
+
+// The mapping engine behind the C ABI: streams, staging and scratch of one mapper worker.
+class Engine {
+public:
+  Engine(std::shared_ptr<DeviceIndex> index, const abg_params &params, uint32_t max_batch, uint32_t max_len)
+    : index_(std::move(index)), params_(params) {
+#ifdef ABISMAL_ENGINE_ORACLE
+    (void)max_batch;
+    (void)max_len;
+#else
+    if (abg_mapper_create(index_->idx_, &params, max_batch, max_len, 0, &mapper_) != 0)
       throw std::runtime_error(abg_last_error());
 #endif
   }
   ~Engine() {
-#ifdef ABISMAL_ENGINE_ORACLE
-    abo_index_destroy(oidx_);
-#else
+#ifndef ABISMAL_ENGINE_ORACLE
     abg_mapper_destroy(mapper_);
-    abg_index_destroy(idx_);
 #endif
   }
   void map(const abg_batch &b, abg_results &r) {
 #ifdef ABISMAL_ENGINE_ORACLE
-    if (abo_map_batch(oidx_, &params_, &b, &r, nullptr) != 0) throw std::runtime_error(abo_last_error());
+    if (abo_map_batch(index_->oidx_, &params_, &b, &r, nullptr) != 0) throw std::runtime_error(abo_last_error());
 #else
     if (abg_map_batch(mapper_, &b, &r) != 0) throw std::runtime_error(abg_last_error());
 #endif
   }
 
 private:
+  std::shared_ptr<DeviceIndex> index_;
   abg_params params_;
-#ifdef ABISMAL_ENGINE_ORACLE
-  abo_index *oidx_ = nullptr;
-#else
-  abg_index *idx_ = nullptr;
+#ifndef ABISMAL_ENGINE_ORACLE
   abg_mapper *mapper_ = nullptr;
 #endif
 };
@@ -163,7 +183,7 @@ struct StageClock {  // busy seconds of one pipeline stage (reported with -v)
 
 struct MapConfig {
   bool paired_end = false, allow_ambig = false, write_bam = false, verbose = false;
-  uint32_t batch_size = 0, n_threads = 1;
+  uint32_t batch_size = 0, n_threads = 1, workers_per_gpu = 2;
   int bam_level = -1;
   std::vector<int> devices;
   abg_params params{};
@@ -175,10 +195,10 @@ class MapPipeline {
 public:
   MapPipeline(const MapConfig &cfg, const ab2::IndexFile &index, const std::string &fq1, const std::string &fq2,
               FILE *out)
-    : cfg_(cfg), index_(index), out_(out), rl1_(fq1), free_(kItems), q12_(kItems), to_map_(kItems),
-      to_out_(kItems), pool_(cfg.n_threads) {
+    : cfg_(cfg), index_(index), out_(out), rl1_(fq1), n_items_(4 + 2 * cfg.devices.size() * cfg.workers_per_gpu),
+      free_(n_items_), q12_(n_items_), to_map_(n_items_), to_out_(n_items_), pool_(cfg.n_threads) {
     if (cfg.paired_end) rl2_.reset(new ab2::FastqReader(fq2));
-    items_.resize(kItems);
+    items_.resize(n_items_);
     for (WorkItem &it : items_) free_.push(&it);
   }
 
@@ -186,8 +206,16 @@ public:
     std::vector<std::thread> th;
     th.emplace_back([this] { guarded([this] { read_end1(); }); });
     if (cfg_.paired_end) th.emplace_back([this] { guarded([this] { read_end2(); }); });
-    n_mappers_live_ = static_cast<int>(cfg_.devices.size());
-    for (int dev : cfg_.devices) th.emplace_back([this, dev] { guarded([this, dev] { map_on(dev); }); });
+    // workers_per_gpu mapper workers per device share its index: while one waits for the tail of its batch
+    // (last kernel, copy back, host scatter) the other keeps the GPU busy
+    n_mappers_live_ = static_cast<int>(cfg_.devices.size() * cfg_.workers_per_gpu);
+    std::vector<std::shared_ptr<std::promise<std::shared_ptr<DeviceIndex>>>> promises;
+    for (int dev : cfg_.devices) {
+      auto pr = std::make_shared<std::promise<std::shared_ptr<DeviceIndex>>>();
+      std::shared_future<std::shared_ptr<DeviceIndex>> fut = pr->get_future().share();
+      for (uint32_t w = 0; w < cfg_.workers_per_gpu; ++w)
+        th.emplace_back([this, dev, w, pr, fut] { guarded([&] { map_on(dev, w == 0 ? pr.get() : nullptr, fut); }); });
+    }
     th.emplace_back([this] { guarded([this] { write_out(); }); });
     for (std::thread &t : th) t.join();
     if (error_) std::rethrow_exception(error_);
@@ -199,8 +227,6 @@ public:
   StageClock t_read1, t_read2, t_map, t_format, t_write;
 
 private:
-  static constexpr size_t kItems = 6;
-
   template <class F>
   void guarded(F f) {
     try {
@@ -260,11 +286,21 @@ private:
     to_map_.close();
   }
 
-  void map_on(int device) {
-    // The engine (index upload to HBM, scratch, streams) is created while the readers parse the first batch.
-    const abg_index_view view = index_.view();
+  void map_on(int device, std::promise<std::shared_ptr<DeviceIndex>> *lead,
+              std::shared_future<std::shared_ptr<DeviceIndex>> shared) {
+    // The index upload to HBM and the engine (scratch, streams) are set up while the readers parse the first
+    // batches; the lead worker of a device uploads, the others wait for it.
+    if (lead) {
+      try {
+        lead->set_value(std::make_shared<DeviceIndex>(index_.view(), device));
+      }
+      catch (...) {
+        lead->set_exception(std::current_exception());
+      }
+    }
+    std::shared_ptr<DeviceIndex> dev_index = shared.get();
     uint32_t engine_max_len = 256;
-    std::unique_ptr<Engine> engine(new Engine(view, cfg_.params, cfg_.batch_size, engine_max_len, device));
+    std::unique_ptr<Engine> engine(new Engine(dev_index, cfg_.params, cfg_.batch_size, engine_max_len));
     WorkItem *it = nullptr;
     while (!failed_ && to_map_.pop(it)) {
       const uint32_t n = it->b1.size();
@@ -274,7 +310,7 @@ private:
         if (max_len > engine_max_len) {
           engine.reset();
           engine_max_len = max_len;
-          engine.reset(new Engine(view, cfg_.params, cfg_.batch_size, engine_max_len, device));
+          engine.reset(new Engine(dev_index, cfg_.params, cfg_.batch_size, engine_max_len));
         }
         it->rb.resize(n, cfg_.params.cigar_stride, cfg_.paired_end);
         abg_batch batch;
@@ -370,6 +406,7 @@ private:
   FILE *out_;
   ab2::FastqReader rl1_;
   std::unique_ptr<ab2::FastqReader> rl2_;
+  size_t n_items_;
   std::vector<WorkItem> items_;
   ab2::BoundedQueue<WorkItem *> free_, q12_, to_map_, to_out_;
   ab2::WorkerPool pool_;
@@ -384,7 +421,7 @@ int map_main(int argc, char *argv[]) {
     bool verbose = false, g_to_a_conversion = false, allow_ambig = false, pbat_mode = false;
     bool random_pbat = false, write_bam_fmt = false, stats_as_json = false, help = false, about = false;
     uint32_t max_candidates = 0, n_threads = 0, min_dist = 32, max_dist = 3000;
-    uint32_t batch_size = 1u << 17, device = 0, n_gpus = 1;
+    uint32_t batch_size = 1u << 18, device = 0, n_gpus = 1, gpu_workers = 2;
     double valid_frac = 0.1;
     std::string index_file, genome_file, outfile, stats_outfile;
 
@@ -411,6 +448,7 @@ int map_main(int argc, char *argv[]) {
     opt.add("gpu-batch", '\0', "reads (or pairs) per GPU batch", false, batch_size);
     opt.add("device", '\0', "first CUDA device ordinal", false, device);
     opt.add("gpus", '\0', "number of GPUs to shard batches over (index replicated)", false, n_gpus);
+    opt.add("gpu-workers", '\0', "mapper workers (streams) per GPU", false, gpu_workers);
     const std::vector<std::string> leftover = opt.parse(argc, argv);
 
     const std::string usage = opt.help_message(argv[0], "<reads-fq1> [<reads-fq2>]");
@@ -452,6 +490,7 @@ int map_main(int argc, char *argv[]) {
     }
     if (batch_size == 0) batch_size = 1;
     if (n_gpus == 0) n_gpus = 1;
+    if (gpu_workers == 0) gpu_workers = 1;
 
     if (verbose) {
       log_msg(paired_end ? "input (PE): " + reads_file + ", " + reads_file2 : "input (SE): " + reads_file);
@@ -468,7 +507,11 @@ int map_main(int argc, char *argv[]) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!index_file.empty()) {
       if (verbose) log_msg("loading index " + index_file);
+#ifdef ABISMAL_ENGINE_ORACLE
       index.read(index_file);
+#else
+      index.read(index_file, true);  // arrays stay in a mapping of the file: they are read once, by the upload to HBM
+#endif
       if (verbose)
         log_msg("loading time: " +
                 fmt_secs(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
@@ -502,6 +545,7 @@ int map_main(int argc, char *argv[]) {
     cfg.verbose = verbose;
     cfg.batch_size = batch_size;
     cfg.n_threads = n_threads;
+    cfg.workers_per_gpu = gpu_workers;
     if (const char *e = std::getenv("ABISMAL_B200_BAM_LEVEL")) cfg.bam_level = std::atoi(e);
     for (uint32_t g = 0; g < n_gpus; ++g) cfg.devices.push_back(static_cast<int>(device + g));
 

@@ -80,6 +80,7 @@ struct abg_index {
 
 constexpr uint32_t kInlineOps = 16;   // CIGAR ops per read copied back with the batch; longer ones are fetched afterwards
 constexpr uint32_t kMaxChunks = 256;  // sub-batches one abg_map_batch call is pipelined over
+constexpr uint32_t kWorkWords = 1 + 4 * kMaxChunks;
 
 struct abg_mapper {
   abg_index *idx = nullptr;
@@ -93,9 +94,17 @@ struct abg_mapper {
   cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_out[kMaxChunks] = {};
   float last_ms = 0.f;
   // launch shape
-  int grid = 0, minb = 0;
+  int grid = 0, minb = 0, grid_scratch = 0;
   size_t smem = 0;
   const void *kernel = nullptr;
+  // two-phase launch: seed_kernel -> align_kernel -> map_reads_kernel over the redo list
+  bool split = false;
+  const void *kernel_s = nullptr, *kernel_a = nullptr;
+  int grid_s = 0, grid_a = 0;
+  uint32_t n_pass = 1, set_slots = 0;
+  uint64_t *d_sets = nullptr;
+  unsigned int *d_redo_flag = nullptr;
+  uint32_t *d_redo_list = nullptr;
   // device batch
   char *d_seq[2] = {nullptr, nullptr};
   uint32_t *d_off[2] = {nullptr, nullptr};
@@ -109,7 +118,7 @@ struct abg_mapper {
   int16_t *d_mem_scr = nullptr;
   uint64_t *d_tb = nullptr;
   uint32_t tb_words = 0;
-  unsigned int *d_work = nullptr;   // [0] error flag, [1 + j] work counter of chunk j
+  unsigned int *d_work = nullptr;   // [0] error flag, [1 + 4j ..] chunk j: work counters of map / seed / align, redo count
   unsigned long long *d_counters = nullptr;
   // pinned staging (used when the caller's buffers are pageable)
   char *h_seq[2] = {nullptr, nullptr};
@@ -148,8 +157,17 @@ int stage_offsets(abg_mapper *m, const uint32_t *off, uint32_t c0, uint32_t c1, 
   return ABG_OK;
 }
 
-void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint32_t n, unsigned int *work) {
+void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint32_t n, uint32_t chunk_idx) {
   std::memset(&P, 0, sizeof P);
+  unsigned int *work = m->d_work + 1 + 4 * chunk_idx;
+  if (m->split) {
+    P.sets = m->d_sets + (size_t)c0 * m->n_pass * (ab2dev::kSetStateWords + m->set_slots);
+    P.set_slots = m->set_slots;
+    P.n_pass = m->n_pass;
+    P.redo_flag = m->d_redo_flag + c0;
+    P.redo_list = m->d_redo_list + c0;
+    P.redo_count = work + 3;
+  }
   P.ix = m->idx->dev;
   P.n = n;
   const uint32_t stride = m->params.cigar_stride;
@@ -181,12 +199,37 @@ void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint
   P.counters = m->d_counters;
 }
 
+int launch_one(const void *kernel, int grid, size_t smem, ab2dev::KernelParams &P, cudaStream_t st) {
+  void *args[] = {&P};
+  ABG_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(ab2dev::kThreadsPerBlock), args, smem, st));
+  return ABG_OK;
+}
+
+// One sub-batch on stream st.  Two-phase mode: seeding (one warp per read strand), then alignment/mating (one
+// warp per pair) from the stored candidate sets, then the single-kernel path for the few pairs whose sets
+// outgrew the stored form.  P.work_counter points at this chunk's {map, seed, align} counters + redo count.
 int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st) {
   if (P.n == 0) return ABG_OK;
-  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid, ((uint64_t)P.n + ab2dev::kWarpsPerBlock - 1) / ab2dev::kWarpsPerBlock);
-  void *args[] = {&P};
-  ABG_CUDA(cudaLaunchKernel(m->kernel, dim3(grid), dim3(ab2dev::kThreadsPerBlock), args, m->smem, st));
-  return ABG_OK;
+  const uint64_t wpb = ab2dev::kWarpsPerBlock;
+  int rc;
+  if (!m->split) {
+    const int grid = (int)std::min<uint64_t>((uint64_t)m->grid, ((uint64_t)P.n + wpb - 1) / wpb);
+    return launch_one(m->kernel, grid, m->smem, P, st);
+  }
+  unsigned int *work = P.work_counter;
+  ABG_CUDA(cudaMemsetAsync(P.redo_flag, 0, (size_t)P.n * sizeof(unsigned int), st));
+  ab2dev::KernelParams Q = P;
+  Q.work_counter = work + 1;
+  const uint64_t n_work = m->paired ? (uint64_t)P.n * m->n_pass : P.n;
+  if ((rc = launch_one(m->kernel_s, (int)std::min<uint64_t>((uint64_t)m->grid_s, (n_work + wpb - 1) / wpb), m->smem, Q, st)))
+    return rc;
+  Q.work_counter = work + 2;
+  if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a, ((uint64_t)P.n + wpb - 1) / wpb), m->smem, Q, st)))
+    return rc;
+  Q.work_counter = work;
+  Q.item_list = P.redo_list;
+  Q.n_items_ptr = P.redo_count;
+  return launch_one(m->kernel, m->grid, m->smem, Q, st);
 }
 
 struct ResultDst {  // where hit records and CIGAR lengths land: the caller's buffers when pinned, else staging
@@ -480,8 +523,41 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     return fail(ABG_ERR_CUDA, "abg_mapper_create: kernel does not fit on an SM");
   }
   m->grid = n_sm * per_sm;
+  {
+    // two-phase launch (default); ABISMAL_B200_SPLIT=0 keeps everything in map_reads_kernel
+    const char *e = std::getenv("ABISMAL_B200_SPLIT");
+    m->split = !(e && std::atoi(e) == 0);
+  }
+  int grid_max = m->grid;
+  if (m->split) {
+    m->kernel_s = m->minb == 2 ? (const void *)ab2dev::seed_kernel<2>
+                : m->minb == 4 ? (const void *)ab2dev::seed_kernel<4>
+                               : (const void *)ab2dev::seed_kernel<3>;
+    m->kernel_a = m->minb == 2 ? (const void *)ab2dev::align_kernel<2>
+                : m->minb == 4 ? (const void *)ab2dev::align_kernel<4>
+                               : (const void *)ab2dev::align_kernel<3>;
+    int per_s = 0, per_a = 0;
+    ABG_M(cudaFuncSetAttribute(m->kernel_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+    ABG_M(cudaFuncSetAttribute(m->kernel_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+    ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_s, m->kernel_s, ab2dev::kThreadsPerBlock, m->smem));
+    ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, m->kernel_a, ab2dev::kThreadsPerBlock, m->smem));
+    if (per_s < 1 || per_a < 1) {
+      abg_mapper_destroy(m);
+      return fail(ABG_ERR_CUDA, "abg_mapper_create: kernel does not fit on an SM");
+    }
+    m->grid_s = n_sm * per_s;
+    m->grid_a = n_sm * per_a;
+    grid_max = std::max(grid_max, std::max(m->grid_s, m->grid_a));
+    const bool rpbat = (p->mode & ABG_MODE_RANDOM_PBAT) != 0;
+    m->n_pass = m->paired ? (rpbat ? 8u : 4u) : 1u;
+    m->set_slots = m->paired ? ab2dev::kSetSlotsPe : ab2dev::kSetSlotsSe;
+    ABG_M(cudaMalloc(&m->d_sets, (size_t)max_batch * m->n_pass * (ab2dev::kSetStateWords + m->set_slots) * sizeof(uint64_t)));
+    ABG_M(cudaMalloc(&m->d_redo_flag, (size_t)max_batch * sizeof(unsigned int)));
+    ABG_M(cudaMalloc(&m->d_redo_list, (size_t)max_batch * sizeof(uint32_t)));
+  }
   // two scratch sets: consecutive chunks run on alternating streams and may overlap at their tails
-  const size_t slots = (size_t)m->grid * ab2dev::kWarpsPerBlock * 2;
+  m->grid_scratch = grid_max;
+  const size_t slots = (size_t)grid_max * ab2dev::kWarpsPerBlock * 2;
 
   m->seq_cap = (size_t)max_batch * max_read_len;
   const uint32_t w = std::min(kInlineOps, stride);
@@ -508,7 +584,7 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   }
   m->tb_words = ab2dev::tb_sm_words(m->ml);
   ABG_M(cudaMalloc(&m->d_tb, slots * 2 * m->tb_words * 32 * sizeof(uint64_t)));
-  ABG_M(cudaMalloc(&m->d_work, (kMaxChunks + 2) * sizeof(unsigned int)));
+  ABG_M(cudaMalloc(&m->d_work, kWorkWords * sizeof(unsigned int)));
   ABG_M(cudaMallocHost(&m->h_flags, 2 * sizeof(unsigned int)));
   if (m->count_work) ABG_M(cudaMalloc(&m->d_counters, 6 * sizeof(unsigned long long)));
 #undef ABG_M
@@ -542,6 +618,9 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFree(m->d_tb);
   cudaFree(m->d_work);
   cudaFree(m->d_counters);
+  cudaFree(m->d_sets);
+  cudaFree(m->d_redo_flag);
+  cudaFree(m->d_redo_list);
   cudaFreeHost(m->h_flags);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -601,8 +680,8 @@ int abg_mapper_run(abg_mapper *m) {
   if (!m) return fail(ABG_ERR_INVALID, "abg_mapper_run: null mapper");
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ab2dev::KernelParams P;
-  fill_params(m, P, 0, m->cur_n, m->d_work + 1);
-  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, 2 * sizeof(unsigned int), m->stream));
+  fill_params(m, P, 0, m->cur_n, 0);
+  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, 5 * sizeof(unsigned int), m->stream));
   if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->stream));
   ABG_CUDA(cudaEventRecord(m->ev0, m->stream));
   int rc;
@@ -667,9 +746,9 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
   const uint32_t chunk = std::max(m->chunk, (n + kMaxChunks - 1) / kMaxChunks);
   const uint32_t n_chunks = n ? (n + chunk - 1) / chunk : 0;
 
-  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, (kMaxChunks + 2) * sizeof(unsigned int), m->s_h2d));
+  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, kWorkWords * sizeof(unsigned int), m->s_h2d));
   if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->s_h2d));
-  const size_t slot_sets = (size_t)m->grid * ab2dev::kWarpsPerBlock;
+  const size_t slot_sets = (size_t)m->grid_scratch * ab2dev::kWarpsPerBlock;
   for (uint32_t j = 0; j < n_chunks; ++j) {
     const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
     for (int e = 0; e < n_ends; ++e) {
@@ -692,7 +771,7 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
     cudaStream_t sr = m->s_run[j & 1];
     ABG_CUDA(cudaStreamWaitEvent(sr, m->ev_in[j], 0));
     ab2dev::KernelParams P;
-    fill_params(m, P, c0, c1 - c0, m->d_work + 1 + j);
+    fill_params(m, P, c0, c1 - c0, j);
     // scratch set of this stream
     if (j & 1) {
       if (P.pe_overflow) P.pe_overflow += slot_sets * 2 * ab2dev::kPeLarge;
@@ -721,7 +800,7 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
 }
 
 float abg_mapper_last_kernel_ms(const abg_mapper *m) { return m ? m->last_ms : 0.f; }
-uint32_t abg_mapper_launches_per_run(const abg_mapper *m) { return (m && m->cur_n) ? 1u : 0u; }
+uint32_t abg_mapper_launches_per_run(const abg_mapper *m) { return (m && m->cur_n) ? (m->split ? 3u : 1u) : 0u; }
 uint32_t abg_mapper_chunk(const abg_mapper *m) { return m ? m->chunk : 0u; }
 
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out) {

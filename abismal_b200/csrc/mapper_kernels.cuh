@@ -62,6 +62,9 @@ constexpr int kLogCap = 128;          // survivor-log entries per pass (specific
 constexpr int kLogMaxLen = 1023;     // reads longer than this do not use the log (9-bit offset field)
 constexpr int kTbLanesSm = 8;       // traceback words of lanes < 8 (band <= 16) stay in shared memory
 constexpr int kTbCacheMaxCands = 4; // record traceback while scoring when a set has at most this many candidates
+constexpr int kSetStateWords = 4;   // u64 words of scalar state in front of a stored candidate set
+constexpr int kSetSlotsPe = 32;     // pe_candidates::max_size_small: a PE set that grew beyond it is redone
+constexpr int kSetSlotsSe = 64;     // >= se_candidates::max_size
 
 struct IndexDev {
   const uint64_t *genome;
@@ -103,6 +106,15 @@ struct KernelParams {
   unsigned int *work_counter;
   unsigned int *error_flag;
   unsigned long long *counters;  // abg_work_counters layout, or nullptr
+  // two-phase launch (seed_kernel -> align_kernel -> map_reads_kernel on the redo list); null / 0 otherwise
+  uint64_t *sets;            // [n][n_pass][kSetStateWords + set_slots]: candidate sets as the seed phase leaves them
+  uint32_t set_slots;        // heap entries stored per set
+  uint32_t n_pass;           // stored sets per read / pair
+  unsigned int *redo_flag;   // [n]: the pair has a set that does not fit set_slots -> mapped by map_reads_kernel
+  uint32_t *redo_list;       // items flagged by the seed phase, in no particular order
+  unsigned int *redo_count;
+  const uint32_t *item_list; // map_reads_kernel only: map item_list[0 .. *n_items_ptr) instead of 0 .. n
+  const unsigned int *n_items_ptr;
 };
 
 // ---- 64-bit view of se_element {int16 diffs; uint16 flags; uint32 pos} -------
@@ -1626,31 +1638,293 @@ __global__ void pack_genome2_kernel(const uint64_t *__restrict__ genome, uint64_
   }
 }
 
+// kernel parameters + base-3 hash tables to shared memory (every device function reads them there)
+__device__ __forceinline__ void block_prologue(const KernelParams &Pin) {
+  {
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(&Pin);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(smem_raw);
+  for (uint32_t k = threadIdx.x; k < sizeof(KernelParams) / 4; k += blockDim.x) dst[k] = src[k];
+  uint32_t *T3 = reinterpret_cast<uint32_t *>(smem_raw + kParamBytes);
+  for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
+    // bit j of x0/x1 is base j of the 16-base window; digit weight of base j is 3^(15-j)
+    uint32_t lo = 0, hi = 0, w = 1;
+    for (int j = 7; j >= 0; --j) {  // hi table: bases 8..15 (bit j -> base 8+j, weight 3^(7-j))
+      if (b & (1u << j)) hi += w;
+      w *= 3u;
+    }
+    for (int j = 7; j >= 0; --j) {  // lo table: bases 0..7 (weight 3^(15-j)), w continues at 3^8
+      if (b & (1u << j)) lo += w;
+      w *= 3u;
+    }
+    T3[b] = lo;
+    T3[256 + b] = hi;
+  }
+}
+__syncthreads();
+}
+
+// map_fragments instantiations of call `call` of a pair: which end is mapped un-reversed
+// (e1, flags f1) and which reversed (e2, flags f2)
+struct CallPlan {
+  bool first_is_r1, swap_ends;
+  uint32_t f1, f2;
+  int e1, e2;
+};
+__device__ __forceinline__ CallPlan call_plan(int call, bool rpbat, bool a_rich) {
+  CallPlan c;
+  c.first_is_r1 = (call & 1) == 0;
+  c.swap_ends = !c.first_is_r1;
+  bool enc_a_call;  // encoding shared by both ends of this call
+  if (rpbat) enc_a_call = (call == 1 || call == 2);
+  else enc_a_call = a_rich ? (call == 0) : (call == 1);
+  c.f1 = enc_a_call ? ABG_FLAG_A_RICH : 0u;                      // un-reversed read: a_rich bit == encoding
+  c.f2 = (enc_a_call ? 0u : ABG_FLAG_A_RICH) | ABG_FLAG_RC;      // reversed read: a_rich bit == !encoding
+  c.e1 = c.first_is_r1 ? 0 : 1;
+  c.e2 = 1 - c.e1;
+  return c;
+}
+
+// candidate set `id` <-> its stored form (kSetStateWords of state, then the heap entries)
+__device__ __forceinline__ void store_set(const Warp &W, int id, uint64_t *dst, int slots) {
+  __syncwarp();
+  const CandState *st = W.cs(id);
+  const HeapRef v = heap_of(W, id);
+  const int sz = st->sz;
+  if (W.lane == 0) {
+    dst[0] = (uint64_t)(uint32_t)st->sz | ((uint64_t)(uint32_t)st->cutoff << 32);
+    dst[1] = (uint64_t)(uint32_t)st->good_cutoff | ((uint64_t)(uint32_t)st->capacity << 32);
+    dst[2] = (uint64_t)(uint32_t)st->sure_ambig | ((uint64_t)(uint32_t)st->is_pe << 32);
+    dst[3] = st->best;
+  }
+  for (int i = W.lane; i < sz && i < slots; i += 32) dst[kSetStateWords + i] = v.get(i).w;
+  __syncwarp();
+}
+__device__ __forceinline__ void load_set(const Warp &W, int id, const uint64_t *src) {
+  __syncwarp();
+  CandState *st = W.cs(id);
+  const HeapRef v = heap_of(W, id);
+  const uint64_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
+  const int sz = (int)(uint32_t)w0;
+  if (W.lane == 0) {
+    st->sz = sz;
+    st->cutoff = (int)(uint32_t)(w0 >> 32);
+    st->good_cutoff = (int)(uint32_t)w1;
+    st->capacity = (int)(uint32_t)(w1 >> 32);
+    st->sure_ambig = (int)(uint32_t)w2;
+    st->is_pe = (int)(uint32_t)(w2 >> 32);
+    st->best = w3;
+  }
+  for (int i = W.lane; i < sz; i += 32) v.set(i, Hit(src[kSetStateWords + i]));
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint64_t *stored_set(const KernelParams &P, unsigned item, int pass) {
+  return P.sets + ((size_t)item * P.n_pass + (size_t)pass) * (size_t)(kSetStateWords + P.set_slots);
+}
+
+// One read / pair through the path.  FROM_SETS: the candidate sets come from seed_kernel (stored_set) instead
+// of being computed here by process_seeds; everything after seeding is the same code.
+template <bool FROM_SETS>
+__device__ __forceinline__ void map_one(const Warp &W, unsigned int item) {
+  const KernelParams &P = params();
+  const int lane = W.lane;
+  const bool paired = P.mode & ABG_MODE_PAIRED;
+  const bool a_rich = P.mode & ABG_MODE_A_RICH;
+  const bool rpbat = P.mode & ABG_MODE_RANDOM_PBAT;
+  WarpScalars *S = W.scal();
+  const uint32_t T = 0, A = ABG_FLAG_A_RICH, RC = ABG_FLAG_RC;
+  if (lane == 0) {
+    S->qkey[0] = S->qkey[1] = ~0u;
+    S->packed_key = ~0u;
+    S->tbk[0].valid = S->tbk[1].valid = 0;
+  }
+  __syncwarp();
+
+  if (!paired) {
+    // map_single_ended<conv> / map_single_ended_rand (abismal.cpp:1511-1704)
+    const uint32_t o0 = P.off[0][item], len = P.off[0][item + 1] - o0;
+    uint32_t cg_n = 0, cg_ref = 0;
+    Hit best(kMaxDiffs, 0, 0);
+    if (lane == 0) S->len[0] = len;
+    __syncwarp();
+    if (len != 0) {
+      load_end(W, 0, P.seq[0] + o0, len);
+      if (FROM_SETS) load_set(W, 0, stored_set(P, item, 0));
+      else if (rpbat) {
+        reset_set(W, 0, 0, len);
+        process_seeds(0, 0, T);
+        process_seeds(0, 0, A);
+        process_seeds(0, 0, A | RC);
+        process_seeds(0, 0, T | RC);
+      }
+      else {
+        reset_set(W, 0, 0, len);
+        const uint32_t cv = a_rich ? A : T;
+        process_seeds(0, 0, cv);
+        process_seeds(0, 0, cv | RC);
+      }
+      best = Hit(align_se_candidates(0, P.valid_frac, P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride,
+                                     &cg_n, &cg_ref, best.w));
+    }
+    if (lane == 0) {
+      P.se[0][item] = to_abg(best);
+      P.n_cigar[0][item] = cg_n;
+      if (cg_n > P.cigar_stride) atomicExch(P.error_flag, 1u);
+    }
+    __syncwarp();
+    if ((uint32_t)lane < P.inline_ops)
+      P.cigar_inline[0][(size_t)item * P.inline_ops + lane] = P.cigar[0][(size_t)item * P.cigar_stride + lane];
+  }
+  else {
+    // map_paired_ended<conv> / map_paired_ended_rand (abismal.cpp:1887-2185)
+    uint32_t len0, len1;
+    {
+      const uint32_t oa = P.off[0][item], ob = P.off[1][item];
+      len0 = P.off[0][item + 1] - oa;
+      len1 = P.off[1][item + 1] - ob;
+      if (lane == 0) {
+        S->len[0] = len0;
+        S->len[1] = len1;
+      }
+      __syncwarp();
+      if (len0 != 0) load_end(W, 0, P.seq[0] + oa, len0);
+      if (len1 != 0) load_end(W, 1, P.seq[1] + ob, len1);
+    }
+    CigarOut cg[2] = {{P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride, 0u, 0u},
+                      {P.cigar[1] + (size_t)item * P.cigar_stride, P.cigar_stride, 0u, 0u}};
+    reset_set(W, 0, 0, len0);
+    reset_set(W, 1, 0, len1);
+    PeBest best;
+    best.reset(len0, len1);
+    Hit best_se0(invalid_hit_diffs(len0), 0, 0), best_se1(invalid_hit_diffs(len1), 0, 0);
+    bool any_success = false;
+    const int n_calls = rpbat ? 4 : 2;
+    for (int call = 0; call < n_calls; ++call) {
+      const CallPlan cp = call_plan(call, rpbat, a_rich);
+      const bool swap_ends = cp.swap_ends;
+      const uint32_t f1 = cp.f1, f2 = cp.f2;
+      const int e1 = cp.e1, e2 = cp.e2;
+      const uint32_t l1 = cp.first_is_r1 ? len0 : len1, l2 = cp.first_is_r1 ? len1 : len0;
+      reset_set(W, 2, 1, l1);
+      reset_set(W, 3, 1, l2);
+      if (l1 == 0 && l2 == 0) continue;
+      any_success = true;
+      if (FROM_SETS) {
+        load_set(W, 2, stored_set(P, item, 2 * call));
+        load_set(W, 3, stored_set(P, item, 2 * call + 1));
+      }
+      else {
+        if (l1 != 0) process_seeds(2, e1, f1);
+        if (l2 != 0) process_seeds(3, e2, f2);
+      }
+      // select_maps (abismal.cpp:1833-1847)
+      CandSet t0, t1;
+      t0.load(W, 2);
+      t1.load(W, 3);
+      if (t0.should_align() && t1.should_align()) {
+        sort_unique(2);
+        sort_unique(3);
+        best_pair(swap_ends, e1, f1, f2, cg, &best);
+      }
+      best_single(2, e1);
+      best_single(3, e2);
+    }
+    if (!any_success) {
+      best.reset();
+      reset_set(W, 0, 2, 0);
+      reset_set(W, 1, 2, 0);
+    }
+    {  // valid_pair (abismal.cpp:624-631)
+      const uint32_t al1 = cg[0].ref_len, al2 = cg[1].ref_len;
+      const bool ok = valid_len(al1, len0) && valid_len(al2, len1) &&
+                      best.diffs() <= frac_of(P.valid_frac, al1 + al2);
+      if (!ok) best.reset();
+    }
+    if (!best.should_report(P.allow_ambig != 0u)) {
+      const double half = P.valid_frac / 2.0;
+      best_se0 = Hit(align_se_candidates(0, half, cg[0].ops, cg[0].stride, &cg[0].n, &cg[0].ref_len, best_se0.w));
+      best_se1 = Hit(align_se_candidates(1, half, cg[1].ops, cg[1].stride, &cg[1].n, &cg[1].ref_len, best_se1.w));
+    }
+    if (lane == 0) {
+      P.pe_r1[item] = to_abg(best.r1);
+      P.pe_r2[item] = to_abg(best.r2);
+      P.se[0][item] = to_abg(best_se0);
+      P.se[1][item] = to_abg(best_se1);
+      P.n_cigar[0][item] = cg[0].n;
+      P.n_cigar[1][item] = cg[1].n;
+      if (cg[0].n > cg[0].stride || cg[1].n > cg[1].stride) atomicExch(P.error_flag, 1u);
+    }
+    __syncwarp();
+    if ((uint32_t)lane < P.inline_ops) {
+      P.cigar_inline[0][(size_t)item * P.inline_ops + lane] = cg[0].ops[lane];
+      P.cigar_inline[1][(size_t)item * P.inline_ops + lane] = cg[1].ops[lane];
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void flush_counters(const Warp &W) {
+  const KernelParams &P = params();
+  const WarpScalars *S = W.scal();
+  if (P.counters != nullptr && W.lane == 0) {
+    atomicAdd(P.counters + 0, S->cnt[0]);  // n_lookup
+    atomicAdd(P.counters + 1, S->cnt[1]);  // n_entry
+    atomicAdd(P.counters + 2, S->cnt[1]);  // n_cmp == n_entry
+    atomicAdd(P.counters + 3, S->cnt[2]);  // n_word
+    atomicAdd(P.counters + 4, S->cnt[3]);  // n_align
+    atomicAdd(P.counters + 5, S->cnt[4]);  // n_dpref
+  }
+}
+
 // MINB = resident CTAs per SM the register allocation is bounded for (2: <=128 regs, 3: <=80, 4: <=64)
 template <int MINB>
 __global__ void __launch_bounds__(kThreadsPerBlock, MINB) map_reads_kernel(const __grid_constant__ KernelParams Pin) {
-  // kernel parameters + base-3 hash tables to shared memory (every device function reads them there)
-  {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(&Pin);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(smem_raw);
-    for (uint32_t k = threadIdx.x; k < sizeof(KernelParams) / 4; k += blockDim.x) dst[k] = src[k];
-    uint32_t *T3 = reinterpret_cast<uint32_t *>(smem_raw + kParamBytes);
-    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
-      // bit j of x0/x1 is base j of the 16-base window; digit weight of base j is 3^(15-j)
-      uint32_t lo = 0, hi = 0, w = 1;
-      for (int j = 7; j >= 0; --j) {  // hi table: bases 8..15 (bit j -> base 8+j, weight 3^(7-j))
-        if (b & (1u << j)) hi += w;
-        w *= 3u;
-      }
-      for (int j = 7; j >= 0; --j) {  // lo table: bases 0..7 (weight 3^(15-j)), w continues at 3^8
-        if (b & (1u << j)) lo += w;
-        w *= 3u;
-      }
-      T3[b] = lo;
-      T3[256 + b] = hi;
-    }
+  block_prologue(Pin);
+  const KernelParams &P = params();
+  const Warp W;
+  const int lane = W.lane;
+  if (lane < 6) W.scal()->cnt[lane] = 0;
+  __syncwarp();
+  const unsigned int n_items = P.n_items_ptr != nullptr ? *P.n_items_ptr : P.n;
+  for (;;) {
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(P.work_counter, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= n_items) break;
+    if (P.item_list != nullptr) item = P.item_list[item];
+    map_one<false>(W, item);
   }
-  __syncthreads();
+  flush_counters(W);
+}
+
+// Phase 2 of the two-phase launch: everything after seeding (sort/unique, banded alignment, mating, selection,
+// CIGARs) for the reads / pairs whose sets seed_kernel stored; flagged pairs are left to map_reads_kernel.
+template <int MINB>
+__global__ void __launch_bounds__(kThreadsPerBlock, MINB) align_kernel(const __grid_constant__ KernelParams Pin) {
+  block_prologue(Pin);
+  const KernelParams &P = params();
+  const Warp W;
+  const int lane = W.lane;
+  if (lane < 6) W.scal()->cnt[lane] = 0;
+  __syncwarp();
+  for (;;) {
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(P.work_counter, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= P.n) break;
+    if (P.redo_flag[item] != 0) continue;
+    map_one<true>(W, item);
+  }
+  flush_counters(W);
+}
+
+// Phase 1 of the two-phase launch: seeding only.  Paired: one work item per (pair, call, side) -- the passes
+// of a pair are independent (every map_fragments call starts from reset pe_candidates) -- so a warp hashes,
+// probes and compares ONE read strand and stores the resulting set.  Single-end: the passes of a read feed
+// the same se_candidates in order, so the work item is the read.
+template <int MINB>
+__global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __grid_constant__ KernelParams Pin) {
+  block_prologue(Pin);
   const KernelParams &P = params();
   const Warp W;
   const int lane = W.lane;
@@ -1660,149 +1934,60 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) map_reads_kernel(const
   WarpScalars *S = W.scal();
   if (lane < 6) S->cnt[lane] = 0;
   __syncwarp();
-
   const uint32_t T = 0, A = ABG_FLAG_A_RICH, RC = ABG_FLAG_RC;
-
+  const unsigned int n_work = paired ? P.n * P.n_pass : P.n;
   for (;;) {
-    unsigned int item = 0;
-    if (lane == 0) item = atomicAdd(P.work_counter, 1u);
-    item = __shfl_sync(FULL, item, 0);
-    if (item >= P.n) break;
+    unsigned int w = 0;
+    if (lane == 0) w = atomicAdd(P.work_counter, 1u);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= n_work) break;
     if (lane == 0) {
       S->qkey[0] = S->qkey[1] = ~0u;
       S->packed_key = ~0u;
-      S->tbk[0].valid = S->tbk[1].valid = 0;
     }
     __syncwarp();
-
     if (!paired) {
-      // map_single_ended<conv> / map_single_ended_rand (abismal.cpp:1511-1704)
+      const unsigned int item = w;
       const uint32_t o0 = P.off[0][item], len = P.off[0][item + 1] - o0;
-      uint32_t cg_n = 0, cg_ref = 0;
-      Hit best(kMaxDiffs, 0, 0);
       if (lane == 0) S->len[0] = len;
       __syncwarp();
-      if (len != 0) {
-        load_end(W, 0, P.seq[0] + o0, len);
-        reset_set(W, 0, 0, len);
-        if (rpbat) {
-          process_seeds(0, 0, T);
-          process_seeds(0, 0, A);
-          process_seeds(0, 0, A | RC);
-          process_seeds(0, 0, T | RC);
-        }
-        else {
-          const uint32_t cv = a_rich ? A : T;
-          process_seeds(0, 0, cv);
-          process_seeds(0, 0, cv | RC);
-        }
-        best = Hit(align_se_candidates(0, P.valid_frac, P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride,
-                                       &cg_n, &cg_ref, best.w));
+      if (len == 0) continue;
+      load_end(W, 0, P.seq[0] + o0, len);
+      reset_set(W, 0, 0, len);
+      if (rpbat) {
+        process_seeds(0, 0, T);
+        process_seeds(0, 0, A);
+        process_seeds(0, 0, A | RC);
+        process_seeds(0, 0, T | RC);
       }
-      if (lane == 0) {
-        P.se[0][item] = to_abg(best);
-        P.n_cigar[0][item] = cg_n;
-        if (cg_n > P.cigar_stride) atomicExch(P.error_flag, 1u);
+      else {
+        const uint32_t cv = a_rich ? A : T;
+        process_seeds(0, 0, cv);
+        process_seeds(0, 0, cv | RC);
       }
-      __syncwarp();
-      if ((uint32_t)lane < P.inline_ops)
-        P.cigar_inline[0][(size_t)item * P.inline_ops + lane] = P.cigar[0][(size_t)item * P.cigar_stride + lane];
+      store_set(W, 0, stored_set(P, item, 0), (int)P.set_slots);
     }
     else {
-      // map_paired_ended<conv> / map_paired_ended_rand (abismal.cpp:1887-2185)
-      uint32_t len0, len1;
-      {
-        const uint32_t oa = P.off[0][item], ob = P.off[1][item];
-        len0 = P.off[0][item + 1] - oa;
-        len1 = P.off[1][item + 1] - ob;
-        if (lane == 0) {
-          S->len[0] = len0;
-          S->len[1] = len1;
-        }
-        __syncwarp();
-        if (len0 != 0) load_end(W, 0, P.seq[0] + oa, len0);
-        if (len1 != 0) load_end(W, 1, P.seq[1] + ob, len1);
-      }
-      CigarOut cg[2] = {{P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride, 0u, 0u},
-                        {P.cigar[1] + (size_t)item * P.cigar_stride, P.cigar_stride, 0u, 0u}};
-      reset_set(W, 0, 0, len0);
-      reset_set(W, 1, 0, len1);
-      PeBest best;
-      best.reset(len0, len1);
-      Hit best_se0(invalid_hit_diffs(len0), 0, 0), best_se1(invalid_hit_diffs(len1), 0, 0);
-      bool any_success = false;
-      const int n_calls = rpbat ? 4 : 2;
-      for (int call = 0; call < n_calls; ++call) {
-        // map_fragments instantiations, SURVEY appendix C
-        const bool first_is_r1 = (call & 1) == 0;
-        const bool swap_ends = !first_is_r1;
-        bool enc_a_call;  // encoding shared by both ends of this call
-        if (rpbat) enc_a_call = (call == 1 || call == 2);
-        else enc_a_call = a_rich ? (call == 0) : (call == 1);
-        const uint32_t f1 = enc_a_call ? A : T;         // un-reversed read: a_rich bit == encoding
-        const uint32_t f2 = (enc_a_call ? T : A) | RC;  // reversed read: a_rich bit == !encoding
-        const int e1 = first_is_r1 ? 0 : 1, e2 = 1 - e1;
-        const uint32_t l1 = first_is_r1 ? len0 : len1, l2 = first_is_r1 ? len1 : len0;
-        reset_set(W, 2, 1, l1);
-        reset_set(W, 3, 1, l2);
-        if (l1 == 0 && l2 == 0) continue;
-        any_success = true;
-        if (l1 != 0) process_seeds(2, e1, f1);
-        if (l2 != 0) process_seeds(3, e2, f2);
-        // select_maps (abismal.cpp:1833-1847)
-        CandSet t0, t1;
-        t0.load(W, 2);
-        t1.load(W, 3);
-        if (t0.should_align() && t1.should_align()) {
-          sort_unique(2);
-          sort_unique(3);
-          best_pair(swap_ends, e1, f1, f2, cg, &best);
-        }
-        best_single(2, e1);
-        best_single(3, e2);
-      }
-      if (!any_success) {
-        best.reset();
-        reset_set(W, 0, 2, 0);
-        reset_set(W, 1, 2, 0);
-      }
-      {  // valid_pair (abismal.cpp:624-631)
-        const uint32_t al1 = cg[0].ref_len, al2 = cg[1].ref_len;
-        const bool ok = valid_len(al1, len0) && valid_len(al2, len1) &&
-                        best.diffs() <= frac_of(P.valid_frac, al1 + al2);
-        if (!ok) best.reset();
-      }
-      if (!best.should_report(P.allow_ambig != 0u)) {
-        const double half = P.valid_frac / 2.0;
-        best_se0 = Hit(align_se_candidates(0, half, cg[0].ops, cg[0].stride, &cg[0].n, &cg[0].ref_len, best_se0.w));
-        best_se1 = Hit(align_se_candidates(1, half, cg[1].ops, cg[1].stride, &cg[1].n, &cg[1].ref_len, best_se1.w));
-      }
-      if (lane == 0) {
-        P.pe_r1[item] = to_abg(best.r1);
-        P.pe_r2[item] = to_abg(best.r2);
-        P.se[0][item] = to_abg(best_se0);
-        P.se[1][item] = to_abg(best_se1);
-        P.n_cigar[0][item] = cg[0].n;
-        P.n_cigar[1][item] = cg[1].n;
-        if (cg[0].n > cg[0].stride || cg[1].n > cg[1].stride) atomicExch(P.error_flag, 1u);
-      }
+      const unsigned int item = w / P.n_pass;
+      const int pass = (int)(w % P.n_pass);
+      const CallPlan cp = call_plan(pass >> 1, rpbat, a_rich);
+      const int end = (pass & 1) ? cp.e2 : cp.e1;
+      const uint32_t flags = (pass & 1) ? cp.f2 : cp.f1;
+      const uint32_t o = P.off[end][item], len = P.off[end][item + 1] - o;
+      if (lane == 0) S->len[end] = len;
       __syncwarp();
-      if ((uint32_t)lane < P.inline_ops) {
-        P.cigar_inline[0][(size_t)item * P.inline_ops + lane] = cg[0].ops[lane];
-        P.cigar_inline[1][(size_t)item * P.inline_ops + lane] = cg[1].ops[lane];
+      reset_set(W, 2, 1, len);
+      if (len != 0) {
+        load_end(W, end, P.seq[end] + o, len);
+        process_seeds(2, end, flags);
       }
+      if (W.cs(2)->sz > (int)P.set_slots) {  // grew beyond the stored form (repeats): the whole pair is redone
+        if (lane == 0 && atomicExch(P.redo_flag + item, 1u) == 0u) P.redo_list[atomicAdd(P.redo_count, 1u)] = item;
+      }
+      store_set(W, 2, stored_set(P, item, pass), (int)P.set_slots);
     }
-    __syncwarp();
   }
-
-  if (P.counters != nullptr && lane == 0) {
-    atomicAdd(P.counters + 0, S->cnt[0]);  // n_lookup
-    atomicAdd(P.counters + 1, S->cnt[1]);  // n_entry
-    atomicAdd(P.counters + 2, S->cnt[1]);  // n_cmp == n_entry
-    atomicAdd(P.counters + 3, S->cnt[2]);  // n_word
-    atomicAdd(P.counters + 4, S->cnt[3]);  // n_align
-    atomicAdd(P.counters + 5, S->cnt[4]);  // n_dpref
-  }
+  flush_counters(W);
 }
 
 }  // namespace ab2dev

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from abismal_b200 import workload, Index, Mapper, MODE_A_RICH, MODE_PAIRED
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
-variants = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "2,3,4").split(",")]
+variants = (sys.argv[2] if len(sys.argv) > 2 else "3,3n").split(",")  # MINB, suffix n = single-kernel path
 check_n = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 log = lambda *a: print("[vp]", *a, flush=True)
 ixf, paths = workload.get_index(int(3.1e9), 20251017, device=0, need_files=True, log=log)
@@ -19,14 +19,15 @@ ix = Index(ixf, 0)
 mode = MODE_PAIRED | MODE_A_RICH
 first = None
 for v in variants:
-    os.environ["ABISMAL_B200_MINB"] = str(v)
+    os.environ["ABISMAL_B200_MINB"] = v.rstrip("n")
+    os.environ["ABISMAL_B200_SPLIT"] = "0" if v.endswith("n") else "1"
     m = Mapper(ix, mode=mode, max_batch=b1.n, max_read_len=max(b1.max_len, b2.max_len, 64),
                count_work=bool(os.environ.get("COUNT")))
     m.upload(b1, b2); m.sync()
     ms = []
     for it in range(4):
         m.run(); m.sync(); ms.append(m.last_kernel_ms)
-    log("MINB=%d kernel ms %s -> %.3f M pairs/s" % (v, ["%.1f" % x for x in ms], b1.n / min(ms[1:]) / 1e3))
+    log("MINB=%s kernel ms %s -> %.3f M pairs/s" % (v, ["%.1f" % x for x in ms], b1.n / min(ms[1:]) / 1e3))
     if os.environ.get("COUNT"):
         log(m.counters().as_dict())
     res = m.map_batch(b1, b2)
@@ -35,13 +36,14 @@ for v in variants:
     else:
         import helpers
         helpers.assert_results_equal(res, first, True)
-        log("variant %d results identical to variant %d" % (v, variants[0]))
+        log("variant %s results identical to variant %s" % (v, variants[0]))
     m.close()
 if check_n:
     import helpers
     o = helpers.OracleMapper(ixf, mode=mode)
     t = time.time(); want = o.map_batch(b1.slice(0, check_n), b2.slice(0, check_n)); dt = time.time() - t
-    os.environ["ABISMAL_B200_MINB"] = str(variants[0])
+    os.environ["ABISMAL_B200_MINB"] = variants[0].rstrip("n")
+    os.environ["ABISMAL_B200_SPLIT"] = "0" if variants[0].endswith("n") else "1"
     m = Mapper(ix, mode=mode, max_batch=check_n, max_read_len=max(b1.max_len, b2.max_len, 64))
     got = m.map_batch(b1.slice(0, check_n), b2.slice(0, check_n))
     helpers.assert_results_equal(got, want, True)
