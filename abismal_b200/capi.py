@@ -63,7 +63,8 @@ class abg_work_counters(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libabismal_b200.so")
+    # ABISMAL_B200_LIB: a differently tuned build of the same library (kernel tuning experiments only)
+    return os.environ.get("ABISMAL_B200_LIB") or os.path.join(_HERE, "libabismal_b200.so")
 
 
 _lib = None

@@ -76,6 +76,9 @@ struct abg_index {
   uint32_t *bits = nullptr, *bits_t = nullptr, *bits_a = nullptr;
   uint64_t *g2 = nullptr;
   uint32_t *gx = nullptr;
+  uint4 *ctx = nullptr, *ctx_t = nullptr, *ctx_a = nullptr;  // seed-context records (IndexDev::ctx)
+  uint4 *cc = nullptr;                                        // compact two-letter counters (IndexDev::cc)
+  uint64_t cc_bytes = 0;
 };
 
 constexpr uint32_t kInlineOps = 16;   // CIGAR ops per read copied back with the batch; longer ones are fetched afterwards
@@ -395,8 +398,16 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
       return fail(ABG_ERR_CUDA, "abg_index_create: out of device memory for the 2-bit genome");
     }
     cudaMemset(ix->gx, 0, nx * 4);
-    ab2dev::pack_genome2_kernel<<<148 * 8, 256>>>(ix->genome, v->genome_words + 4, n2, ix->g2, ix->gx);
-    const cudaError_t e3 = cudaDeviceSynchronize();
+    unsigned int *d_iupac = nullptr, h_iupac = 1;
+    if (cudaMalloc(reinterpret_cast<void **>(&d_iupac), 4) != cudaSuccess) {
+      abg_index_destroy(ix);
+      return fail(ABG_ERR_CUDA, "abg_index_create: out of device memory");
+    }
+    cudaMemset(d_iupac, 0, 4);
+    ab2dev::pack_genome2_kernel<<<148 * 8, 256>>>(ix->genome, v->genome_words + 4, n2, ix->g2, ix->gx, d_iupac);
+    cudaError_t e3 = cudaDeviceSynchronize();
+    if (e3 == cudaSuccess) e3 = cudaMemcpy(&h_iupac, d_iupac, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_iupac);
     if (e3 != cudaSuccess) {
       abg_index_destroy(ix);
       return fail(ABG_ERR_CUDA, std::string("pack_genome2_kernel: ") + cudaGetErrorString(e3));
@@ -404,6 +415,76 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
     ix->dev.g2 = ix->g2;
     ix->dev.gx = ix->gx;
     ix->bytes_extra = n2 * 8 + nx * 4;
+    // Seed-context records: 4 x 32 bytes per index entry (21 GB at 3.1 Gbp -- HBM is 180 GB).  They are an
+    // accelerator of the compare, not a different algorithm: without them (genome with IUPAC codes, not
+    // enough memory, ABISMAL_B200_CTX=0) every candidate takes the direct index + genome gather.
+    const char *env = std::getenv("ABISMAL_B200_CTX");
+    if (!(env && env[0] == '0') && h_iupac == 0) {
+      struct Tab {
+        const uint32_t *index;
+        uint64_t n;
+        uint4 **dst;
+      } tabs[3] = {{ix->index, v->index_size, &ix->ctx},
+                   {ix->index_t, v->index_size_three, &ix->ctx_t},
+                   {ix->index_a, v->index_size_three, &ix->ctx_a}};
+      bool ok = true;
+      for (const Tab &t : tabs) {
+        if (t.n == 0) continue;
+        const uint64_t bytes = t.n * (uint64_t)ab2dev::kCtxArrays * 32u;
+        if (cudaMalloc(reinterpret_cast<void **>(t.dst), bytes) != cudaSuccess) {
+          (void)cudaGetLastError();
+          *t.dst = nullptr;
+          ok = false;
+          break;
+        }
+        ab2dev::seed_context_kernel<<<148 * 16, 256>>>(t.index, t.n, ix->g2, *t.dst);
+        ix->bytes_extra += bytes;
+      }
+      const cudaError_t e4 = cudaDeviceSynchronize();
+      if (e4 != cudaSuccess) {
+        abg_index_destroy(ix);
+        return fail(ABG_ERR_CUDA, std::string("seed_context_kernel: ") + cudaGetErrorString(e4));
+      }
+      if (!ok) {  // all or nothing, so that the memory footprint is predictable
+        for (const Tab &t : tabs) {
+          if (*t.dst) ix->bytes_extra -= t.n * (uint64_t)ab2dev::kCtxArrays * 32u;
+          cudaFree(*t.dst);
+          *t.dst = nullptr;
+        }
+      }
+      ix->dev.ctx = ix->ctx;
+      ix->dev.ctx_t = ix->ctx_t;
+      ix->dev.ctx_a = ix->ctx_a;
+      ix->dev.n_ctx = v->index_size;
+      ix->dev.n_ctx3 = v->index_size_three;
+    }
+  }
+  {  // compact two-letter counters, pinned in L2 by the mappers' streams (ABISMAL_B200_CC=0 disables)
+    const char *env = std::getenv("ABISMAL_B200_CC");
+    if (!(env && env[0] == '0')) {
+      const uint64_t n_blocks = (v->counter_size + ab2dev::kCcKeys - 1) / ab2dev::kCcKeys;
+      if (cudaMalloc(reinterpret_cast<void **>(&ix->cc), n_blocks * 32) == cudaSuccess) {
+        ab2dev::compact_counter_kernel<<<148 * 8, 256>>>(ix->counter, v->counter_size, n_blocks, ix->cc);
+        const cudaError_t e5 = cudaDeviceSynchronize();
+        if (e5 != cudaSuccess) {
+          abg_index_destroy(ix);
+          return fail(ABG_ERR_CUDA, std::string("compact_counter_kernel: ") + cudaGetErrorString(e5));
+        }
+        ix->cc_bytes = n_blocks * 32;
+        ix->bytes_extra += ix->cc_bytes;
+        ix->dev.cc = ix->cc;
+        // reserve as much persisting L2 as the device allows for it (a hint; failure only costs speed)
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+          const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)ix->cc_bytes);
+          if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) (void)cudaGetLastError();
+        }
+      }
+      else {
+        (void)cudaGetLastError();
+        ix->cc = nullptr;
+      }
+    }
   }
   ix->dev.bits = ix->bits;
   ix->dev.bits_t = ix->bits_t;
@@ -437,6 +518,10 @@ void abg_index_destroy(abg_index *ix) {
   cudaFree(ix->bits_a);
   cudaFree(ix->g2);
   cudaFree(ix->gx);
+  cudaFree(ix->cc);
+  cudaFree(ix->ctx);
+  cudaFree(ix->ctx_t);
+  cudaFree(ix->ctx_a);
   delete ix;
 }
 
@@ -494,6 +579,22 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   ABG_M(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
   ABG_M(cudaStreamCreateWithFlags(&m->s_run[0], cudaStreamNonBlocking));
   ABG_M(cudaStreamCreateWithFlags(&m->s_run[1], cudaStreamNonBlocking));
+  if (ix->cc != nullptr) {
+    // keep the compact counters resident in L2 while the kernels stream the rest of the index past them
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ix->device) == cudaSuccess && prop.accessPolicyMaxWindowSize > 0) {
+      cudaStreamAttrValue av;
+      std::memset(&av, 0, sizeof av);
+      av.accessPolicyWindow.base_ptr = ix->cc;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)ix->cc_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      const double avail = (double)prop.persistingL2CacheMaxSize;
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, avail / (double)av.accessPolicyWindow.num_bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      for (cudaStream_t st : {m->stream, m->s_run[0], m->s_run[1]})
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
+    }
+  }
   ABG_M(cudaEventCreate(&m->ev0));
   ABG_M(cudaEventCreate(&m->ev1));
   ABG_M(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));

@@ -56,7 +56,10 @@ constexpr int kPeSmall = 32;        // pe_candidates::max_size_small
 constexpr int kPeLarge = 32 << 10;  // pe_candidates::max_size_large
 constexpr int kPeSmemSlots = 128;   // PE heap entries kept in shared memory
 constexpr int kMaxDiffs = 32767;
-constexpr int kCand = 1;            // candidates per lane per compare round (the memory system saturates at ~120
+#ifndef ABG_KCAND
+#define ABG_KCAND 1
+#endif
+constexpr int kCand = ABG_KCAND;    // candidates per lane per compare round (the memory system saturates at ~120
                                     // sectors in flight per SM: one 5-word gather per lane is plenty)
 constexpr int kLogCap = 128;          // survivor-log entries per pass (specific -> sensitive reuse)
 constexpr int kLogMaxLen = 1023;     // reads longer than this do not use the log (9-bit offset field)
@@ -79,8 +82,22 @@ struct IndexDev {
   // whose window touches a flagged block take the exact 4-bit compare instead.
   const uint64_t *g2;
   const uint32_t *gx;
+  // Seed-context records (prefilter of the candidate compare): for entry j of an index table, record
+  // ctx[a * n_ctx + j] (32 bytes = one sector, g2 word format) holds the 128 genome bases starting at
+  // entry - 32 a, a = 0..kCtxArrays-1.  A candidate found at seed offset i reads ONE record (a = min(i / 32,
+  // kCtxArrays - 1)) instead of its index entry plus a random genome window; buckets are contiguous in every
+  // array, so the candidates of a bucket share DRAM pages.  Null = not built (no memory, genome with IUPAC
+  // codes, or disabled): every candidate then takes the direct compare.
+  const uint4 *ctx, *ctx_t, *ctx_a;
+  uint64_t n_ctx, n_ctx3;
+  // Compact two-letter counters: block b (32 bytes = one sector) = {counter[28 b], 28 one-byte bucket sizes},
+  // 38 MB instead of 134 MB so that the table can be pinned in L2 (persisting access window) and a probe
+  // costs no HBM access.  A block with a bucket of 255 or more entries has base ~0u: probe the full table.
+  const uint4 *cc;
   uint32_t max_candidates;
 };
+constexpr int kCtxArrays = 4;
+constexpr uint32_t kCcKeys = 28;
 
 struct KernelParams {
   IndexDev ix;
@@ -665,8 +682,22 @@ __device__ __forceinline__ uint32_t match_bits(uint32_t lo, uint32_t hi, uint32_
 // against the 2-bit genome.  NC0 = 32-base chunks compared in the first stage (NC0 + 1 words gathered at once
 // per candidate, all before any use); later stages add two chunks at a time while the distance is within the
 // bound.  Every base pair contributes 0 or 1 here, so the running distance is monotone and pm == d.
+// One 32-byte seed-context record (one sector)
+__device__ __forceinline__ void load_ctx(const uint4 *p, uint32_t (&w)[8]) {
+#ifdef ABG_LDG256
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+#else
+  const uint4 x = __ldg(p), y = __ldg(p + 1);
+  w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+  w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+#endif
+}
+
 template <int KC, int NC0>
 __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
+                                              const uint4 *__restrict__ ctx3,
                                               const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
                                               const uint32_t *mT, int n_words, int bound, uint32_t c0,
                                               uint32_t total, uint32_t base_off, uint32_t incl, uint32_t tot,
@@ -677,7 +708,9 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
   bool valid[KC];
   const int n_bases = 16 * n_words;          // compared positions incl. the 0xF tail of the last packed word
   const int n_chunks = (n_bases + 31) >> 5;
-  // ---- owners + index gathers (KC independent loads per lane) ----
+  // ---- owners; seed-context prefilter (one sector per candidate) ----
+  uint32_t slot[KC];  // position of the candidate's entry in its index table
+  bool any_left = false;
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
     const uint32_t cidx = c0 + 32u * k + lane;
@@ -695,17 +728,53 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
     const uint32_t o_n2 = __shfl_sync(FULL, n2, o);
     const uint32_t o_s2 = __shfl_sync(FULL, s2, o);
     const uint32_t o_s3 = __shfl_sync(FULL, s3, o);
-    uint32_t entry = 0;
-    if (valid[k]) {
-      const uint32_t r = cidx - (o_incl - o_tot);
-      entry = (r < o_n2) ? __ldg(ix.index + o_s2 + r) : __ldg(index3 + o_s3 + (r - o_n2));
-    }
-    the_pos[k] = entry;
+    const uint32_t r = cidx - (o_incl - o_tot);
+    const bool three = valid[k] && r >= o_n2;
+    slot[k] = three ? o_s3 + (r - o_n2) : o_s2 + r;
     // seed offset of the candidate; bit 31 = it came from the three-letter bucket
-    sub[k] = (base_off + (uint32_t)o) | ((valid[k] && cidx - (o_incl - o_tot) >= o_n2) ? 0x80000000u : 0u);
-  }
+    sub[k] = (base_off + (uint32_t)o) | (three ? 0x80000000u : 0u);
+    d[k] = 0;
+    pm[k] = 1 << 30;
+    the_pos[k] = 0;
+    const uint4 *tab = three ? ctx3 : ix.ctx;
+    if (valid[k] && tab != nullptr) {
+      // Lower bound of the distance from the 128 genome bases of the record: every compared position adds 0
+      // or 1 (no IUPAC codes in a genome that has records; an N reads as A here and really mismatches), so
+      // more than `bound` mismatches on a subset of the positions already rejects the candidate.
+      const uint32_t i_off = base_off + (uint32_t)o;
+      const uint32_t a = min((uint32_t)(kCtxArrays - 1), i_off >> 5);
+      const uint32_t q0 = i_off - 32u * a;  // read position of the record's first base
+      uint32_t w[8];
+      load_ctx(tab + 2 * ((uint64_t)a * (three ? ix.n_ctx3 : ix.n_ctx) + slot[k]), w);
+      int lb = 0;
 #pragma unroll
-  for (int k = 0; k < KC; ++k) the_pos[k] -= sub[k] & 0x7fffffffu;
+      for (int c = 0; c < 4; ++c) {
+        const int qb = (int)q0 + 32 * c;
+        const int nb = n_bases - qb;
+        if (nb > 0) {
+          const uint32_t wi = (uint32_t)qb >> 5, sh = (uint32_t)qb & 31u;
+          const uint32_t a_ = __funnelshift_r(mA[wi], mA[wi + 1], sh), c_ = __funnelshift_r(mC[wi], mC[wi + 1], sh);
+          const uint32_t g_ = __funnelshift_r(mG[wi], mG[wi + 1], sh), t_ = __funnelshift_r(mT[wi], mT[wi + 1], sh);
+          const uint32_t mm = ~match_bits(w[2 * c], w[2 * c + 1], a_, c_, g_, t_);
+          lb += __popc(nb >= 32 ? mm : (mm & ((1u << nb) - 1u)));
+        }
+      }
+      if (lb > bound) {
+        valid[k] = false;
+        n_entry += 1;
+        n_word += 4;
+      }
+    }
+    any_left = any_left || valid[k];
+  }
+  if (!__any_sync(FULL, any_left)) return;
+  // ---- index gathers of the candidates the records did not reject (all of them without records) ----
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    uint32_t entry = 0;
+    if (valid[k]) entry = (sub[k] >> 31) ? __ldg(index3 + slot[k]) : __ldg(ix.index + slot[k]);
+    the_pos[k] = entry - (sub[k] & 0x7fffffffu);
+  }
 
   // ---- stage 0: NC0 + 1 words of the 2-bit genome per candidate + its exception bits ----
   uint64_t g[KC][NC0 + 1];
@@ -841,6 +910,33 @@ __device__ __forceinline__ void probe(const uint32_t *__restrict__ counter, cons
   e = __ldg(counter + k + 1);
 }
 
+// Two-letter bucket [s, e) of key k through the compact counters when they exist
+__device__ __forceinline__ void probe_two(const IndexDev &ix, uint32_t k, uint32_t &s, uint32_t &e) {
+  if (ix.cc == nullptr) {
+    probe(ix.counter, ix.bits, k, s, e);
+    return;
+  }
+  const uint32_t b = k / kCcKeys, t = k - b * kCcKeys;
+  const uint4 x = __ldg(ix.cc + 2 * (size_t)b), y = __ldg(ix.cc + 2 * (size_t)b + 1);
+  if (x.x == ~0u) {
+    s = __ldg(ix.counter + k);
+    e = __ldg(ix.counter + k + 1);
+    return;
+  }
+  const uint32_t w[7] = {x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+  uint32_t before = 0, cnt = 0;
+#pragma unroll
+  for (int m = 0; m < 7; ++m) {
+    const int nb = min(4, max(0, (int)t - 4 * m));  // bytes of word m that precede bucket t
+    const uint32_t mask = nb == 4 ? ~0u : ((1u << (8 * nb)) - 1u);
+    before += __vsadu4(w[m] & mask, 0u);
+    if ((int)(t >> 2) == m) cnt = (w[m] >> (8u * (t & 3u))) & 255u;
+  }
+  s = x.x + before;
+  e = s + cnt;
+  if (cnt == 0u) s = e = 0u;  // what probe() reports for an empty bucket
+}
+
 // process_seeds (abismal.cpp:1269-1375) for pass `strand_code` of `end` into candidate set `set_id`
 __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_code) {
   const Warp W;
@@ -858,6 +954,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
   const uint32_t *counter3 = g_to_a ? ix.counter_a : ix.counter_t;
   const uint32_t *index3 = g_to_a ? ix.index_a : ix.index_t;
   const uint32_t *bits3 = g_to_a ? ix.bits_a : ix.bits_t;
+  const uint4 *ctx3 = g_to_a ? ix.ctx_a : ix.ctx_t;
   const uint32_t maxc = P.max_candidates;
   const int n_words = (int)((readlen + 15) / 16);
   unsigned long long c_lookup = 0, c_entry = 0, c_word = 0;
@@ -900,7 +997,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
         const uint32_t k = __brev(plane_window(p2, i)) >> 7;
         const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
         const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
-        probe(ix.counter, ix.bits, k, s2, e2);
+        probe_two(ix, k, s2, e2);
         probe(counter3, bits3, k3, s3, e3);
         {  // the sensitive phase's bucket rule (abismal.cpp:1351-1370), on the raw bucket sizes
           const uint32_t d_two = e2 - s2, d_three = e3 - s3;
@@ -961,7 +1058,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
         int d[kCand], pm[kCand];
         uint32_t the_pos[kCand];
         uint32_t sub[kCand];
-        compare_chunk<kCand, 4>(ix, index3, mA, mC, mG, mT, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3,
+        compare_chunk<kCand, 4>(ix, index3, ctx3, mA, mC, mG, mT, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3,
                                 lane, d, pm, the_pos, sub, c_entry, c_word);
         __syncwarp();
 #pragma unroll
@@ -1614,7 +1711,8 @@ __global__ void bucket_bitmap_kernel(const uint32_t *__restrict__ counter, uint6
 
 // 2-bit copy of the 4-bit genome + exception bits (see IndexDev::g2 / gx).  One thread per 32 bases.
 __global__ void pack_genome2_kernel(const uint64_t *__restrict__ genome, uint64_t n_words4, uint64_t n_words2,
-                                    uint64_t *g2, uint32_t *gx) {
+                                    uint64_t *g2, uint32_t *gx, unsigned int *iupac) {
+  bool multi = false;  // a multi-bit (IUPAC) code was seen: *iupac = 1
   for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words2; w += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = 0;
     bool bad = false;
@@ -1629,12 +1727,67 @@ __global__ void pack_genome2_kernel(const uint64_t *__restrict__ genome, uint64_
         else if (nib == 4u) code = 2;
         else if (nib == 8u) code = 3;
         else if (nib != 1u) bad = true;
+        multi = multi || (nib & (nib - 1u)) != 0u;
         lo |= (code & 1u) << (16 * h + j);
         hi |= (code >> 1) << (16 * h + j);
       }
     }
     g2[w] = (uint64_t)lo | ((uint64_t)hi << 32);
     if (bad) atomicOr(gx + (w >> 8), 1u << ((w >> 3) & 31u));  // block = (32 w) >> 8 = w >> 3
+  }
+  if (multi) atomicOr(iupac, 1u);
+}
+
+// Compact two-letter counters (IndexDev::cc): one thread per block of kCcKeys keys.
+__global__ void compact_counter_kernel(const uint32_t *__restrict__ counter, uint64_t n_keys, uint64_t n_blocks,
+                                       uint4 *cc) {
+  for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_blocks; b += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const uint64_t k0 = b * kCcKeys;
+    uint32_t prev = counter[k0];
+    w[0] = prev;
+    bool big = false;
+    for (uint32_t t = 0; t < kCcKeys; ++t) {
+      const uint64_t k = k0 + t;
+      uint32_t c = 0;
+      if (k < n_keys) {
+        const uint32_t nxt = counter[k + 1];
+        c = nxt - prev;
+        prev = nxt;
+      }
+      big = big || c >= 255u;
+      w[1 + (t >> 2)] |= (c & 255u) << (8u * (t & 3u));
+    }
+    if (big) w[0] = ~0u;
+    cc[2 * b] = make_uint4(w[0], w[1], w[2], w[3]);
+    cc[2 * b + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// Seed-context records of one index table (IndexDev::ctx): one thread per (array a, entry j) writes the 128
+// genome bases starting at index[j] - 32 a in g2 word format.  The writes stream; the reads are one random
+// 40-byte window of the 2-bit genome per record (once per index load).
+__global__ void seed_context_kernel(const uint32_t *__restrict__ index, uint64_t n, const uint64_t *__restrict__ g2,
+                                    uint4 *ctx) {
+  const uint64_t total = n * (uint64_t)kCtxArrays;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = (uint32_t)(t / n);
+    const uint32_t e = index[t - (uint64_t)a * n];
+    uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (e >= 32u * a) {  // always: index entries lie beyond the 32 767-base padding
+      const uint32_t p = e - 32u * a, sh = p & 31u;
+      const uint64_t *gp = g2 + (p >> 5);
+      uint64_t cur = __ldg(gp);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint64_t nxt = __ldg(gp + c + 1);
+        w[2 * c] = __funnelshift_r((uint32_t)cur, (uint32_t)nxt, sh);
+        w[2 * c + 1] = __funnelshift_r((uint32_t)(cur >> 32), (uint32_t)(nxt >> 32), sh);
+        cur = nxt;
+      }
+    }
+    ctx[2 * t] = make_uint4(w[0], w[1], w[2], w[3]);
+    ctx[2 * t + 1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 

@@ -103,6 +103,8 @@ int main(int argc, char **argv) {
   RUN(128, 128, 4);
   RUN(32, 8, 8);
   RUN(64, 32, 4);
+  RUN(160, 32, 2);  // a bucket of five contiguous seed-context records
+  RUN(160, 32, 4);
   timeit("40B window aligned 8, 4 in flight", [&](int it, uint64_t s) { window40<4><<<blocks, threads>>>((const uint64_t *)a, n_bytes / 8, it, out, s); }, per_iter * 4, 40);
   timeit("40B window aligned 8, 8 in flight", [&](int it, uint64_t s) { window40<8><<<blocks, threads>>>((const uint64_t *)a, n_bytes / 8, it, out, s); }, per_iter * 8, 40);
   return 0;

@@ -1,5 +1,7 @@
 """Kernel-variant timing on the bench workload (3.1 Gbp synthetic genome, PBAT pairs).
-usage: variant_perf.py [pairs] [variants, e.g. 2,3,4] [check_n]"""
+usage: variant_perf.py [pairs] [variants, e.g. 2,3,4 or 3/0/0,3/1/0,3/1/1] [check_n]
+A variant is MINB[n][/CTX[/CC]]: n = single-kernel path, CTX / CC = ABISMAL_B200_CTX / ABISMAL_B200_CC
+(seed-context records, compact counters) for the index the variant runs on."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -15,10 +17,21 @@ prefix = os.path.join(paths["dir"], "pbat_n%d_r0" % pairs)
 fq1, fq2 = workload.simulate_reads(ref_bin, paths["fasta"], prefix, pairs, seed=20251017 % 1000, paired=True,
                                    mode_flag="-a", n_procs=16, log=log)
 b1, b2 = workload.load_fastq_fast(fq1), workload.load_fastq_fast(fq2)
-ix = Index(ixf, 0)
 mode = MODE_PAIRED | MODE_A_RICH
 first = None
-for v in variants:
+ix, ix_key = None, None
+for vfull in variants:
+    parts = vfull.split("/")
+    v = parts[0]
+    key = (parts[1] if len(parts) > 1 else "1", parts[2] if len(parts) > 2 else "1")
+    if key != ix_key:
+        if ix is not None:
+            ix.close()
+        os.environ["ABISMAL_B200_CTX"], os.environ["ABISMAL_B200_CC"] = key
+        t = time.time()
+        ix = Index(ixf, 0)
+        ix_key = key
+        log("index ctx=%s cc=%s: %.2f GB resident, created in %.1fs" % (key[0], key[1], ix.device_bytes / 1e9, time.time() - t))
     os.environ["ABISMAL_B200_MINB"] = v.rstrip("n")
     os.environ["ABISMAL_B200_SPLIT"] = "0" if v.endswith("n") else "1"
     m = Mapper(ix, mode=mode, max_batch=b1.n, max_read_len=max(b1.max_len, b2.max_len, 64),
@@ -27,7 +40,7 @@ for v in variants:
     ms = []
     for it in range(4):
         m.run(); m.sync(); ms.append(m.last_kernel_ms)
-    log("MINB=%s kernel ms %s -> %.3f M pairs/s" % (v, ["%.1f" % x for x in ms], b1.n / min(ms[1:]) / 1e3))
+    log("variant %s kernel ms %s -> %.3f M pairs/s" % (vfull, ["%.1f" % x for x in ms], b1.n / min(ms[1:]) / 1e3))
     if os.environ.get("COUNT"):
         log(m.counters().as_dict())
     res = m.map_batch(b1, b2)
@@ -35,15 +48,19 @@ for v in variants:
         first = res
     else:
         import helpers
-        helpers.assert_results_equal(res, first, True)
-        log("variant %s results identical to variant %s" % (v, variants[0]))
+        try:
+            helpers.assert_results_equal(res, first, True)
+            log("variant %s results identical to variant %s" % (vfull, variants[0]))
+        except AssertionError as e:
+            log("MISMATCH: variant %s differs from variant %s: %s" % (vfull, variants[0], str(e)[:500]))
     m.close()
 if check_n:
     import helpers
     o = helpers.OracleMapper(ixf, mode=mode)
     t = time.time(); want = o.map_batch(b1.slice(0, check_n), b2.slice(0, check_n)); dt = time.time() - t
-    os.environ["ABISMAL_B200_MINB"] = variants[0].rstrip("n")
-    os.environ["ABISMAL_B200_SPLIT"] = "0" if variants[0].endswith("n") else "1"
+    v0 = variants[-1].split("/")[0]  # the index of the last variant is still resident
+    os.environ["ABISMAL_B200_MINB"] = v0.rstrip("n")
+    os.environ["ABISMAL_B200_SPLIT"] = "0" if v0.endswith("n") else "1"
     m = Mapper(ix, mode=mode, max_batch=check_n, max_read_len=max(b1.max_len, b2.max_len, 64))
     got = m.map_batch(b1.slice(0, check_n), b2.slice(0, check_n))
     helpers.assert_results_equal(got, want, True)
