@@ -98,6 +98,8 @@ def load_library():
     lib.abg_mapper_download.argtypes = [C.c_void_p, C.POINTER(abg_results)]
     lib.abg_mapper_last_kernel_ms.argtypes = [C.c_void_p]
     lib.abg_mapper_last_kernel_ms.restype = C.c_float
+    lib.abg_mapper_last_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.abg_mapper_last_phase_ms.restype = None
     lib.abg_mapper_launches_per_run.argtypes = [C.c_void_p]
     lib.abg_mapper_launches_per_run.restype = C.c_uint32
     lib.abg_mapper_get_counters.argtypes = [C.c_void_p, C.POINTER(abg_work_counters)]
@@ -309,6 +311,13 @@ class Mapper:
     @property
     def last_kernel_ms(self):
         return float(self.lib.abg_mapper_last_kernel_ms(self._h))
+
+    @property
+    def last_phase_ms(self):
+        """(seed_kernel, align_kernel, redo map_reads_kernel) CUDA-event ms of the last run()."""
+        out = (C.c_float * 3)()
+        self.lib.abg_mapper_last_phase_ms(self._h, out)
+        return [float(x) for x in out]
 
     @property
     def launches_per_run(self):

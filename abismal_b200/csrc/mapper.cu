@@ -94,6 +94,8 @@ struct abg_mapper {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;       // pipelined abg_map_batch
   cudaStream_t s_run[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_start = nullptr;
+  cudaEvent_t ev_ph[2] = {nullptr, nullptr};           // abg_mapper_run: after seed_kernel, after align_kernel
+  float phase_ms[3] = {0.f, 0.f, 0.f};                 // seed, align, redo (two-phase) or {whole, 0, 0}
   cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_out[kMaxChunks] = {};
   float last_ms = 0.f;
   // launch shape
@@ -211,7 +213,7 @@ int launch_one(const void *kernel, int grid, size_t smem, ab2dev::KernelParams &
 // One sub-batch on stream st.  Two-phase mode: seeding (one warp per read strand), then alignment/mating (one
 // warp per pair) from the stored candidate sets, then the single-kernel path for the few pairs whose sets
 // outgrew the stored form.  P.work_counter points at this chunk's {map, seed, align} counters + redo count.
-int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st) {
+int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const cudaEvent_t *ev_ph = nullptr) {
   if (P.n == 0) return ABG_OK;
   const uint64_t wpb = ab2dev::kWarpsPerBlock;
   int rc;
@@ -226,9 +228,11 @@ int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st) {
   const uint64_t n_work = m->paired ? (uint64_t)P.n * m->n_pass : P.n;
   if ((rc = launch_one(m->kernel_s, (int)std::min<uint64_t>((uint64_t)m->grid_s, (n_work + wpb - 1) / wpb), m->smem, Q, st)))
     return rc;
+  if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[0], st));
   Q.work_counter = work + 2;
   if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a, ((uint64_t)P.n + wpb - 1) / wpb), m->smem, Q, st)))
     return rc;
+  if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[1], st));
   Q.work_counter = work;
   Q.item_list = P.redo_list;
   Q.n_items_ptr = P.redo_count;
@@ -597,6 +601,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   }
   ABG_M(cudaEventCreate(&m->ev0));
   ABG_M(cudaEventCreate(&m->ev1));
+  ABG_M(cudaEventCreate(&m->ev_ph[0]));
+  ABG_M(cudaEventCreate(&m->ev_ph[1]));
   ABG_M(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
   for (uint32_t k = 0; k < kMaxChunks; ++k) {
     ABG_M(cudaEventCreateWithFlags(&m->ev_in[k], cudaEventDisableTiming));
@@ -725,6 +731,8 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFreeHost(m->h_flags);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  for (cudaEvent_t e : m->ev_ph)
+    if (e) cudaEventDestroy(e);
   if (m->ev_start) cudaEventDestroy(m->ev_start);
   for (uint32_t k = 0; k < kMaxChunks; ++k) {
     if (m->ev_in[k]) cudaEventDestroy(m->ev_in[k]);
@@ -786,20 +794,40 @@ int abg_mapper_run(abg_mapper *m) {
   if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->stream));
   ABG_CUDA(cudaEventRecord(m->ev0, m->stream));
   int rc;
-  if ((rc = launch(m, P, m->stream)) != ABG_OK) return rc;
+  if ((rc = launch(m, P, m->stream, m->ev_ph)) != ABG_OK) return rc;
   ABG_CUDA(cudaEventRecord(m->ev1, m->stream));
   m->timed = true;
   return ABG_OK;
 }
 
+namespace {
+void read_times(abg_mapper *m) {
+  m->phase_ms[0] = m->phase_ms[1] = m->phase_ms[2] = 0.f;
+  if (!m->timed || cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) {
+    m->last_ms = 0.f;
+    (void)cudaGetLastError();  // do not leave a stale error behind
+    return;
+  }
+  m->phase_ms[0] = m->last_ms;
+  if (m->split && m->cur_n) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (cudaEventElapsedTime(&a, m->ev0, m->ev_ph[0]) == cudaSuccess && cudaEventElapsedTime(&b, m->ev_ph[0], m->ev_ph[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&c, m->ev_ph[1], m->ev1) == cudaSuccess) {
+      m->phase_ms[0] = a;
+      m->phase_ms[1] = b;
+      m->phase_ms[2] = c;
+    }
+    else
+      (void)cudaGetLastError();
+  }
+}
+}  // namespace
+
 int abg_mapper_sync(abg_mapper *m) {
   if (!m) return fail(ABG_ERR_INVALID, "abg_mapper_sync: null mapper");
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ABG_CUDA(cudaStreamSynchronize(m->stream));
-  if (!m->timed || cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) {
-    m->last_ms = 0.f;
-    (void)cudaGetLastError();  // do not leave a stale error behind
-  }
+  read_times(m);
   return ABG_OK;
 }
 
@@ -817,10 +845,7 @@ int abg_mapper_download(abg_mapper *m, abg_results *r) {
     ABG_CUDA(cudaMemcpyAsync(&m->counters, m->d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              m->stream));
   ABG_CUDA(cudaStreamSynchronize(m->stream));
-  if (!m->timed || cudaEventElapsedTime(&m->last_ms, m->ev0, m->ev1) != cudaSuccess) {
-    m->last_ms = 0.f;
-    (void)cudaGetLastError();  // do not leave a stale error behind
-  }
+  read_times(m);
   scatter_results(m, d, r, 0, n);
   return finish_results(m, d, r, n);
 }
@@ -901,6 +926,9 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
 }
 
 float abg_mapper_last_kernel_ms(const abg_mapper *m) { return m ? m->last_ms : 0.f; }
+void abg_mapper_last_phase_ms(const abg_mapper *m, float out[3]) {
+  for (int k = 0; k < 3; ++k) out[k] = m ? m->phase_ms[k] : 0.f;
+}
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m) { return (m && m->cur_n) ? (m->split ? 3u : 1u) : 0u; }
 uint32_t abg_mapper_chunk(const abg_mapper *m) { return m ? m->chunk : 0u; }
 

@@ -115,9 +115,11 @@ def run_reference_map(index_path, fq1, fq2, n_threads, extra=("-P",)):
 
 
 def algorithmic_bytes(counters, units):
-    """bytes = 8 N_lookup + 4 N_entry + 8 (N_word + N_cmp) + 0.5 N_dpref, per unit."""
+    """bytes = 8 N_lookup + 4 N_entry + 8 (N_word + N_cmp) + 0.5 N_dpref, per unit.
+    -> (seeding part: counter probes, index entries, packed compares; alignment part: DP reference bases)"""
     c = counters
-    return (8 * c["n_lookup"] + 4 * c["n_entry"] + 8 * (c["n_word"] + c["n_cmp"]) + 0.5 * c["n_dpref"]) / units
+    return ((8 * c["n_lookup"] + 4 * c["n_entry"] + 8 * (c["n_word"] + c["n_cmp"])) / units,
+            0.5 * c["n_dpref"] / units)
 
 
 def main():
@@ -234,11 +236,12 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    kernel_ms = []
+    kernel_ms, phase_ms = [], [0.0, 0.0, 0.0]
     for _ in range(args.steps):
         m.run()
         m.sync()
         kernel_ms.append(m.last_kernel_ms)
+        phase_ms = [a + b for a, b in zip(phase_ms, m.last_phase_ms)]
     barrier()
     dev_ms = sum(kernel_ms)
     launches = args.steps * m.launches_per_run
@@ -290,14 +293,22 @@ def main():
             t = time.perf_counter()
             o.map_batch(b1.slice(0, n_o), b2.slice(0, n_o))
             port_s = time.perf_counter() - t
-            bytes_per_pair = algorithmic_bytes(o.counters.as_dict(), n_o)
+            seed_bytes, dp_bytes = algorithmic_bytes(o.counters.as_dict(), n_o)
             o.close()
-            ms_per_launch = dev_ms / launches
+            # dominant kernel: seed_kernel (seed hashing, counter/index lookups, packed compare, candidate sets);
+            # its launch time comes from CUDA events recorded on the launching stream between the kernels
+            names = ("seed_kernel", "align_kernel", "map_reads_kernel(redo)")
+            per_kernel = {nm: {"ms_per_launch": t / args.steps, "share_of_step": t / dev_ms}
+                          for nm, t in zip(names, phase_ms)}
+            ms_per_launch = phase_ms[0] / args.steps
+            bytes_per_pair = seed_bytes
             achieved = bytes_per_pair * b1.n / (ms_per_launch / 1e3) / 1e9
             traffic, gather = None, None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                     tj = json.load(f)
+                if not tj.get("kernel", "").startswith("seed_kernel"):
+                    raise KeyError("traffic.json is not a seed_kernel capture")
                 # ncu --set full capture of the same kernel on a 262144-pair batch of the same reads,
                 # scaled to this launch's batch (the kernel's work is linear in the number of pairs)
                 traffic = float(tj["dram_bytes_per_pair"]) * b1.n
@@ -312,7 +323,8 @@ def main():
             out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                                "algorithmic_bytes_per_pair": bytes_per_pair,
-                               "kernel": "map_reads_kernel", "ms_per_launch": ms_per_launch,
+                               "algorithmic_bytes_per_pair_whole_path": seed_bytes + dp_bytes,
+                               "kernel": "seed_kernel", "ms_per_launch": ms_per_launch, "kernels": per_kernel,
                                "counters_from": "CPU oracle on the first %d pairs of the batch" % n_o,
                                "random_gather": gather}
             n_s = min(args.cpu_sample_pairs, b1.n)

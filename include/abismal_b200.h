@@ -171,6 +171,10 @@ int abg_mapper_sync(abg_mapper *m);
 int abg_mapper_download(abg_mapper *m, abg_results *results);
 /* CUDA-event time of the most recent abg_mapper_run (after abg_mapper_sync). */
 float abg_mapper_last_kernel_ms(const abg_mapper *m);
+/* The same run split by kernel (CUDA events on the launching stream between the launches):
+ * out[0] seed_kernel, out[1] align_kernel, out[2] map_reads_kernel over the redo list.
+ * Single-kernel mode (ABISMAL_B200_SPLIT=0): out[0] = the whole run. */
+void abg_mapper_last_phase_ms(const abg_mapper *m, float out[3]);
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m);
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out);
 
