@@ -100,7 +100,7 @@ struct abg_mapper {
   float last_ms = 0.f;
   // launch shape
   int grid = 0, minb = 0, grid_scratch = 0;
-  size_t smem = 0;
+  size_t smem = 0, smem_s = 0, smem_a = 0;   // dynamic shared memory: full layout, seeding kernel, alignment kernel
   const void *kernel = nullptr;
   // two-phase launch: seed_kernel -> align_kernel -> map_reads_kernel over the redo list
   bool split = false;
@@ -219,6 +219,7 @@ int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const 
   int rc;
   if (!m->split) {
     const int grid = (int)std::min<uint64_t>((uint64_t)m->grid, ((uint64_t)P.n + wpb - 1) / wpb);
+    P.layout_kind = ab2dev::kLayoutFull;
     return launch_one(m->kernel, grid, m->smem, P, st);
   }
   unsigned int *work = P.work_counter;
@@ -226,16 +227,19 @@ int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const 
   ab2dev::KernelParams Q = P;
   Q.work_counter = work + 1;
   const uint64_t n_work = m->paired ? (uint64_t)P.n * m->n_pass : P.n;
-  if ((rc = launch_one(m->kernel_s, (int)std::min<uint64_t>((uint64_t)m->grid_s, (n_work + wpb - 1) / wpb), m->smem, Q, st)))
+  Q.layout_kind = ab2dev::kLayoutSeed;
+  if ((rc = launch_one(m->kernel_s, (int)std::min<uint64_t>((uint64_t)m->grid_s, (n_work + wpb - 1) / wpb), m->smem_s, Q, st)))
     return rc;
   if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[0], st));
   Q.work_counter = work + 2;
-  if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a, ((uint64_t)P.n + wpb - 1) / wpb), m->smem, Q, st)))
+  Q.layout_kind = ab2dev::kLayoutAlign;
+  if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a, ((uint64_t)P.n + wpb - 1) / wpb), m->smem_a, Q, st)))
     return rc;
   if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[1], st));
   Q.work_counter = work;
   Q.item_list = P.redo_list;
   Q.n_items_ptr = P.redo_count;
+  Q.layout_kind = ab2dev::kLayoutFull;
   return launch_one(m->kernel, m->grid, m->smem, Q, st);
 }
 
@@ -611,7 +615,9 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   }
 
   // launch shape: persistent grid, as many CTAs per SM as shared memory/registers allow
-  m->smem = ab2dev::block_smem_bytes(m->ml, m->paired);
+  m->smem = ab2dev::block_smem_bytes(m->ml, m->paired, ab2dev::kLayoutFull);
+  m->smem_s = ab2dev::block_smem_bytes(m->ml, m->paired, ab2dev::kLayoutSeed);
+  m->smem_a = ab2dev::block_smem_bytes(m->ml, m->paired, ab2dev::kLayoutAlign);
   {
     // register-allocation variant (CTAs per SM the kernel is bounded for); ABISMAL_B200_MINB overrides for tuning
     const char *e = std::getenv("ABISMAL_B200_MINB");
@@ -644,10 +650,10 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
                 : m->minb == 4 ? (const void *)ab2dev::align_kernel<4>
                                : (const void *)ab2dev::align_kernel<3>;
     int per_s = 0, per_a = 0;
-    ABG_M(cudaFuncSetAttribute(m->kernel_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
-    ABG_M(cudaFuncSetAttribute(m->kernel_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
-    ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_s, m->kernel_s, ab2dev::kThreadsPerBlock, m->smem));
-    ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, m->kernel_a, ab2dev::kThreadsPerBlock, m->smem));
+    ABG_M(cudaFuncSetAttribute(m->kernel_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_s));
+    ABG_M(cudaFuncSetAttribute(m->kernel_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_a));
+    ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_s, m->kernel_s, ab2dev::kThreadsPerBlock, m->smem_s));
+    ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, m->kernel_a, ab2dev::kThreadsPerBlock, m->smem_a));
     if (per_s < 1 || per_a < 1) {
       abg_mapper_destroy(m);
       return fail(ABG_ERR_CUDA, "abg_mapper_create: kernel does not fit on an SM");

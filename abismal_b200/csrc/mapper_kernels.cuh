@@ -132,6 +132,7 @@ struct KernelParams {
   unsigned int *redo_count;
   const uint32_t *item_list; // map_reads_kernel only: map item_list[0 .. *n_items_ptr) instead of 0 .. n
   const unsigned int *n_items_ptr;
+  uint32_t layout_kind;      // kLayoutFull / kLayoutSeed / kLayoutAlign: which regions the warp's shared memory holds
 };
 
 // ---- 64-bit view of se_element {int16 diffs; uint16 flags; uint32 pos} -------
@@ -201,49 +202,60 @@ static_assert(sizeof(KernelParams) <= kParamBytes, "KernelParams must fit its sh
 
 __host__ __device__ __forceinline__ uint32_t tb_sm_words(uint32_t ml) { return (ml + 64u + 32u + 15u) / 16u; }
 
+// Shared-memory regions per warp.  The three kernels keep different subsets (layout_kind): the seeding kernel
+// needs no traceback words, no reference bytes and one candidate set, and spends the room on the staging
+// buffers of its asynchronous seed-context gathers; the alignment kernel needs no staging, log or planes.
+constexpr uint32_t kLayoutFull = 0, kLayoutSeed = 1, kLayoutAlign = 2;
+constexpr int kStages = 4;             // chunks of 32 seed-context records in flight per warp (cp.async groups)
+constexpr uint32_t kStageBytes = 32u * 32u + 2u * 32u * 4u;  // 32 records + {slot, sub} of their candidates
+
 struct WarpLayout {
-  uint32_t o_packed, o_masks, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, total;
+  uint32_t o_packed, o_masks, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, o_stage,
+      total;
   uint32_t plane_words, elig_words, mask_words;
 };
 
-__host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool paired) {
+__host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool paired, uint32_t kind) {
   WarpLayout L;
+  const bool seed = kind != kLayoutAlign, aln = kind != kLayoutSeed;
   uint32_t o = 0;
+  L.o_stage = o;
+  if (seed) o += (uint32_t)kStages * kStageBytes;  // first: 16-byte aligned cp.async destinations
   L.o_packed = o;
   o += ml / 2;                               // packed read, ml/16 u64
   L.o_se = o;
-  o += 2u * kSeSlots * 8u;                   // two SE heaps
+  if (aln || !paired) o += 2u * kSeSlots * 8u;  // two SE heaps
   L.o_pe = o;
-  if (paired) o += 2u * kPeSmemSlots * 8u;   // two PE heap heads
+  if (paired) o += (aln ? 2u : 1u) * kPeSmemSlots * 8u;   // PE heap heads (the seeding kernel fills one set)
   L.o_cs = o;
   o += 4u * (uint32_t)sizeof(CandState);
   L.o_scal = o;
   o += (uint32_t)sizeof(WarpScalars);
   L.o_tb = o;
-  o += 2u * tb_sm_words(ml) * kTbLanesSm * 8u;  // traceback words of 2 slots
+  if (aln) o += 2u * tb_sm_words(ml) * kTbLanesSm * 8u;  // traceback words of 2 slots
   L.o_log = o;
-  o += 2u * kLogCap * 4u;                    // survivor log: positions + packed (d, pm, table, offset)
+  if (seed) o += 2u * kLogCap * 4u;          // survivor log: positions + packed (d, pm, table, offset)
   L.elig_words = ml / 64u + 1u;              // specific offsets are < readlen / 2
   L.o_elig = o;
-  o += 2u * L.elig_words * 4u;
+  if (seed) o += 2u * L.elig_words * 4u;
   L.mask_words = ml / 32u + 1u;
   L.o_masks = o;
-  o += 4u * L.mask_words * 4u;               // read-vs-{A,C,G,T} match masks per 32-base chunk
+  if (seed) o += 4u * L.mask_words * 4u;     // read-vs-{A,C,G,T} match masks per 32-base chunk
   L.plane_words = ml / 32u + 2u;
   L.o_planes = o;
-  o += 3u * L.plane_words * 4u;
+  if (seed) o += 3u * L.plane_words * 4u;
   L.o_base = o;
   o += 2u * ml;
   L.o_qcode = o;
   o += 2u * (ml + 32u);
   L.o_refb = o;
-  o += ml + 64u + 32u;
+  if (aln) o += ml + 64u + 32u;              // reference bytes of the DP
   L.total = (o + 15u) & ~15u;
   return L;
 }
 
-__host__ __device__ __forceinline__ size_t block_smem_bytes(uint32_t ml, bool paired) {
-  return (size_t)kParamBytes + kTab3Bytes + (size_t)warp_layout(ml, paired).total * kWarpsPerBlock;
+__host__ __device__ __forceinline__ size_t block_smem_bytes(uint32_t ml, bool paired, uint32_t kind) {
+  return (size_t)kParamBytes + kTab3Bytes + (size_t)warp_layout(ml, paired, kind).total * kWarpsPerBlock;
 }
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -257,7 +269,7 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   int lane;
   __device__ __forceinline__ Warp() {
     const KernelParams &P = params();
-    L = warp_layout(P.ml, (P.mode & ABG_MODE_PAIRED) != 0);
+    L = warp_layout(P.ml, (P.mode & ABG_MODE_PAIRED) != 0, P.layout_kind);
     base_ptr = smem_raw + kParamBytes + kTab3Bytes + (size_t)L.total * (threadIdx.x >> 5);
     lane = threadIdx.x & 31;
   }
@@ -276,6 +288,7 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   __device__ __forceinline__ uint32_t *masks(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_masks) + k * L.mask_words; }
   __device__ __forceinline__ uint32_t *log_pos() const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_log); }
   __device__ __forceinline__ uint32_t *log_meta() const { return log_pos() + kLogCap; }
+  __device__ __forceinline__ unsigned char *stage(int k) const { return base_ptr + L.o_stage + (size_t)k * kStageBytes; }
   __device__ __forceinline__ uint32_t *elig(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_elig) + k * L.elig_words; }
   __device__ __forceinline__ size_t slot() const { return (size_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); }
   __device__ __forceinline__ uint64_t *tb_gm(int s) const {
@@ -695,6 +708,105 @@ __device__ __forceinline__ void load_ctx(const uint4 *p, uint32_t (&w)[8]) {
 #endif
 }
 
+// Deep part of a compare chunk: index entries, 2-bit genome windows (staged, with early exit at the bound) and
+// the exact 4-bit compare for windows that hold N / IUPAC codes, for the candidates still `valid`.
+template <int KC, int NC0>
+__device__ __forceinline__ void compare_deep(const IndexDev &ix, const uint32_t *__restrict__ index3,
+                                             const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
+                                             const uint32_t *mT, int n_words, int bound, const bool (&valid)[KC],
+                                             const uint32_t (&slot)[KC], const uint32_t (&sub)[KC], int (&d)[KC],
+                                             int (&pm)[KC], uint32_t (&the_pos)[KC], uint32_t &n_entry,
+                                             uint32_t &n_word) {
+  const int n_bases = 16 * n_words;
+  const int n_chunks = (n_bases + 31) >> 5;
+  // ---- index gathers of the candidates the records did not reject (all of them without records) ----
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    uint32_t entry = 0;
+    if (valid[k]) entry = (sub[k] >> 31) ? __ldg(index3 + slot[k]) : __ldg(ix.index + slot[k]);
+    the_pos[k] = entry - (sub[k] & 0x7fffffffu);
+  }
+
+  // ---- stage 0: NC0 + 1 words of the 2-bit genome per candidate + its exception bits ----
+  uint64_t g[KC][NC0 + 1];
+  bool exc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const uint64_t *gp = ix.g2 + (the_pos[k] >> 5);
+#pragma unroll
+    for (int j = 0; j <= NC0; ++j) g[k][j] = (valid[k] && j <= n_chunks) ? __ldg(gp + j) : 0ull;
+    exc[k] = false;
+    if (valid[k]) {
+      const uint32_t b0 = the_pos[k] >> 8, b1 = (the_pos[k] + (uint32_t)n_bases - 1u) >> 8;
+      if (b1 - b0 <= 1u && (b0 >> 5) == (b1 >> 5))  // the usual case: one probe of the (L2-resident) bitmap
+        exc[k] = ((__ldg(ix.gx + (b0 >> 5)) >> (b0 & 31u)) & (1u | (1u << (b1 - b0)))) != 0u;
+      else
+        for (uint32_t b = b0; b <= b1; ++b) exc[k] = exc[k] || ((__ldg(ix.gx + (b >> 5)) >> (b & 31u)) & 1u);
+    }
+  }
+  uint64_t carry[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const uint32_t sh = the_pos[k] & 31u;
+    int dd = 0;
+#pragma unroll
+    for (int c = 0; c < NC0; ++c)
+      if (c < n_chunks) {
+        const uint32_t lo = __funnelshift_r((uint32_t)g[k][c], (uint32_t)g[k][c + 1], sh);
+        const uint32_t hi = __funnelshift_r((uint32_t)(g[k][c] >> 32), (uint32_t)(g[k][c + 1] >> 32), sh);
+        dd += min(32, n_bases - 32 * c) - __popc(match_bits(lo, hi, mA[c], mC[c], mG[c], mT[c]));
+      }
+    d[k] = dd;
+    pm[k] = valid[k] ? dd : (1 << 30);
+    carry[k] = g[k][NC0];
+    if (valid[k]) {
+      n_entry += 1;
+      n_word += (uint32_t)min(NC0, n_chunks);
+    }
+  }
+  // ---- later stages: two more chunks for every candidate still within the bound ----
+  for (int c = NC0; c < n_chunks; c += 2) {
+    uint64_t a[KC], b[KC];
+    bool alive[KC], any = false;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      alive[k] = pm[k] <= bound && !exc[k];
+      any = any || alive[k];
+      const uint64_t *gp = ix.g2 + (the_pos[k] >> 5) + c;
+      a[k] = alive[k] ? __ldg(gp + 1) : 0ull;
+      b[k] = (alive[k] && c + 1 < n_chunks) ? __ldg(gp + 2) : 0ull;
+    }
+    if (!any) break;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      if (alive[k]) {
+        const uint32_t sh = the_pos[k] & 31u;
+        uint32_t lo = __funnelshift_r((uint32_t)carry[k], (uint32_t)a[k], sh);
+        uint32_t hi = __funnelshift_r((uint32_t)(carry[k] >> 32), (uint32_t)(a[k] >> 32), sh);
+        int dd = d[k] + min(32, n_bases - 32 * c) - __popc(match_bits(lo, hi, mA[c], mC[c], mG[c], mT[c]));
+        if (c + 1 < n_chunks) {
+          lo = __funnelshift_r((uint32_t)a[k], (uint32_t)b[k], sh);
+          hi = __funnelshift_r((uint32_t)(a[k] >> 32), (uint32_t)(b[k] >> 32), sh);
+          dd += min(32, n_bases - 32 * (c + 1)) -
+                __popc(match_bits(lo, hi, mA[c + 1], mC[c + 1], mG[c + 1], mT[c + 1]));
+        }
+        d[k] = dd;
+        pm[k] = dd;
+        carry[k] = b[k];
+        n_word += (c + 1 < n_chunks) ? 2u : 1u;
+      }
+    }
+  }
+  // ---- windows holding N / IUPAC bases: the exact 4-bit compare (rare) ----
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+    if (exc[k]) {
+      int mx = 0;
+      d[k] = exact_compare(the_pos[k], n_words, bound, &mx);
+      pm[k] = mx;
+    }
+}
+
 template <int KC, int NC0>
 __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
                                               const uint4 *__restrict__ ctx3,
@@ -703,8 +815,8 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
                                               uint32_t total, uint32_t base_off, uint32_t incl, uint32_t tot,
                                               uint32_t n2, uint32_t s2, uint32_t s3, int lane, int (&d)[KC],
                                               int (&pm)[KC], uint32_t (&the_pos)[KC], uint32_t (&sub)[KC],
-                                              unsigned long long &n_entry,
-                                              unsigned long long &n_word) {
+                                              uint32_t &n_entry,
+                                              uint32_t &n_word) {
   bool valid[KC];
   const int n_bases = 16 * n_words;          // compared positions incl. the 0xF tail of the last packed word
   const int n_chunks = (n_bases + 31) >> 5;
@@ -768,92 +880,112 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
     any_left = any_left || valid[k];
   }
   if (!__any_sync(FULL, any_left)) return;
-  // ---- index gathers of the candidates the records did not reject (all of them without records) ----
-#pragma unroll
-  for (int k = 0; k < KC; ++k) {
-    uint32_t entry = 0;
-    if (valid[k]) entry = (sub[k] >> 31) ? __ldg(index3 + slot[k]) : __ldg(ix.index + slot[k]);
-    the_pos[k] = entry - (sub[k] & 0x7fffffffu);
-  }
+  compare_deep<KC, NC0>(ix, index3, mA, mC, mG, mT, n_words, bound, valid, slot, sub, d, pm, the_pos, n_entry, n_word);
+}
 
-  // ---- stage 0: NC0 + 1 words of the 2-bit genome per candidate + its exception bits ----
-  uint64_t g[KC][NC0 + 1];
-  bool exc[KC];
+// ---- asynchronous seed-context gathers (cp.async into the warp's staging buffers) ------------------------
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr uint32_t kSubThree = 0x80000000u;  // candidate comes from the three-letter bucket
+constexpr uint32_t kSubRec = 0x40000000u;    // its seed-context record was requested (staged path)
+
+// Issue the gathers of chunk [c0, c0 + 32) of this round's candidates (canonical order) into staging buffer
+// `st`: lane l owns candidate c0 + l, finds its bucket by binary search over the lanes' inclusive bucket-size
+// sums, and copies its 32-byte record global -> shared without going through registers.  Always commits one
+// cp.async group (possibly empty) so that the caller's group accounting is uniform.
+__device__ __forceinline__ void stage_issue(const IndexDev &ix, const uint4 *__restrict__ ctx3, unsigned char *st,
+                                            uint32_t c0, uint32_t total, uint32_t base_off, uint32_t incl,
+                                            uint32_t tot, uint32_t n2, uint32_t s2, uint32_t s3, int lane) {
+  uint32_t *meta = reinterpret_cast<uint32_t *>(st + 32u * 32u);
+  uint32_t slot = 0, sub = ~0u;
+  if (c0 < total) {
+    const uint32_t cidx = c0 + (uint32_t)lane;
+    int o = 0;
 #pragma unroll
-  for (int k = 0; k < KC; ++k) {
-    const uint64_t *gp = ix.g2 + (the_pos[k] >> 5);
-#pragma unroll
-    for (int j = 0; j <= NC0; ++j) g[k][j] = (valid[k] && j <= n_chunks) ? __ldg(gp + j) : 0ull;
-    exc[k] = false;
-    if (valid[k]) {
-      const uint32_t b0 = the_pos[k] >> 8, b1 = (the_pos[k] + (uint32_t)n_bases - 1u) >> 8;
-      if (b1 - b0 <= 1u && (b0 >> 5) == (b1 >> 5))  // the usual case: one probe of the (L2-resident) bitmap
-        exc[k] = ((__ldg(ix.gx + (b0 >> 5)) >> (b0 & 31u)) & (1u | (1u << (b1 - b0)))) != 0u;
-      else
-        for (uint32_t b = b0; b <= b1; ++b) exc[k] = exc[k] || ((__ldg(ix.gx + (b >> 5)) >> (b & 31u)) & 1u);
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+      const uint32_t vv = __shfl_sync(FULL, incl, (o + sft - 1) & 31);
+      if (vv <= cidx) o += sft;
+    }
+    o &= 31;
+    const uint32_t o_incl = __shfl_sync(FULL, incl, o);
+    const uint32_t o_tot = __shfl_sync(FULL, tot, o);
+    const uint32_t o_n2 = __shfl_sync(FULL, n2, o);
+    const uint32_t o_s2 = __shfl_sync(FULL, s2, o);
+    const uint32_t o_s3 = __shfl_sync(FULL, s3, o);
+    if (cidx < total) {
+      const uint32_t r = cidx - (o_incl - o_tot);
+      const bool three = r >= o_n2;
+      slot = three ? o_s3 + (r - o_n2) : o_s2 + r;
+      const uint32_t i_off = base_off + (uint32_t)o;
+      sub = i_off | (three ? kSubThree : 0u);
+      const uint4 *tab = three ? ctx3 : ix.ctx;
+      if (tab != nullptr) {
+        sub |= kSubRec;
+        const uint32_t a = min((uint32_t)(kCtxArrays - 1), i_off >> 5);
+        const uint4 *src = tab + 2 * ((uint64_t)a * (three ? ix.n_ctx3 : ix.n_ctx) + slot);
+        unsigned char *dst = st + 32u * (uint32_t)lane;
+        cp_async16(dst, src);
+        cp_async16(dst + 16, src + 1);
+      }
     }
   }
-  uint64_t carry[KC];
+  meta[lane] = slot;
+  meta[32 + lane] = sub;
+  cp_async_commit();
+}
+
+// Compare the chunk staged in `st` (its records have landed): seed-context prefilter from shared memory, then
+// the deep compare for what it could not reject.  Same results as compare_chunk<1, 4>.
+__device__ __forceinline__ void compare_staged(const IndexDev &ix, const uint32_t *__restrict__ index3,
+                                               const unsigned char *st, const uint32_t *mA, const uint32_t *mC,
+                                               const uint32_t *mG, const uint32_t *mT, int n_words, int bound, int lane,
+                                               int (&d)[1], int (&pm)[1], uint32_t (&the_pos)[1], uint32_t (&sub)[1],
+                                               uint32_t &n_entry, uint32_t &n_word) {
+  const uint32_t *meta = reinterpret_cast<const uint32_t *>(st + 32u * 32u);
+  const int n_bases = 16 * n_words;
+  const uint32_t sub_m = meta[32 + lane];
+  uint32_t slot[1] = {meta[lane]};
+  bool valid[1] = {sub_m != ~0u};
+  sub[0] = sub_m & ~kSubRec;
+  d[0] = 0;
+  pm[0] = 1 << 30;
+  the_pos[0] = 0;
+  if (valid[0] && (sub_m & kSubRec) != 0u) {
+    const uint4 *rec = reinterpret_cast<const uint4 *>(st + 32u * (uint32_t)lane);
+    const uint4 x = rec[0], y = rec[1];
+    const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    const uint32_t i_off = sub_m & 0x3fffffffu;
+    const uint32_t a = min((uint32_t)(kCtxArrays - 1), i_off >> 5);
+    const uint32_t q0 = i_off - 32u * a;  // read position of the record's first base
+    int lb = 0;
 #pragma unroll
-  for (int k = 0; k < KC; ++k) {
-    const uint32_t sh = the_pos[k] & 31u;
-    int dd = 0;
-#pragma unroll
-    for (int c = 0; c < NC0; ++c)
-      if (c < n_chunks) {
-        const uint32_t lo = __funnelshift_r((uint32_t)g[k][c], (uint32_t)g[k][c + 1], sh);
-        const uint32_t hi = __funnelshift_r((uint32_t)(g[k][c] >> 32), (uint32_t)(g[k][c + 1] >> 32), sh);
-        dd += min(32, n_bases - 32 * c) - __popc(match_bits(lo, hi, mA[c], mC[c], mG[c], mT[c]));
+    for (int c = 0; c < 4; ++c) {
+      const int qb = (int)q0 + 32 * c;
+      const int nb = n_bases - qb;
+      if (nb > 0) {
+        const uint32_t wi = (uint32_t)qb >> 5, sh = (uint32_t)qb & 31u;
+        const uint32_t a_ = __funnelshift_r(mA[wi], mA[wi + 1], sh), c_ = __funnelshift_r(mC[wi], mC[wi + 1], sh);
+        const uint32_t g_ = __funnelshift_r(mG[wi], mG[wi + 1], sh), t_ = __funnelshift_r(mT[wi], mT[wi + 1], sh);
+        const uint32_t mm = ~match_bits(w[2 * c], w[2 * c + 1], a_, c_, g_, t_);
+        lb += __popc(nb >= 32 ? mm : (mm & ((1u << nb) - 1u)));
       }
-    d[k] = dd;
-    pm[k] = valid[k] ? dd : (1 << 30);
-    carry[k] = g[k][NC0];
-    if (valid[k]) {
+    }
+    if (lb > bound) {
+      valid[0] = false;
       n_entry += 1;
-      n_word += (unsigned long long)min(NC0, n_chunks);
+      n_word += 4;
     }
   }
-  // ---- later stages: two more chunks for every candidate still within the bound ----
-  for (int c = NC0; c < n_chunks; c += 2) {
-    uint64_t a[KC], b[KC];
-    bool alive[KC], any = false;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      alive[k] = pm[k] <= bound && !exc[k];
-      any = any || alive[k];
-      const uint64_t *gp = ix.g2 + (the_pos[k] >> 5) + c;
-      a[k] = alive[k] ? __ldg(gp + 1) : 0ull;
-      b[k] = (alive[k] && c + 1 < n_chunks) ? __ldg(gp + 2) : 0ull;
-    }
-    if (!any) break;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      if (alive[k]) {
-        const uint32_t sh = the_pos[k] & 31u;
-        uint32_t lo = __funnelshift_r((uint32_t)carry[k], (uint32_t)a[k], sh);
-        uint32_t hi = __funnelshift_r((uint32_t)(carry[k] >> 32), (uint32_t)(a[k] >> 32), sh);
-        int dd = d[k] + min(32, n_bases - 32 * c) - __popc(match_bits(lo, hi, mA[c], mC[c], mG[c], mT[c]));
-        if (c + 1 < n_chunks) {
-          lo = __funnelshift_r((uint32_t)a[k], (uint32_t)b[k], sh);
-          hi = __funnelshift_r((uint32_t)(a[k] >> 32), (uint32_t)(b[k] >> 32), sh);
-          dd += min(32, n_bases - 32 * (c + 1)) -
-                __popc(match_bits(lo, hi, mA[c + 1], mC[c + 1], mG[c + 1], mT[c + 1]));
-        }
-        d[k] = dd;
-        pm[k] = dd;
-        carry[k] = b[k];
-        n_word += (c + 1 < n_chunks) ? 2ull : 1ull;
-      }
-    }
-  }
-  // ---- windows holding N / IUPAC bases: the exact 4-bit compare (rare) ----
-#pragma unroll
-  for (int k = 0; k < KC; ++k)
-    if (exc[k]) {
-      int mx = 0;
-      d[k] = exact_compare(the_pos[k], n_words, bound, &mx);
-      pm[k] = mx;
-    }
+  if (!__any_sync(FULL, valid[0])) return;
+  compare_deep<1, 4>(ix, index3, mA, mC, mG, mT, n_words, bound, valid, slot, sub, d, pm, the_pos, n_entry, n_word);
 }
 
 // Ordered replay of the survivors of one compare round against candidate set `set_id`
@@ -923,15 +1055,24 @@ __device__ __forceinline__ void probe_two(const IndexDev &ix, uint32_t k, uint32
     e = __ldg(ix.counter + k + 1);
     return;
   }
-  const uint32_t w[7] = {x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-  uint32_t before = 0, cnt = 0;
-#pragma unroll
-  for (int m = 0; m < 7; ++m) {
-    const int nb = min(4, max(0, (int)t - 4 * m));  // bytes of word m that precede bucket t
-    const uint32_t mask = nb == 4 ? ~0u : ((1u << (8 * nb)) - 1u);
-    before += __vsadu4(w[m] & mask, 0u);
-    if ((int)(t >> 2) == m) cnt = (w[m] >> (8u * (t & 3u))) & 255u;
-  }
+  // 28 one-byte bucket sizes in 7 words; bucket t = byte (t & 3) of word t >> 2.  Kept in registers (no array)
+  const uint32_t tw = t >> 2, tb = 8u * (t & 3u);
+  uint32_t before = 0;
+  before += tw > 0u ? __vsadu4(x.y, 0u) : 0u;
+  before += tw > 1u ? __vsadu4(x.z, 0u) : 0u;
+  before += tw > 2u ? __vsadu4(x.w, 0u) : 0u;
+  before += tw > 3u ? __vsadu4(y.x, 0u) : 0u;
+  before += tw > 4u ? __vsadu4(y.y, 0u) : 0u;
+  before += tw > 5u ? __vsadu4(y.z, 0u) : 0u;
+  uint32_t cur = x.y;
+  cur = tw == 1u ? x.z : cur;
+  cur = tw == 2u ? x.w : cur;
+  cur = tw == 3u ? y.x : cur;
+  cur = tw == 4u ? y.y : cur;
+  cur = tw == 5u ? y.z : cur;
+  cur = tw == 6u ? y.w : cur;
+  before += __vsadu4(cur & ((1u << tb) - 1u), 0u);  // bytes of the bucket's own word that precede it
+  const uint32_t cnt = (cur >> tb) & 255u;
   s = x.x + before;
   e = s + cnt;
   if (cnt == 0u) s = e = 0u;  // what probe() reports for an empty bucket
@@ -957,7 +1098,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
   const uint4 *ctx3 = g_to_a ? ix.ctx_a : ix.ctx_t;
   const uint32_t maxc = P.max_candidates;
   const int n_words = (int)((readlen + 15) / 16);
-  unsigned long long c_lookup = 0, c_entry = 0, c_word = 0;
+  uint32_t c_lookup = 0, c_entry = 0, c_word = 0;  // per pass: far below 2^32
   volatile CandState *st = W.cs(set_id);  // the set's scalar state stays in shared memory
   const volatile uint64_t *heap0 = heap_of(W, set_id).sm;
   uint32_t *log_pos = W.log_pos(), *log_meta = W.log_meta();
@@ -1040,7 +1181,15 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
       const uint32_t incl = warp_incl_scan_add(tot, lane);
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       bool stop = false;
-      for (uint32_t c0 = 0; c0 < total && !stop; c0 += 32u * kCand) {
+      // Staged path: the records of up to kStages chunks are in flight (cp.async) while one chunk is compared
+      const bool staged = ix.ctx != nullptr && (ctx3 != nullptr || ix.n_ctx3 == 0);
+      if (staged) {
+#pragma unroll
+        for (int sg = 0; sg < kStages; ++sg)
+          stage_issue(ix, ctx3, W.stage(sg), 32u * sg, total, base_off, incl, tot, n2, s2, s3, lane);
+      }
+      int sg = 0;
+      for (uint32_t c0 = 0; c0 < total && !stop; c0 += 32u * (staged ? 1 : kCand)) {
         const int cutoff = st->cutoff;
         // In the specific phase compare against the looser bound the sensitive phase may use later (the heap
         // top only ever decreases) and log what survives it, unless the set is already full (then the
@@ -1058,8 +1207,26 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
         int d[kCand], pm[kCand];
         uint32_t the_pos[kCand];
         uint32_t sub[kCand];
-        compare_chunk<kCand, 4>(ix, index3, ctx3, mA, mC, mG, mT, n_words, bound, c0, total, base_off, incl, tot, n2, s2, s3,
-                                lane, d, pm, the_pos, sub, c_entry, c_word);
+        if (staged) {
+          cp_async_wait<kStages - 1>();  // the oldest of the kStages groups in flight = this chunk
+          int d1[1], pm1[1];
+          uint32_t pos1[1], sub1[1];
+          compare_staged(ix, index3, W.stage(sg), mA, mC, mG, mT, n_words, bound, lane, d1, pm1, pos1, sub1, c_entry,
+                         c_word);
+#pragma unroll
+          for (int k = 0; k < kCand; ++k) {
+            d[k] = k == 0 ? d1[0] : 0;
+            pm[k] = k == 0 ? pm1[0] : (1 << 30);
+            the_pos[k] = k == 0 ? pos1[0] : 0u;
+            sub[k] = k == 0 ? sub1[0] : 0u;
+          }
+          // refill the buffer just consumed with the chunk kStages ahead
+          stage_issue(ix, ctx3, W.stage(sg), c0 + 32u * kStages, total, base_off, incl, tot, n2, s2, s3, lane);
+          sg = (sg + 1) & (kStages - 1);
+        }
+        else
+          compare_chunk<kCand, 4>(ix, index3, ctx3, mA, mC, mG, mT, n_words, bound, c0, total, base_off, incl, tot, n2, s2,
+                                  s3, lane, d, pm, the_pos, sub, c_entry, c_word);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < kCand; ++k) {
@@ -1082,6 +1249,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
           }
         }
       }
+      if (staged) cp_async_wait<0>();  // nothing may land in a buffer the next round re-issues into
     }
     __syncwarp();
   }
@@ -1167,8 +1335,8 @@ __device__ __forceinline__ int band_width(int diffs, int max_diffs) {  // Abisma
 //   left  (i, j-1)   A: lane l-1's B of the previous iteration (its row was i); B: own A of this iteration
 // Arrow precedence on ties is left (I) > above (D) > diag (M), the reference's write order; the result is
 // the first maximum in row-major order (std::max_element).
-__device__ __noinline__ void align_wave(bool do_tb, int tb_slot, int end, int bw, int q_sz, uint32_t t_pos,
-                                        AlnOut *out) {
+template <bool TB>
+__device__ __noinline__ void align_wave(int tb_slot, int end, int bw, int q_sz, uint32_t t_pos, AlnOut *out) {
   const Warp W;
   const KernelParams &P = params();
   const int lane = W.lane;
@@ -1195,77 +1363,80 @@ __device__ __noinline__ void align_wave(bool do_tb, int tb_slot, int end, int bw
   }
   const int nl = (bw + 1) >> 1;  // lanes in use
   const int n_iter = (t_shift - 1) + (nl - 1);
-  const int jA = 2 * lane, jB = 2 * lane + 1;
+  // Cell (i, j) of the band holds query base qi = i + j - bw; it exists iff j < bw and 0 <= qi < q_sz (that is
+  // the reference's [left, right) of row i).  Cells that do not exist hold 0, as in the zero-filled table, so
+  // an `above` or `left` taken from one is -4 and never wins against v >= 0; the one existing cell the
+  // reference leaves out is `above` for the last query base (j + 1 == right on the rows below q_sz).
+  // At iteration T this lane is on row i = T - lane: qi(A) = T + lane - bw, qi(B) = qi(A) + 1.
+  const unsigned limA = 2 * lane < bw ? (unsigned)q_sz : 0u;
+  const unsigned limB = 2 * lane + 1 < bw ? (unsigned)q_sz : 0u;
+  const int up_mask = lane > 0 ? -1 : 0;  // lane 0 has no left neighbour for its A column
   uint64_t *tbs = W.tb_sm(tb_slot) + lane;           // [word][kTbLanesSm]
   uint64_t *tbg = W.tb_gm(tb_slot) + lane;           // [word][32]
   int A = 0, B = 0;
-  int best = 0, best_row = 0, best_col = 0;
+  int best = 0, best_at = 0;  // best_at = 2 T + (column B)
   uint64_t tbw = 0;
-  for (int T = 1; T <= n_iter; ++T) {
-    const int i = T - lane;
-    const bool row_ok = i >= 1 && i < t_shift;
-    const int left_lim = max(0, bw - i);
-    const int right_lim = min(bw, t_shift - i);
-    const uint32_t ref = row_ok ? refb[i - 1] : 0u;
-    const int b_up = __shfl_up_sync(FULL, B, 1);
-    int newA = 0, codeA = 3;
-    if (row_ok && jA >= left_lim && jA < right_lim) {
-      const uint32_t qb = q[i + jA - bw];
-      const int diag = A + ((qb & ref) ? 2 : -3);
-      int v = max(0, diag);
-      int a = (v == diag) ? 0 : 3;
-      if (jA + 1 < right_lim) {
-        const int above = B - 4;
-        v = max(v, above);
-        if (v == above) a = 2;
+  int qi = 1 + lane - bw;     // qi(A) of iteration T = 1
+  const uint8_t *rp = refb - lane;  // rp[T - 1] = reference base of this lane's row
+  uint32_t qa = (unsigned)qi < limA ? (uint32_t)q[qi] : 0u;
+  for (int T = 1; T <= n_iter; ++T, ++qi) {
+    const bool okA = (unsigned)qi < limA, okB = (unsigned)(qi + 1) < limB;
+    const uint32_t ref = (okA || okB) ? (uint32_t)rp[T - 1] : 0u;
+    const uint32_t qb = (unsigned)(qi + 1) < (unsigned)q_sz ? (uint32_t)q[qi + 1] : 0u;
+    const int left_in = __shfl_up_sync(FULL, B, 1) & up_mask;
+    // column A
+    int diag = A + ((qa & ref) ? 2 : -3);
+    int v = max(diag, 0);
+    int cA = diag >= 0 ? 0 : 3;
+    {
+      const int above = (qi + 1 < q_sz ? B : 0) - 4;
+      if (above >= v) {
+        v = above;
+        cA = 2;
       }
-      if (lane > 0) {
-        const int left = b_up - 4;
-        if (left >= v) {
-          v = left;
-          a = 1;
-        }
+      const int left = left_in - 4;
+      if (left >= v) {
+        v = left;
+        cA = 1;
       }
-      codeA = v > 0 ? a : 3;
-      if (v > best) {
-        best = v;
-        best_row = i;
-        best_col = jA;
-      }
-      newA = v;
+    }
+    const int newA = okA ? v : 0;
+    if (TB) cA = newA > 0 ? cA : 3;
+    if (newA > best) {
+      best = newA;
+      best_at = 2 * T;
     }
     const int a_down = __shfl_down_sync(FULL, newA, 1);
-    int newB = 0, codeB = 3;
-    if (row_ok && jB >= left_lim && jB < right_lim) {
-      const uint32_t qb = q[i + jB - bw];
-      const int diag = B + ((qb & ref) ? 2 : -3);
-      int v = max(0, diag);
-      int a = (v == diag) ? 0 : 3;
-      if (jB + 1 < right_lim) {
-        const int above = a_down - 4;
-        v = max(v, above);
-        if (v == above) a = 2;
+    // column B
+    diag = B + ((qb & ref) ? 2 : -3);
+    v = max(diag, 0);
+    int cB = diag >= 0 ? 0 : 3;
+    {
+      const int above = (qi + 2 < q_sz ? a_down : 0) - 4;
+      if (above >= v) {
+        v = above;
+        cB = 2;
       }
-      {
-        const int left = newA - 4;
-        if (left >= v) {
-          v = left;
-          a = 1;
-        }
+      const int left = newA - 4;
+      if (left >= v) {
+        v = left;
+        cB = 1;
       }
-      codeB = v > 0 ? a : 3;
-      if (v > best) {
-        best = v;
-        best_row = i;
-        best_col = jB;
-      }
-      newB = v;
+    }
+    const int newB = okB ? v : 0;
+    if (TB) cB = newB > 0 ? cB : 3;
+    if (newB > best) {
+      best = newB;
+      best_at = 2 * T + 1;
     }
     A = newA;
     B = newB;
-    if (do_tb) {
-      tbw |= (uint64_t)(uint32_t)(codeA | (codeB << 2)) << (4 * (T & 15));
+    qa = qb;
+    if (TB) {
+      // 4 bits per iteration, iteration T at bits 4 (T & 15) of word T >> 4
+      tbw = (tbw >> 4) | ((uint64_t)(uint32_t)(cA | (cB << 2)) << 60);
       if ((T & 15) == 15 || T == n_iter) {
+        if ((T & 15) != 15) tbw >>= 4 * (15 - (T & 15));
         if (lane < nl) {
           if (lane < kTbLanesSm) tbs[(T >> 4) * kTbLanesSm] = tbw;
           else tbg[(size_t)(T >> 4) * 32] = tbw;
@@ -1275,7 +1446,8 @@ __device__ __noinline__ void align_wave(bool do_tb, int tb_slot, int end, int bw
     }
   }
   // first maximum in row-major order (std::max_element)
-  int bv = best, br = best_row, bc = best_col;
+  int bv = best, br = (best_at >> 1) - lane, bc = 2 * lane + (best_at & 1);
+  if (best == 0) br = 0, bc = 0;
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) {
     const int ov = __shfl_xor_sync(FULL, bv, d);
@@ -1321,7 +1493,8 @@ __device__ __forceinline__ int align(bool record_tb, bool need_tb, int tb_slot, 
   }
   __syncwarp();
   if (tb && W.lane == 0) tk->valid = 0;
-  align_wave(tb, tb_slot, end, bw, q_sz, t_pos, &out);
+  if (tb) align_wave<true>(tb_slot, end, bw, q_sz, t_pos, &out);
+  else align_wave<false>(tb_slot, end, bw, q_sz, t_pos, &out);
   if (tb && W.lane == 0) {
     tk->pos = t_pos;
     tk->key = key;
