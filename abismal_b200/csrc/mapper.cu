@@ -106,6 +106,14 @@ struct abg_mapper {
   bool split = false;
   const void *kernel_s = nullptr, *kernel_a = nullptr;
   int grid_s = 0, grid_a = 0;
+  // overlapped launch: align_kernel (grid_a_aux) next to seed_kernel (grid_s) on a second stream, then the rest
+  // of the alignment (grid_a) behind the seeding; see launch()
+  bool overlap = false;
+  int grid_a_aux = 0;
+  uint32_t wait_ns = 0;
+  unsigned int *d_ready = nullptr;
+  cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};          // partners of stream, s_run[0], s_run[1]
+  cudaEvent_t ev_go[3] = {nullptr, nullptr, nullptr}, ev_aux[3] = {nullptr, nullptr, nullptr};
   uint32_t n_pass = 1, set_slots = 0;
   uint64_t *d_sets = nullptr;
   unsigned int *d_redo_flag = nullptr;
@@ -225,21 +233,47 @@ int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const 
   unsigned int *work = P.work_counter;
   ABG_CUDA(cudaMemsetAsync(P.redo_flag, 0, (size_t)P.n * sizeof(unsigned int), st));
   ab2dev::KernelParams Q = P;
-  Q.work_counter = work + 1;
   const uint64_t n_work = m->paired ? (uint64_t)P.n * m->n_pass : P.n;
+  const int grid_s = (int)std::min<uint64_t>((uint64_t)m->grid_s, (n_work + wpb - 1) / wpb);
+  const int s_idx = st == m->stream ? 0 : (st == m->s_run[0] ? 1 : 2);
+  const bool overlap = m->overlap;
+  if (overlap) {
+    // Seeding is bound by DRAM latency and leaves most issue slots idle; alignment is bound by issue slots
+    // and needs no DRAM.  Run them on the same SMs at the same time: seed_kernel with grid_s CTAs, next to it
+    // (second stream) align_kernel with grid_a_aux CTAs that consumes pairs as their sets are published,
+    // and behind the seeding a second align_kernel launch that takes the SM share the seeding frees.
+    Q.ready = m->d_ready + (P.redo_flag - m->d_redo_flag);
+    Q.ready_need = m->paired ? m->n_pass : 1u;
+    Q.wait_ns = m->wait_ns;
+    ABG_CUDA(cudaMemsetAsync(Q.ready, 0, (size_t)P.n * sizeof(unsigned int), st));
+    ABG_CUDA(cudaEventRecord(m->ev_go[s_idx], st));
+    ABG_CUDA(cudaStreamWaitEvent(m->s_aux[s_idx], m->ev_go[s_idx], 0));
+  }
+  Q.work_counter = work + 1;
   Q.layout_kind = ab2dev::kLayoutSeed;
-  if ((rc = launch_one(m->kernel_s, (int)std::min<uint64_t>((uint64_t)m->grid_s, (n_work + wpb - 1) / wpb), m->smem_s, Q, st)))
-    return rc;
+  Q.slot_base = P.slot_base;
+  if ((rc = launch_one(m->kernel_s, grid_s, m->smem_s, Q, st))) return rc;
   if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[0], st));
   Q.work_counter = work + 2;
   Q.layout_kind = ab2dev::kLayoutAlign;
-  if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a, ((uint64_t)P.n + wpb - 1) / wpb), m->smem_a, Q, st)))
-    return rc;
+  const uint64_t a_blocks = ((uint64_t)P.n + wpb - 1) / wpb;
+  if (overlap) {
+    ab2dev::KernelParams A = Q;
+    A.slot_base = P.slot_base + (uint32_t)m->grid_s * (uint32_t)wpb;  // disjoint from the seeding kernel's slots
+    if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a_aux, a_blocks), m->smem_a, A, m->s_aux[s_idx])))
+      return rc;
+    ABG_CUDA(cudaEventRecord(m->ev_aux[s_idx], m->s_aux[s_idx]));
+  }
+  // behind the seeding (stream order): every set is stored, nothing to wait for; takes the seeding's slots
+  Q.ready = nullptr;
+  if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a, a_blocks), m->smem_a, Q, st))) return rc;
+  if (overlap) ABG_CUDA(cudaStreamWaitEvent(st, m->ev_aux[s_idx], 0));
   if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[1], st));
   Q.work_counter = work;
   Q.item_list = P.redo_list;
   Q.n_items_ptr = P.redo_count;
   Q.layout_kind = ab2dev::kLayoutFull;
+  Q.slot_base = P.slot_base;
   return launch_one(m->kernel, m->grid, m->smem, Q, st);
 }
 
@@ -660,7 +694,30 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     }
     m->grid_s = n_sm * per_s;
     m->grid_a = n_sm * per_a;
-    grid_max = std::max(grid_max, std::max(m->grid_s, m->grid_a));
+    {
+      // overlapped launch (default): ABISMAL_B200_OVERLAP=0 runs seed_kernel -> align_kernel back to back.
+      // ABISMAL_B200_SEED_BLOCKS / ABISMAL_B200_AUX_BLOCKS: CTAs per SM of seed_kernel and of the align_kernel
+      // launch that runs next to it (together they must fit on an SM: registers and shared memory).
+      const char *e = std::getenv("ABISMAL_B200_OVERLAP");
+      m->overlap = !(e && std::atoi(e) == 0) && per_s >= 2;
+      if (m->overlap) {
+        const char *es = std::getenv("ABISMAL_B200_SEED_BLOCKS"), *ea = std::getenv("ABISMAL_B200_AUX_BLOCKS");
+        const int sb = std::max(1, std::min(per_s, es ? std::atoi(es) : per_s - 1));
+        const int ab = std::max(1, std::min(per_a, ea ? std::atoi(ea) : 1));
+        m->grid_s = n_sm * sb;
+        m->grid_a_aux = n_sm * ab;
+        const char *ew = std::getenv("ABISMAL_B200_WAIT_MS");
+        const long wms = ew ? std::atol(ew) : 50;
+        m->wait_ns = (uint32_t)std::min<long>(4000, std::max<long>(1, wms)) * 1000000u;
+        ABG_M(cudaMalloc(&m->d_ready, (size_t)max_batch * sizeof(unsigned int)));
+        for (int k = 0; k < 3; ++k) {
+          ABG_M(cudaStreamCreateWithFlags(&m->s_aux[k], cudaStreamNonBlocking));
+          ABG_M(cudaEventCreateWithFlags(&m->ev_go[k], cudaEventDisableTiming));
+          ABG_M(cudaEventCreateWithFlags(&m->ev_aux[k], cudaEventDisableTiming));
+        }
+      }
+    }
+    grid_max = std::max(grid_max, std::max(m->grid_s + m->grid_a_aux, m->grid_a));
     const bool rpbat = (p->mode & ABG_MODE_RANDOM_PBAT) != 0;
     m->n_pass = m->paired ? (rpbat ? 8u : 4u) : 1u;
     m->set_slots = m->paired ? ab2dev::kSetSlotsPe : ab2dev::kSetSlotsSe;
@@ -730,6 +787,12 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFree(m->d_mem_scr);
   cudaFree(m->d_tb);
   cudaFree(m->d_work);
+  cudaFree(m->d_ready);
+  for (int k = 0; k < 3; ++k) {
+    if (m->s_aux[k]) cudaStreamDestroy(m->s_aux[k]);
+    if (m->ev_go[k]) cudaEventDestroy(m->ev_go[k]);
+    if (m->ev_aux[k]) cudaEventDestroy(m->ev_aux[k]);
+  }
   cudaFree(m->d_counters);
   cudaFree(m->d_sets);
   cudaFree(m->d_redo_flag);
@@ -935,7 +998,9 @@ float abg_mapper_last_kernel_ms(const abg_mapper *m) { return m ? m->last_ms : 0
 void abg_mapper_last_phase_ms(const abg_mapper *m, float out[3]) {
   for (int k = 0; k < 3; ++k) out[k] = m ? m->phase_ms[k] : 0.f;
 }
-uint32_t abg_mapper_launches_per_run(const abg_mapper *m) { return (m && m->cur_n) ? (m->split ? 3u : 1u) : 0u; }
+uint32_t abg_mapper_launches_per_run(const abg_mapper *m) {
+  return (m && m->cur_n) ? (m->split ? (m->overlap ? 4u : 3u) : 1u) : 0u;
+}
 uint32_t abg_mapper_chunk(const abg_mapper *m) { return m ? m->chunk : 0u; }
 
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out) {

@@ -133,6 +133,11 @@ struct KernelParams {
   const uint32_t *item_list; // map_reads_kernel only: map item_list[0 .. *n_items_ptr) instead of 0 .. n
   const unsigned int *n_items_ptr;
   uint32_t layout_kind;      // kLayoutFull / kLayoutSeed / kLayoutAlign: which regions the warp's shared memory holds
+  uint32_t slot_base;        // first per-warp scratch slot of this launch (kernels that run concurrently get disjoint slots)
+  // Overlapped launch: align_kernel runs next to seed_kernel and consumes pairs as their sets complete.
+  unsigned int *ready;       // [n]: stored sets of the item so far (seed_kernel increments, release); null = stream order
+  uint32_t ready_need;       // sets per item
+  uint32_t wait_ns;          // how long an align warp waits for an item before leaving it to the redo kernel
 };
 
 // ---- 64-bit view of se_element {int16 diffs; uint16 flags; uint32 pos} -------
@@ -206,7 +211,13 @@ __host__ __device__ __forceinline__ uint32_t tb_sm_words(uint32_t ml) { return (
 // needs no traceback words, no reference bytes and one candidate set, and spends the room on the staging
 // buffers of its asynchronous seed-context gathers; the alignment kernel needs no staging, log or planes.
 constexpr uint32_t kLayoutFull = 0, kLayoutSeed = 1, kLayoutAlign = 2;
-constexpr int kStages = 4;             // chunks of 32 seed-context records in flight per warp (cp.async groups)
+#ifndef ABG_STAGES
+#define ABG_STAGES 4
+#endif
+#ifndef ABG_STAGED
+#define ABG_STAGED 1
+#endif
+constexpr int kStages = ABG_STAGES;    // chunks of 32 seed-context records in flight per warp (cp.async groups)
 constexpr uint32_t kStageBytes = 32u * 32u + 2u * 32u * 4u;  // 32 records + {slot, sub} of their candidates
 
 struct WarpLayout {
@@ -290,7 +301,9 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   __device__ __forceinline__ uint32_t *log_meta() const { return log_pos() + kLogCap; }
   __device__ __forceinline__ unsigned char *stage(int k) const { return base_ptr + L.o_stage + (size_t)k * kStageBytes; }
   __device__ __forceinline__ uint32_t *elig(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_elig) + k * L.elig_words; }
-  __device__ __forceinline__ size_t slot() const { return (size_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); }
+  __device__ __forceinline__ size_t slot() const {
+    return (size_t)params().slot_base + (size_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  }
   __device__ __forceinline__ uint64_t *tb_gm(int s) const {
     const KernelParams &P = params();
     return P.tb + (slot() * 2 + s) * (size_t)P.tb_words * 32;
@@ -711,7 +724,7 @@ __device__ __forceinline__ void load_ctx(const uint4 *p, uint32_t (&w)[8]) {
 // Deep part of a compare chunk: index entries, 2-bit genome windows (staged, with early exit at the bound) and
 // the exact 4-bit compare for windows that hold N / IUPAC codes, for the candidates still `valid`.
 template <int KC, int NC0>
-__device__ __forceinline__ void compare_deep(const IndexDev &ix, const uint32_t *__restrict__ index3,
+__device__ __noinline__ void compare_deep(const IndexDev &ix, const uint32_t *__restrict__ index3,
                                              const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
                                              const uint32_t *mT, int n_words, int bound, const bool (&valid)[KC],
                                              const uint32_t (&slot)[KC], const uint32_t (&sub)[KC], int (&d)[KC],
@@ -808,7 +821,7 @@ __device__ __forceinline__ void compare_deep(const IndexDev &ix, const uint32_t 
 }
 
 template <int KC, int NC0>
-__device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
+__device__ __noinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
                                               const uint4 *__restrict__ ctx3,
                                               const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
                                               const uint32_t *mT, int n_words, int bound, uint32_t c0,
@@ -901,7 +914,7 @@ constexpr uint32_t kSubRec = 0x40000000u;    // its seed-context record was requ
 // `st`: lane l owns candidate c0 + l, finds its bucket by binary search over the lanes' inclusive bucket-size
 // sums, and copies its 32-byte record global -> shared without going through registers.  Always commits one
 // cp.async group (possibly empty) so that the caller's group accounting is uniform.
-__device__ __forceinline__ void stage_issue(const IndexDev &ix, const uint4 *__restrict__ ctx3, unsigned char *st,
+__device__ __noinline__ void stage_issue(const IndexDev &ix, const uint4 *__restrict__ ctx3, unsigned char *st,
                                             uint32_t c0, uint32_t total, uint32_t base_off, uint32_t incl,
                                             uint32_t tot, uint32_t n2, uint32_t s2, uint32_t s3, int lane) {
   uint32_t *meta = reinterpret_cast<uint32_t *>(st + 32u * 32u);
@@ -1182,9 +1195,9 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       bool stop = false;
       // Staged path: the records of up to kStages chunks are in flight (cp.async) while one chunk is compared
-      const bool staged = ix.ctx != nullptr && (ctx3 != nullptr || ix.n_ctx3 == 0);
+      const bool staged = ABG_STAGED != 0 && ix.ctx != nullptr && (ctx3 != nullptr || ix.n_ctx3 == 0);
       if (staged) {
-#pragma unroll
+#pragma unroll 1
         for (int sg = 0; sg < kStages; ++sg)
           stage_issue(ix, ctx3, W.stage(sg), 32u * sg, total, base_off, incl, tot, n2, s2, s3, lane);
       }
@@ -2029,7 +2042,9 @@ __device__ __forceinline__ void load_set(const Warp &W, int id, const uint64_t *
   __syncwarp();
   CandState *st = W.cs(id);
   const HeapRef v = heap_of(W, id);
-  const uint64_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
+  // __ldcg: the sets may have been written by seed_kernel on another SM while this kernel was already
+  // running (overlapped launch); a neighbouring item's 128-byte line in L1 could predate them.
+  const uint64_t w0 = __ldcg(src), w1 = __ldcg(src + 1), w2 = __ldcg(src + 2), w3 = __ldcg(src + 3);
   const int sz = (int)(uint32_t)w0;
   if (W.lane == 0) {
     st->sz = sz;
@@ -2040,7 +2055,7 @@ __device__ __forceinline__ void load_set(const Warp &W, int id, const uint64_t *
     st->is_pe = (int)(uint32_t)(w2 >> 32);
     st->best = w3;
   }
-  for (int i = W.lane; i < sz; i += 32) v.set(i, Hit(src[kSetStateWords + i]));
+  for (int i = W.lane; i < sz; i += 32) v.set(i, Hit(__ldcg(src + kSetStateWords + i)));
   __syncwarp();
 }
 
@@ -2223,6 +2238,25 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) map_reads_kernel(const
   flush_counters(W);
 }
 
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_cg(const unsigned int *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Publish one stored set of `item` (all lanes: their stores first, then one release increment)
+__device__ __forceinline__ void publish_set(const KernelParams &P, unsigned int item, int lane) {
+  if (P.ready == nullptr) return;
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicAdd(P.ready + item, 1u);
+}
+
 // Phase 2 of the two-phase launch: everything after seeding (sort/unique, banded alignment, mating, selection,
 // CIGARs) for the reads / pairs whose sets seed_kernel stored; flagged pairs are left to map_reads_kernel.
 template <int MINB>
@@ -2238,7 +2272,29 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) align_kernel(const __g
     if (lane == 0) item = atomicAdd(P.work_counter, 1u);
     item = __shfl_sync(FULL, item, 0);
     if (item >= P.n) break;
-    if (P.redo_flag[item] != 0) continue;
+    if (P.ready != nullptr) {
+      // overlapped launch: wait until seed_kernel has stored every set of this item (acquire)
+      unsigned int ok = 1;
+      if (lane == 0 && ld_acquire(P.ready + item) < P.ready_need) {
+        const unsigned long long t0 = global_ns();
+        for (;;) {
+          __nanosleep(256);
+          if (ld_acquire(P.ready + item) >= P.ready_need) break;
+          if (global_ns() - t0 > (unsigned long long)P.wait_ns) {
+            ok = 0;
+            break;
+          }
+        }
+      }
+      ok = __shfl_sync(FULL, ok, 0);
+      if (!ok) {
+        // The seeding of this item is not coming (its kernel is not resident, or extremely slow): leave the
+        // item to the redo kernel, which maps it from scratch after both kernels, and stop waiting here.
+        if (lane == 0 && atomicExch(P.redo_flag + item, 1u) == 0u) P.redo_list[atomicAdd(P.redo_count, 1u)] = item;
+        break;
+      }
+    }
+    if (ld_relaxed_cg(P.redo_flag + item) != 0) continue;
     map_one<true>(W, item);
   }
   flush_counters(W);
@@ -2277,7 +2333,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
       const uint32_t o0 = P.off[0][item], len = P.off[0][item + 1] - o0;
       if (lane == 0) S->len[0] = len;
       __syncwarp();
-      if (len == 0) continue;
+      if (len == 0) {  // skipped read: nothing stored, but the alignment kernel must not wait for it
+        publish_set(P, item, lane);
+        continue;
+      }
       load_end(W, 0, P.seq[0] + o0, len);
       reset_set(W, 0, 0, len);
       if (rpbat) {
@@ -2292,6 +2351,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
         process_seeds(0, 0, cv | RC);
       }
       store_set(W, 0, stored_set(P, item, 0), (int)P.set_slots);
+      publish_set(P, item, lane);
     }
     else {
       const unsigned int item = w / P.n_pass;
@@ -2311,6 +2371,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
         if (lane == 0 && atomicExch(P.redo_flag + item, 1u) == 0u) P.redo_list[atomicAdd(P.redo_count, 1u)] = item;
       }
       store_set(W, 2, stored_set(P, item, pass), (int)P.set_slots);
+      publish_set(P, item, lane);
     }
   }
   flush_counters(W);
