@@ -266,7 +266,8 @@ int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const 
   }
   // behind the seeding (stream order): every set is stored, nothing to wait for; takes the seeding's slots
   Q.ready = nullptr;
-  if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)m->grid_a, a_blocks), m->smem_a, Q, st))) return rc;
+  const int grid_a_main = overlap ? m->grid_s : m->grid_a;  // overlapped: exactly the slots the seeding kernel had
+  if ((rc = launch_one(m->kernel_a, (int)std::min<uint64_t>((uint64_t)grid_a_main, a_blocks), m->smem_a, Q, st))) return rc;
   if (overlap) ABG_CUDA(cudaStreamWaitEvent(st, m->ev_aux[s_idx], 0));
   if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[1], st));
   Q.work_counter = work;

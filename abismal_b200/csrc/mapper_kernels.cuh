@@ -217,6 +217,9 @@ constexpr uint32_t kLayoutFull = 0, kLayoutSeed = 1, kLayoutAlign = 2;
 #ifndef ABG_STAGED
 #define ABG_STAGED 1
 #endif
+#ifndef ABG_CPASYNC_CA
+#define ABG_CPASYNC_CA 1
+#endif
 constexpr int kStages = ABG_STAGES;    // chunks of 32 seed-context records in flight per warp (cp.async groups)
 constexpr uint32_t kStageBytes = 32u * 32u + 2u * 32u * 4u;  // 32 records + {slot, sub} of their candidates
 
@@ -724,7 +727,7 @@ __device__ __forceinline__ void load_ctx(const uint4 *p, uint32_t (&w)[8]) {
 // Deep part of a compare chunk: index entries, 2-bit genome windows (staged, with early exit at the bound) and
 // the exact 4-bit compare for windows that hold N / IUPAC codes, for the candidates still `valid`.
 template <int KC, int NC0>
-__device__ __noinline__ void compare_deep(const IndexDev &ix, const uint32_t *__restrict__ index3,
+__device__ __forceinline__ void compare_deep(const IndexDev &ix, const uint32_t *__restrict__ index3,
                                              const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
                                              const uint32_t *mT, int n_words, int bound, const bool (&valid)[KC],
                                              const uint32_t (&slot)[KC], const uint32_t (&sub)[KC], int (&d)[KC],
@@ -821,7 +824,7 @@ __device__ __noinline__ void compare_deep(const IndexDev &ix, const uint32_t *__
 }
 
 template <int KC, int NC0>
-__device__ __noinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
+__device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t *__restrict__ index3,
                                               const uint4 *__restrict__ ctx3,
                                               const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
                                               const uint32_t *mT, int n_words, int bound, uint32_t c0,
@@ -899,7 +902,12 @@ __device__ __noinline__ void compare_chunk(const IndexDev &ix, const uint32_t *_
 // ---- asynchronous seed-context gathers (cp.async into the warp's staging buffers) ------------------------
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+#if ABG_CPASYNC_CA
+  // .ca: the two 16-byte halves of a record meet in L1 (one 32-byte sector request to L2)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -955,23 +963,46 @@ __device__ __noinline__ void stage_issue(const IndexDev &ix, const uint4 *__rest
   cp_async_commit();
 }
 
+// Out-of-line deep compare of one candidate per lane, everything by value (survivors of the prefilter are rare;
+// keeping this out of the staged loop keeps the loop small, and by-value keeps its state in registers).
+struct Deep1 {
+  int d, pm;
+  uint32_t pos, n_entry, n_word;
+};
+__device__ __noinline__ Deep1 compare_deep_one(const uint32_t *__restrict__ index3, int n_words, int bound, bool valid_in,
+                                               uint32_t slot_in, uint32_t sub_in) {
+  const Warp W;
+  const bool valid[1] = {valid_in};
+  const uint32_t slot[1] = {slot_in}, sub[1] = {sub_in};
+  int d[1] = {0}, pm[1] = {1 << 30};
+  uint32_t the_pos[1] = {0u};
+  Deep1 r;
+  r.n_entry = 0;
+  r.n_word = 0;
+  compare_deep<1, 4>(params().ix, index3, W.masks(0), W.masks(1), W.masks(2), W.masks(3), n_words, bound, valid, slot, sub,
+                     d, pm, the_pos, r.n_entry, r.n_word);
+  r.d = d[0];
+  r.pm = pm[0];
+  r.pos = the_pos[0];
+  return r;
+}
+
 // Compare the chunk staged in `st` (its records have landed): seed-context prefilter from shared memory, then
 // the deep compare for what it could not reject.  Same results as compare_chunk<1, 4>.
-__device__ __forceinline__ void compare_staged(const IndexDev &ix, const uint32_t *__restrict__ index3,
-                                               const unsigned char *st, const uint32_t *mA, const uint32_t *mC,
-                                               const uint32_t *mG, const uint32_t *mT, int n_words, int bound, int lane,
-                                               int (&d)[1], int (&pm)[1], uint32_t (&the_pos)[1], uint32_t (&sub)[1],
-                                               uint32_t &n_entry, uint32_t &n_word) {
+__device__ __forceinline__ void compare_staged(const uint32_t *__restrict__ index3, const unsigned char *st,
+                                               const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
+                                               const uint32_t *mT, int n_words, int bound, int lane, int &d, int &pm,
+                                               uint32_t &the_pos, uint32_t &sub, uint32_t &n_entry, uint32_t &n_word) {
   const uint32_t *meta = reinterpret_cast<const uint32_t *>(st + 32u * 32u);
   const int n_bases = 16 * n_words;
   const uint32_t sub_m = meta[32 + lane];
-  uint32_t slot[1] = {meta[lane]};
-  bool valid[1] = {sub_m != ~0u};
-  sub[0] = sub_m & ~kSubRec;
-  d[0] = 0;
-  pm[0] = 1 << 30;
-  the_pos[0] = 0;
-  if (valid[0] && (sub_m & kSubRec) != 0u) {
+  const uint32_t slot = meta[lane];
+  bool valid = sub_m != ~0u;
+  sub = sub_m & ~kSubRec;
+  d = 0;
+  pm = 1 << 30;
+  the_pos = 0;
+  if (valid && (sub_m & kSubRec) != 0u) {
     const uint4 *rec = reinterpret_cast<const uint4 *>(st + 32u * (uint32_t)lane);
     const uint4 x = rec[0], y = rec[1];
     const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
@@ -992,13 +1023,18 @@ __device__ __forceinline__ void compare_staged(const IndexDev &ix, const uint32_
       }
     }
     if (lb > bound) {
-      valid[0] = false;
+      valid = false;
       n_entry += 1;
       n_word += 4;
     }
   }
-  if (!__any_sync(FULL, valid[0])) return;
-  compare_deep<1, 4>(ix, index3, mA, mC, mG, mT, n_words, bound, valid, slot, sub, d, pm, the_pos, n_entry, n_word);
+  if (!__any_sync(FULL, valid)) return;
+  const Deep1 r = compare_deep_one(index3, n_words, bound, valid, slot, sub);
+  d = r.d;
+  pm = r.pm;
+  the_pos = r.pos;
+  n_entry += r.n_entry;
+  n_word += r.n_word;
 }
 
 // Ordered replay of the survivors of one compare round against candidate set `set_id`
@@ -1222,16 +1258,15 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
         uint32_t sub[kCand];
         if (staged) {
           cp_async_wait<kStages - 1>();  // the oldest of the kStages groups in flight = this chunk
-          int d1[1], pm1[1];
-          uint32_t pos1[1], sub1[1];
-          compare_staged(ix, index3, W.stage(sg), mA, mC, mG, mT, n_words, bound, lane, d1, pm1, pos1, sub1, c_entry,
-                         c_word);
+          int d1, pm1;
+          uint32_t pos1, sub1;
+          compare_staged(index3, W.stage(sg), mA, mC, mG, mT, n_words, bound, lane, d1, pm1, pos1, sub1, c_entry, c_word);
 #pragma unroll
           for (int k = 0; k < kCand; ++k) {
-            d[k] = k == 0 ? d1[0] : 0;
-            pm[k] = k == 0 ? pm1[0] : (1 << 30);
-            the_pos[k] = k == 0 ? pos1[0] : 0u;
-            sub[k] = k == 0 ? sub1[0] : 0u;
+            d[k] = k == 0 ? d1 : 0;
+            pm[k] = k == 0 ? pm1 : (1 << 30);
+            the_pos[k] = k == 0 ? pos1 : 0u;
+            sub[k] = k == 0 ? sub1 : 0u;
           }
           // refill the buffer just consumed with the chunk kStages ahead
           stage_issue(ix, ctx3, W.stage(sg), c0 + 32u * kStages, total, base_off, incl, tot, n2, s2, s3, lane);
@@ -2238,9 +2273,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) map_reads_kernel(const
   flush_counters(W);
 }
 
+// Poll with a relaxed GPU-scope load: ld.acquire would add a CCTL.IVALL (the whole L1 of the SM invalidated) to
+// every poll, which wrecks the seeding kernel running on the same SM.  Everything read after the flag is read
+// with L1-bypassing loads (__ldcg), issued after the branch on the flag resolves.
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned int ld_relaxed_cg(const unsigned int *p) { return __ldcg(p); }
@@ -2278,7 +2316,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) align_kernel(const __g
       if (lane == 0 && ld_acquire(P.ready + item) < P.ready_need) {
         const unsigned long long t0 = global_ns();
         for (;;) {
-          __nanosleep(256);
+          __nanosleep(1000);
           if (ld_acquire(P.ready + item) >= P.ready_need) break;
           if (global_ns() - t0 > (unsigned long long)P.wait_ns) {
             ok = 0;
