@@ -685,6 +685,11 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
                 : m->minb == 4 ? (const void *)ab2dev::align_kernel<4>
                                : (const void *)ab2dev::align_kernel<3>;
     int per_s = 0, per_a = 0;
+    // one shared-memory carve-out for every kernel of the path: CTAs of kernels that ask for different
+    // carve-outs cannot share an SM (the overlapped launch co-schedules seed_kernel and align_kernel)
+    for (const void *k : {m->kernel, m->kernel_s, m->kernel_a})
+      if (cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        (void)cudaGetLastError();
     ABG_M(cudaFuncSetAttribute(m->kernel_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_s));
     ABG_M(cudaFuncSetAttribute(m->kernel_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_a));
     ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_s, m->kernel_s, ab2dev::kThreadsPerBlock, m->smem_s));
@@ -696,11 +701,15 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     m->grid_s = n_sm * per_s;
     m->grid_a = n_sm * per_a;
     {
-      // overlapped launch (default): ABISMAL_B200_OVERLAP=0 runs seed_kernel -> align_kernel back to back.
+      // overlapped launch: ABISMAL_B200_OVERLAP=1 (default: seed_kernel -> align_kernel back to back).
       // ABISMAL_B200_SEED_BLOCKS / ABISMAL_B200_AUX_BLOCKS: CTAs per SM of seed_kernel and of the align_kernel
       // launch that runs next to it (together they must fit on an SM: registers and shared memory).
       const char *e = std::getenv("ABISMAL_B200_OVERLAP");
-      m->overlap = !(e && std::atoi(e) == 0) && per_s >= 2;
+      m->overlap = (e && std::atoi(e) != 0) && per_s >= 2;
+      if (!m->overlap) {
+        const char *es = std::getenv("ABISMAL_B200_SEED_BLOCKS");  // tuning: fewer seeding CTAs per SM
+        if (es && std::atoi(es) >= 1) m->grid_s = n_sm * std::min(per_s, std::atoi(es));
+      }
       if (m->overlap) {
         const char *es = std::getenv("ABISMAL_B200_SEED_BLOCKS"), *ea = std::getenv("ABISMAL_B200_AUX_BLOCKS");
         const int sb = std::max(1, std::min(per_s, es ? std::atoi(es) : per_s - 1));

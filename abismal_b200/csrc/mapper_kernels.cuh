@@ -214,8 +214,11 @@ constexpr uint32_t kLayoutFull = 0, kLayoutSeed = 1, kLayoutAlign = 2;
 #ifndef ABG_STAGES
 #define ABG_STAGES 4
 #endif
+// Measured on B200 (profiles/README.md): staging the records through shared memory with cp.async is SLOWER than
+// plain register gathers (seed_kernel 131-136 ms vs 105 ms per 2^20 pairs) -- the kernel is bound by the rate of
+// random DRAM sectors, not by loads in flight per warp -- so the staged path is compiled out by default.
 #ifndef ABG_STAGED
-#define ABG_STAGED 1
+#define ABG_STAGED 0
 #endif
 #ifndef ABG_CPASYNC_CA
 #define ABG_CPASYNC_CA 1
@@ -234,7 +237,7 @@ __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool pai
   const bool seed = kind != kLayoutAlign, aln = kind != kLayoutSeed;
   uint32_t o = 0;
   L.o_stage = o;
-  if (seed) o += (uint32_t)kStages * kStageBytes;  // first: 16-byte aligned cp.async destinations
+  if (seed && ABG_STAGED) o += (uint32_t)kStages * kStageBytes;  // first: 16-byte aligned cp.async destinations
   L.o_packed = o;
   o += ml / 2;                               // packed read, ml/16 u64
   L.o_se = o;
