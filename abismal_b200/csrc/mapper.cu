@@ -17,7 +17,8 @@
 
 namespace {
 
-constexpr int kDefaultMinB = 3;
+constexpr int kDefaultMinB = 4;       // measured: 4 CTAs/SM (<= 64 registers) beats 3 (<= 80) on both kernels
+constexpr int kDefaultMinBSeed = 4;
 
 thread_local std::string g_err;
 
@@ -678,9 +679,17 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   }
   int grid_max = m->grid;
   if (m->split) {
-    m->kernel_s = m->minb == 2 ? (const void *)ab2dev::seed_kernel<2>
-                : m->minb == 4 ? (const void *)ab2dev::seed_kernel<4>
-                               : (const void *)ab2dev::seed_kernel<3>;
+    int minb_s = m->minb == kDefaultMinB ? kDefaultMinBSeed : m->minb;
+    {
+      const char *e = std::getenv("ABISMAL_B200_MINB_SEED");  // tuning: the seeding kernel's own register bound
+      const int v = e ? std::atoi(e) : 0;
+      if (v >= 2 && v <= 6) minb_s = v;
+    }
+    m->kernel_s = minb_s == 2 ? (const void *)ab2dev::seed_kernel<2>
+                : minb_s == 3 ? (const void *)ab2dev::seed_kernel<3>
+                : minb_s == 5 ? (const void *)ab2dev::seed_kernel<5>
+                : minb_s == 6 ? (const void *)ab2dev::seed_kernel<6>
+                              : (const void *)ab2dev::seed_kernel<4>;
     m->kernel_a = m->minb == 2 ? (const void *)ab2dev::align_kernel<2>
                 : m->minb == 4 ? (const void *)ab2dev::align_kernel<4>
                                : (const void *)ab2dev::align_kernel<3>;
