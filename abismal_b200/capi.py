@@ -30,7 +30,7 @@ class abg_index_view(C.Structure):
         ("counter_t", C.c_void_p), ("counter_a", C.c_void_p), ("counter_size_three", C.c_uint64),
         ("index", C.c_void_p), ("index_size", C.c_uint64),
         ("index_t", C.c_void_p), ("index_a", C.c_void_p), ("index_size_three", C.c_uint64),
-        ("max_candidates", C.c_uint32), ("reserved", C.c_uint32),
+        ("max_candidates", C.c_uint32), ("window_size", C.c_uint32),
     ]
 
 
@@ -167,6 +167,7 @@ def make_view(ix):
     v.index_a = _ptr(ix.index_a)
     v.index_size_three = ix.index_size_three
     v.max_candidates = ix.max_candidates
+    v.window_size = getattr(ix, "window_size", 20)
     return v
 
 

@@ -133,16 +133,17 @@ void prepare_genome(const std::string &path, PreparedGenome &out) {
 }
 
 #ifndef ABISMAL_ENGINE_ORACLE
-void build_index(PreparedGenome &&g, int device, IndexFile &out) {
+void build_index(PreparedGenome &&g, int device, IndexFile &out, uint32_t window_size) {
   abg_built_index b;
   std::memset(&b, 0, sizeof b);
-  if (abg_build_index(g.words.data(), g.genome_size, g.exclude.data(), static_cast<uint32_t>(g.exclude.size() / 2),
-                      device, &b) != 0)
+  if (abg_build_index_w(g.words.data(), g.genome_size, g.exclude.data(), static_cast<uint32_t>(g.exclude.size() / 2),
+                        window_size, device, &b) != 0)
     throw std::runtime_error(std::string("index construction failed: ") + abg_index_build_last_error());
   out.cl = std::move(g.cl);
   out.genome = std::move(g.words);
   out.genome.push_back(0);  // the look-ahead word IndexFile::read also appends
   out.max_candidates = b.max_candidates;
+  out.window_size = window_size;
   out.counter_size = b.counter_size;
   out.counter_size_three = b.counter_size_three;
   out.index_size = b.index_size;
@@ -166,7 +167,7 @@ void write_index_file(const IndexFile &ix, const std::string &path) {
   const auto put64 = [&](uint64_t v) { put(&v, 8); };
   put("AbismalIndex", 12);
   put32(25);   // seed::key_weight
-  put32(20);   // seed::window_size
+  put32(ix.window_size);  // seed::window_size
   put32(256);  // seed::n_sorting_positions
   put32(static_cast<uint32_t>(ix.cl.names.size()));
   for (const std::string &nm : ix.cl.names) {

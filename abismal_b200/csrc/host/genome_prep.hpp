@@ -26,13 +26,14 @@ struct PreparedGenome {
 void prepare_genome(const std::string &fasta_path, PreparedGenome &out);
 
 // Builds the index arrays on CUDA device `device` and fills `out` as if it had been read from a file.
-void build_index(PreparedGenome &&g, int device, IndexFile &out);
+// window_size: seed::window_size, 20 or 12 (--enable-short)
+void build_index(PreparedGenome &&g, int device, IndexFile &out, uint32_t window_size = 20);
 
 void write_index_file(const IndexFile &ix, const std::string &path);
 
 }  // namespace ab2
 
 // defined in map_main.cpp's translation unit for both engines
-void build_index_from_fasta(const std::string &fasta_path, int device, ab2::IndexFile &out);
+void build_index_from_fasta(const std::string &fasta_path, int device, ab2::IndexFile &out, uint32_t window_size = 20);
 
 #endif

@@ -63,12 +63,14 @@ void IndexFile::read(const std::string &path, bool map_file) {
     throw std::runtime_error("index file format problem: " + path);
 
   // seed::read (src/AbismalIndex.cpp:988-1024)
-  uint32_t key_weight = 0, window_size = 0, n_sorting = 0;
+  uint32_t key_weight = 0, n_sorting = 0;
   read_pod(in, key_weight, "failed to read seed data");
   if (key_weight != 25u)
     throw std::runtime_error("inconsistent k-mer size. Expected: 25, got: " + std::to_string(key_weight));
   read_pod(in, window_size, "failed to read seed data");
-  if (window_size != 20u)
+  // the reference accepts the one window it was configured with (20, or 12 with --enable-short); this
+  // reader takes either and the mapper follows the file
+  if (window_size != 20u && window_size != 12u)
     throw std::runtime_error("inconsistent window size size. Expected: 20, got: " +
                              std::to_string(window_size));
   read_pod(in, n_sorting, "failed to read seed data");
@@ -130,6 +132,7 @@ void IndexFile::read(const std::string &path, bool map_file) {
     mapped_.index_size = index_size;
     mapped_.index_size_three = index_size_three;
     mapped_.max_candidates = max_candidates;
+    mapped_.window_size = window_size;
     return;
   }
   // one spare zero word: the look-ahead word of a compare at the very end
@@ -170,6 +173,7 @@ abg_index_view IndexFile::view() const {
   v.index_a = index_a.data();
   v.index_size_three = index_size_three;
   v.max_candidates = max_candidates;
+  v.window_size = window_size;
   return v;
 }
 

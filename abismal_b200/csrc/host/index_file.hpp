@@ -25,6 +25,7 @@ struct ChromLookup {
 struct IndexFile {
   ChromLookup cl;
   uint32_t max_candidates = 100;
+  uint32_t window_size = 20;  // seed::window_size of the file: 20, or 12 (reference configured with --enable-short)
   uint64_t counter_size = 0, counter_size_three = 0, index_size = 0, index_size_three = 0;
   std::vector<uint64_t> genome;
   std::vector<uint32_t> counter, counter_t, counter_a, index, index_t, index_a;

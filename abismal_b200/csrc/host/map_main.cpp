@@ -198,6 +198,8 @@ public:
     : cfg_(cfg), index_(index), out_(out), rl1_(fq1), n_items_(4 + 2 * cfg.devices.size() * cfg.workers_per_gpu),
       free_(n_items_), q12_(n_items_), to_map_(n_items_), to_out_(n_items_), pool_(cfg.n_threads) {
     if (cfg.paired_end) rl2_.reset(new ab2::FastqReader(fq2));
+    rl1_.set_window_size(index.window_size);
+    if (rl2_) rl2_->set_window_size(index.window_size);
     items_.resize(n_items_);
     for (WorkItem &it : items_) free_.push(&it);
   }
@@ -424,6 +426,7 @@ int map_main(int argc, char *argv[]) {
     uint32_t batch_size = 1u << 18, device = 0, n_gpus = 1, gpu_workers = 2;
     double valid_frac = 0.1;
     std::string index_file, genome_file, outfile, stats_outfile;
+    bool enable_short = false;
 
     ab2::Options opt;
     opt.add("help", '?', "print this help message", false, help);
@@ -449,6 +452,7 @@ int map_main(int argc, char *argv[]) {
     opt.add("device", '\0', "first CUDA device ordinal", false, device);
     opt.add("gpus", '\0', "number of GPUs to shard batches over (index replicated)", false, n_gpus);
     opt.add("gpu-workers", '\0', "mapper workers (streams) per GPU", false, gpu_workers);
+    opt.add("enable-short", '\0', "with -g: index with window 12 (the reference's --enable-short build)", false, enable_short);
     const std::vector<std::string> leftover = opt.parse(argc, argv);
 
     const std::string usage = opt.help_message(argv[0], "<reads-fq1> [<reads-fq2>]");
@@ -519,7 +523,7 @@ int map_main(int argc, char *argv[]) {
     else {
       // abismal.cpp:2439-2446: index the genome on the fly
       if (verbose) log_msg("indexing genome " + genome_file);
-      build_index_from_fasta(genome_file, static_cast<int>(device), index);
+      build_index_from_fasta(genome_file, static_cast<int>(device), index, enable_short ? 12u : 20u);
       if (verbose)
         log_msg("indexing time: " +
                 fmt_secs(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()));
@@ -610,7 +614,7 @@ int map_main(int argc, char *argv[]) {
 // `abismal-b200 idx`: the reference's abismalidx (src/abismalidx.cpp:30-120) with the index built on the GPU.
 int idx_main(int argc, char *argv[]) {
   try {
-    bool verbose = false, help = false, about = false;
+    bool verbose = false, help = false, about = false, enable_short = false;
     uint32_t n_threads = 1, device = 0;
     std::string target_regions_file;
     ab2::Options opt;
@@ -620,6 +624,7 @@ int idx_main(int argc, char *argv[]) {
     opt.add("threads", 't', "number of threads", false, n_threads);
     opt.add("verbose", 'v', "print more run info", false, verbose);
     opt.add("device", '\0', "CUDA device ordinal", false, device);
+    opt.add("enable-short", '\0', "window 12 instead of 20 (the reference's --enable-short build)", false, enable_short);
     const std::vector<std::string> leftover = opt.parse(argc, argv);
     const std::string usage = opt.help_message(argv[0], "<genome-fasta> <abismal-index-file>");
     if (argc == 1 || help || about) {
@@ -635,7 +640,7 @@ int idx_main(int argc, char *argv[]) {
     const auto t0 = std::chrono::steady_clock::now();
     if (verbose) log_msg("indexing genome " + leftover.front());
     ab2::IndexFile index;
-    build_index_from_fasta(leftover.front(), static_cast<int>(device), index);
+    build_index_from_fasta(leftover.front(), static_cast<int>(device), index, enable_short ? 12u : 20u);
     if (verbose) log_msg("writing index file " + leftover.back());
     ab2::write_index_file(index, leftover.back());
     if (verbose)
@@ -651,16 +656,17 @@ int idx_main(int argc, char *argv[]) {
 
 }  // namespace
 
-void build_index_from_fasta(const std::string &fasta_path, int device, ab2::IndexFile &out) {
+void build_index_from_fasta(const std::string &fasta_path, int device, ab2::IndexFile &out, uint32_t window_size) {
 #ifdef ABISMAL_ENGINE_ORACLE
   (void)fasta_path;
   (void)device;
   (void)out;
+  (void)window_size;
   throw std::runtime_error("index construction is not part of the oracle test tool; pass an index with -i");
 #else
   ab2::PreparedGenome g;
   ab2::prepare_genome(fasta_path, g);
-  ab2::build_index(std::move(g), device, out);
+  ab2::build_index(std::move(g), device, out, window_size);
 #endif
 }
 

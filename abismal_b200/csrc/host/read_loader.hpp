@@ -27,7 +27,9 @@ struct ReadBatch {
 
 class FastqReader {
 public:
-  static constexpr uint32_t min_read_length = 25 + 20 - 1;  // abismal.cpp:212-213
+  // key_weight + window_size - 1 (abismal.cpp:212-213): 44, or 36 for an index with window 12
+  uint32_t min_read_length = 25 + 20 - 1;
+  void set_window_size(uint32_t w) { min_read_length = 25 + w - 1; }
   static constexpr size_t padding_size = 32767;              // seed::padding_size
 
   explicit FastqReader(const std::string &filename);

@@ -31,7 +31,7 @@ namespace {
 
 thread_local std::string g_ierr;
 
-constexpr uint32_t kKeyW = 25, kKeyW3 = 16, kWindow = 20, kSortPos = 256;
+constexpr uint32_t kKeyW = 25, kKeyW3 = 16, kSortPos = 256;  // seed::window_size (20, or 12) is a run-time argument
 constexpr uint32_t kMask25 = (1u << 25) - 1u;
 constexpr uint32_t kPow3 = 43046721u;
 constexpr uint64_t kBlockSize = 1000000ull;
@@ -142,7 +142,7 @@ __global__ void pos_pass_kernel(int mode, const uint64_t *g, uint64_t lim2, uint
 // compress_dp (src/AbismalIndex.cpp:726-855): one thread per block.
 __global__ void dp_kernel(const uint64_t *g, const uint64_t *blocks, uint32_t n_blocks, const uint32_t *c2,
                           const uint32_t *ct, const uint32_t *ca, const uint8_t *is_two, uint32_t *prev_arr,
-                          uint8_t *keep) {
+                          uint8_t *keep, uint32_t kWindow) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
   const uint64_t block_start = blocks[2 * b];
@@ -434,8 +434,15 @@ void abg_built_index_free(abg_built_index *b) {
 
 int abg_build_index(const uint64_t *genome, uint64_t genome_size, const uint64_t *exclude, uint32_t n_exclude,
                     int device, abg_built_index *out) {
+  return abg_build_index_w(genome, genome_size, exclude, n_exclude, 20u, device, out);
+}
+
+int abg_build_index_w(const uint64_t *genome, uint64_t genome_size, const uint64_t *exclude, uint32_t n_exclude,
+                      uint32_t window_size, int device, abg_built_index *out) {
   if (!genome || !exclude || !out || n_exclude == 0 || genome_size < 2 * 32767ull)
     return ifail(ABG_ERR_INVALID, "abg_build_index: bad argument");
+  if (window_size != 12u && window_size != 20u)
+    return ifail(ABG_ERR_INVALID, "abg_build_index: window_size must be 20, or 12 (--enable-short)");
   if (genome_size >= (1ull << 32)) return ifail(ABG_ERR_INVALID, "abg_build_index: genome must be < 2^32 bases");
   std::memset(out, 0, sizeof *out);
   if (cudaSetDevice(device) != cudaSuccess) return ifail(ABG_ERR_CUDA, "abg_build_index: cannot select device");
@@ -489,7 +496,7 @@ int abg_build_index(const uint64_t *genome, uint64_t genome_size, const uint64_t
     IB_CUDA(cudaMalloc(&d_blocks, blocks.size() * 8));
     IB_CUDA(cudaMemcpy(d_blocks, blocks.data(), blocks.size() * 8, cudaMemcpyHostToDevice));
     IB_CUDA(cudaMalloc(&d_prev, (genome_size + 1) * 4));
-    dp_kernel<<<(n_blocks + 31) / 32, 32>>>(d_g, d_blocks, n_blocks, d_c2, d_ct, d_ca, d_is_two, d_prev, d_keep);
+    dp_kernel<<<(n_blocks + 31) / 32, 32>>>(d_g, d_blocks, n_blocks, d_c2, d_ct, d_ca, d_is_two, d_prev, d_keep, window_size);
     IB_CUDA(cudaDeviceSynchronize());
     cudaFree(d_prev);
     d_prev = nullptr;

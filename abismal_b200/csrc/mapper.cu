@@ -163,8 +163,8 @@ int stage_offsets(abg_mapper *m, const uint32_t *off, uint32_t c0, uint32_t c1, 
   for (uint32_t i = c0; i < c1; ++i) {
     const uint32_t len = off[i + 1] - off[i];
     if (len > m->max_read_len) return fail(ABG_ERR_TOO_LONG, "abg_map_batch: read longer than max_read_len");
-    if (len != 0 && len < 44)
-      return fail(ABG_ERR_INVALID, "abg_map_batch: reads shorter than 44 bases must be passed as empty");
+    if (len != 0 && len < m->idx->dev.window_size + 24u)  // ReadLoader::min_read_length, abismal.cpp:212-213
+      return fail(ABG_ERR_INVALID, "abg_map_batch: reads shorter than 44 bases (36 with window 12) must be passed as empty");
     dst[i] = off[i] - base;
   }
   dst[c1] = off[c1] - base;
@@ -203,6 +203,7 @@ void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint
   P.max_dist = m->params.max_dist;
   P.max_candidates = m->params.max_candidates ? m->params.max_candidates : m->idx->dev.max_candidates;
   P.valid_frac = m->params.valid_frac;
+  P.window_size = m->idx->dev.window_size;
   P.ml = m->ml;
   P.pe_overflow = m->d_pe_overflow;
   P.mem_scr = m->d_mem_scr;
@@ -404,6 +405,8 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
     return fail(ABG_ERR_INVALID, "abg_index_create: null argument");
   if (v->counter_size != (1ull << 25) || v->counter_size_three != 43046721ull)
     return fail(ABG_ERR_INVALID, "abg_index_create: unexpected counter sizes");
+  if (v->window_size != 0u && v->window_size != 12u && v->window_size != 20u)
+    return fail(ABG_ERR_INVALID, "abg_index_create: window_size must be 20, or 12 (--enable-short)");
   int n_dev = 0;
   ABG_CUDA(cudaGetDeviceCount(&n_dev));
   if (device < 0 || device >= n_dev) return fail(ABG_ERR_CUDA, "abg_index_create: no such CUDA device");
@@ -543,6 +546,7 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
   ix->dev.index_t = ix->index_t;
   ix->dev.index_a = ix->index_a;
   ix->dev.max_candidates = v->max_candidates;
+  ix->dev.window_size = v->window_size ? v->window_size : 20u;
   *out = ix;
   return ABG_OK;
 }

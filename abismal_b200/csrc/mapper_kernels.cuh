@@ -95,6 +95,7 @@ struct IndexDev {
   // costs no HBM access.  A block with a bucket of 255 or more entries has base ~0u: probe the full table.
   const uint4 *cc;
   uint32_t max_candidates;
+  uint32_t window_size;  // seed::window_size the index was built with (20, or 12)
 };
 constexpr int kCtxArrays = 4;
 constexpr uint32_t kCcKeys = 28;
@@ -132,6 +133,7 @@ struct KernelParams {
   unsigned int *redo_count;
   const uint32_t *item_list; // map_reads_kernel only: map item_list[0 .. *n_items_ptr) instead of 0 .. n
   const unsigned int *n_items_ptr;
+  uint32_t window_size;      // seed::window_size of the index: 20, or 12 (--enable-short)
   uint32_t layout_kind;      // kLayoutFull / kLayoutSeed / kLayoutAlign: which regions the warp's shared memory holds
   uint32_t slot_base;        // first per-warp scratch slot of this launch (kernels that run concurrently get disjoint slots)
   // Overlapped launch: align_kernel runs next to seed_kernel and consumes pairs as their sets complete.
@@ -168,10 +170,11 @@ __device__ __forceinline__ int frac_of(double f, uint32_t x) {  // static_cast<s
   return (int)(int16_t)__double2int_rz(__dmul_rn(f, (double)x));
 }
 __device__ __forceinline__ int invalid_hit_diffs(uint32_t readlen) { return frac_of(0.4, readlen); }
-__device__ __forceinline__ bool valid_len(uint32_t aln_len, uint32_t readlen) {  // abismal.cpp:307-314
+// min_len = ReadLoader::min_read_length = key_weight + window_size - 1 (abismal.cpp:212-213): 44, or 36
+__device__ __forceinline__ bool valid_len(uint32_t aln_len, uint32_t readlen, uint32_t min_len) {  // abismal.cpp:307-314
   const double min_aln_frac = __dsub_rn(1.0, 0.4);
   const uint32_t a = (uint32_t)__double2uint_rz(__dmul_rn(min_aln_frac, (double)readlen));
-  return aln_len >= (a > 44u ? a : 44u);
+  return aln_len >= (a > min_len ? a : min_len);
 }
 
 // ---- shared memory ----------------------------------------------------------------
@@ -1156,8 +1159,8 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
   uint32_t *log_pos = W.log_pos(), *log_meta = W.log_meta();
   uint32_t *elig2 = W.elig(0), *elig3 = W.elig(1);
 
-  const uint32_t specific_len = min(readlen - 20u, readlen >> 1);
-  const uint32_t specific_lim = max(20u, readlen >> 1);
+  const uint32_t specific_len = min(readlen - P.window_size, readlen >> 1);  // seed::window_size, abismal.cpp:1302-1305
+  const uint32_t specific_lim = max(P.window_size, readlen >> 1);
   const uint32_t lim_two = readlen - 25u + 1u;
   int n_log = 0;
   bool log_ok = readlen <= (uint32_t)kLogMaxLen;
@@ -1761,7 +1764,8 @@ __device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uin
     *cg_ref_len = cg.ref_len;
     best.set_pos(pos);
     best.set_diffs(nm);
-    if (!(valid_len(len, (uint32_t)readlen) && nm <= frac_of(cutoff, (uint32_t)readlen))) best.reset();
+    if (!(valid_len(len, (uint32_t)readlen, params().window_size + 24u) && nm <= frac_of(cutoff, (uint32_t)readlen)))
+      best.reset();
   }
   else best.reset();
   return best.w;
@@ -2215,7 +2219,8 @@ __device__ __forceinline__ void map_one(const Warp &W, unsigned int item) {
     }
     {  // valid_pair (abismal.cpp:624-631)
       const uint32_t al1 = cg[0].ref_len, al2 = cg[1].ref_len;
-      const bool ok = valid_len(al1, len0) && valid_len(al2, len1) &&
+      const uint32_t min_len = P.window_size + 24u;
+      const bool ok = valid_len(al1, len0, min_len) && valid_len(al2, len1, min_len) &&
                       best.diffs() <= frac_of(P.valid_frac, al1 + al2);
       if (!ok) best.reset();
     }

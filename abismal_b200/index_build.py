@@ -124,17 +124,18 @@ def prepare_fasta(path):
 class BuiltIndex:
     """Result of abg_build_index as numpy arrays + everything IndexFile exposes."""
 
-    def __init__(self, prepared, device=0):
+    def __init__(self, prepared, device=0, window_size=20):
         lib = capi.load_library()
+        self.window_size = window_size
         lib.abg_index_build_last_error.restype = C.c_char_p
-        lib.abg_build_index.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int,
-                                        C.POINTER(abg_built_index)]
+        lib.abg_build_index_w.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                          C.POINTER(abg_built_index)]
         lib.abg_built_index_free.argtypes = [C.POINTER(abg_built_index)]
         lib.abg_built_index_free.restype = None
         out = abg_built_index()
         ex = np.ascontiguousarray(prepared.exclude, "<u8")
-        rc = lib.abg_build_index(prepared.words.ctypes.data_as(C.c_void_p), prepared.genome_size,
-                                 ex.ctypes.data_as(C.c_void_p), ex.shape[0], device, C.byref(out))
+        rc = lib.abg_build_index_w(prepared.words.ctypes.data_as(C.c_void_p), prepared.genome_size,
+                                   ex.ctypes.data_as(C.c_void_p), ex.shape[0], window_size, device, C.byref(out))
         if rc != 0:
             raise capi.AbgError(lib.abg_index_build_last_error().decode())
         try:
@@ -167,7 +168,7 @@ class BuiltIndex:
         n_words = (self.genome_size + 15) // 16
         with open(path, "wb") as f:
             f.write(b"AbismalIndex")
-            f.write(struct.pack("<3I", 25, 20, 256))
+            f.write(struct.pack("<3I", 25, self.window_size, 256))
             f.write(struct.pack("<I", len(self.names)))
             for nm in self.names:
                 b = nm.encode()
@@ -186,7 +187,7 @@ class BuiltIndex:
             self.index_a[:self.index_size_three].tofile(f)
 
 
-def build_index_file(fasta_path, index_path, device=0):
-    built = BuiltIndex(prepare_fasta(fasta_path), device)
+def build_index_file(fasta_path, index_path, device=0, window_size=20):
+    built = BuiltIndex(prepare_fasta(fasta_path), device, window_size)
     built.write(index_path)
     return built

@@ -13,8 +13,10 @@ class IndexFile:
             if f.read(12) != b"AbismalIndex":
                 raise ValueError("index file format problem: " + path)
             kw, ws, nsp = struct.unpack("<3I", f.read(12))
-            if (kw, ws, nsp) != (25, 20, 256):
+            # window_size 12 = an index of the reference configured with --enable-short (AbismalIndex.hpp:73-77)
+            if (kw, nsp) != (25, 256) or ws not in (12, 20):
                 raise ValueError("inconsistent seed parameters in " + path)
+            self.window_size = ws
             (n_chroms,) = struct.unpack("<I", f.read(4))
             self.names = []
             for _ in range(n_chroms):

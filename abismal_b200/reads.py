@@ -45,8 +45,8 @@ class ReadBatch:
         return int(self.off[-1]) + self.off.nbytes
 
 
-def trim_read(line):
-    if sum(1 for c in line if c != "N") < MIN_READ_LENGTH:
+def trim_read(line, min_read_length=MIN_READ_LENGTH):
+    if sum(1 for c in line if c != "N") < min_read_length:
         return ""
     line = line.rstrip("N")
     for i, c in enumerate(line):
@@ -55,7 +55,7 @@ def trim_read(line):
     raise ValueError("read without A/C/G/T")
 
 
-def load_fastq(path, limit=None):
+def load_fastq(path, limit=None, min_read_length=MIN_READ_LENGTH):
     opener = gzip.open if path.endswith(".gz") else open
     names, seqs = [], []
     with opener(path, "rt") as f:
@@ -65,7 +65,7 @@ def load_fastq(path, limit=None):
                 ws = min([p for p in (line.find(" "), line.find("\t")) if p >= 0], default=len(line))
                 names.append(line[1:ws])
             elif k % 4 == 1:
-                seqs.append(trim_read(line))
+                seqs.append(trim_read(line, min_read_length))
                 if limit is not None and len(seqs) >= limit:
                     break
     return ReadBatch(names[:len(seqs)], seqs)

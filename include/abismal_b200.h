@@ -74,7 +74,8 @@ typedef struct abg_index_view {
   const uint32_t *index_a;
   uint64_t index_size_three;
   uint32_t max_candidates;  /* value stored in the index file (default 100) */
-  uint32_t reserved;
+  uint32_t window_size;     /* seed::window_size of the index file (AbismalIndex.hpp:73-77): 20, or 12 for
+                             * an index built by a reference configured with --enable-short; 0 means 20 */
 } abg_index_view;
 
 /* Per-run knobs that the reference keeps in globals mutated by the CLI
@@ -91,7 +92,7 @@ typedef struct abg_params {
 
 /* One batch of reads as the reference's ReadLoader (abismal.cpp:164-201)
  * leaves them: upper-case sequence, Ns trimmed from both ends, reads with
- * fewer than 44 non-N bases emptied (length 0).  Read i of end e occupies
+ * fewer than 25 + window_size - 1 (= 44, or 36 with window 12) non-N bases emptied (length 0).  Read i of end e occupies
  * seq_e[off_e[i] .. off_e[i+1]).  seq2/off2 are NULL for single-end. */
 typedef struct abg_batch {
   uint32_t n;           /* reads (SE) or pairs (PE)                          */

@@ -37,6 +37,10 @@ const char *abg_index_build_last_error(void);
  * than 256 bases, ascending (AbismalIndex::exclude), paddings included. */
 int abg_build_index(const uint64_t *genome, uint64_t genome_size, const uint64_t *exclude, uint32_t n_exclude,
                     int device, abg_built_index *out);
+/* The same with seed::window_size given (src/AbismalIndex.hpp:73-77): 20, or 12 = the index a reference
+ * configured with --enable-short builds (denser selection of positions, reads down to 36 bases). */
+int abg_build_index_w(const uint64_t *genome, uint64_t genome_size, const uint64_t *exclude, uint32_t n_exclude,
+                      uint32_t window_size, int device, abg_built_index *out);
 void abg_built_index_free(abg_built_index *b);
 
 #ifdef __cplusplus

@@ -45,10 +45,12 @@ constexpr score_t kMaxDiffs = 32767;          // se_element::MAX_DIFFS :229
 constexpr double kInvalidHitFrac = 0.4;       // :228
 constexpr uint32_t kKeyWeight = 25;           // AbismalIndex.hpp:68
 constexpr uint32_t kKeyWeightThree = 16;      // :69
-constexpr uint32_t kWindow = 20;              // :76
+// seed::window_size, AbismalIndex.hpp:73-77: 20, or 12 when the reference is configured with --enable-short.
+// Taken from the index (abg_index_view::window_size) at the start of every abo_map_batch call.
+thread_local uint32_t kWindow = 20;
 constexpr uint32_t kHashMask = (1u << 25) - 1;    // :82
 constexpr uint32_t kHashMaskThree = 43046721u;    // 3^16, :88
-constexpr uint32_t kMinReadLen = kKeyWeight + kWindow - 1;  // abismal.cpp:212-213
+thread_local uint32_t kMinReadLen = kKeyWeight + 20 - 1;  // abismal.cpp:212-213
 constexpr uint32_t kSeMax = 50;               // se_candidates::max_size :448
 constexpr uint32_t kPeSmall = 32;             // pe_candidates::max_size_small :861
 constexpr uint32_t kPeLarge = 32u << 10;      // :862
@@ -819,6 +821,12 @@ int abo_map_batch(const abo_index *idx, const abg_params *params, const abg_batc
     return ABG_ERR_INVALID;
   }
   const abg_index_view &ix = idx->v;
+  if (ix.window_size != 0 && ix.window_size != 12 && ix.window_size != 20) {
+    g_err = "abo_map_batch: window_size must be 12 or 20";
+    return ABG_ERR_INVALID;
+  }
+  kWindow = ix.window_size ? ix.window_size : 20u;
+  kMinReadLen = kKeyWeight + kWindow - 1;
   const bool paired = params->mode & ABG_MODE_PAIRED;
   const bool a_rich = params->mode & ABG_MODE_A_RICH;
   const bool rpbat = params->mode & ABG_MODE_RANDOM_PBAT;

@@ -10,6 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "abismal")
+# the same sources compiled with -DENABLE_SHORT (configure --enable-short: seed::window_size 12)
+REF_BIN_SHORT = os.path.join(ORACLE_DIR, "_ref", "abismal_short")
 REF_DATA = os.path.join(ORACLE_DIR, "_ref", "data")
 ORACLE_MAP = os.path.join(ORACLE_DIR, "oracle_map")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libabismal_oracle.so")
@@ -27,7 +29,7 @@ def run(cmd, cwd=None, check=True):
 def ensure_built():
     if not (os.path.exists(ORACLE_LIB) and os.path.exists(ORACLE_MAP)):
         run(["make", "-C", ORACLE_DIR, "oracle", "oracle_map"])
-    if not os.path.exists(REF_BIN) and os.path.isdir("/root/reference/src"):
+    if not (os.path.exists(REF_BIN) and os.path.exists(REF_BIN_SHORT)) and os.path.isdir("/root/reference/src"):
         run(["make", "-C", ORACLE_DIR, "-j8", "ref"])
     lib = os.path.join(ROOT, "abismal_b200", "libabismal_b200.so")
     if not (os.path.exists(lib) and os.path.exists(CLI)):
@@ -90,6 +92,22 @@ class Workspace:
         self.ref("sim", "-seed", "6", "-a", "-l", "100", "-min-fraglen", "100", "-max-fraglen", "250", "-n", "4000",
                  "-m", "0.01", "-b", "0.98", "-o", "tests/rep_pbat", "tests/rep.fa")
         self._made.add("rep")
+
+    def need_short(self):
+        """Window-12 index (the --enable-short reference) of the repeat genome + reads down to 48 bases."""
+        if "short" in self._made:
+            return
+        import make_genome
+        if not os.path.exists(self.path("rep.fa")):
+            make_genome.write_fasta(make_genome.repeat_genome(), self.path("rep.fa"))
+        run([REF_BIN_SHORT, "idx", "-t", "4", "tests/rep.fa", "tests/rep_w12.idx"], cwd=self.dir)
+        self.ref("sim", "-seed", "11", "-single", "-l", "50", "-n", "5000", "-m", "0.03", "-b", "0.95",
+                 "-o", "tests/w12_se", "tests/rep.fa")
+        self.ref("sim", "-seed", "12", "-l", "60", "-min-fraglen", "60", "-max-fraglen", "250", "-n", "4000",
+                 "-m", "0.02", "-b", "0.98", "-o", "tests/w12_pe", "tests/rep.fa")
+        self.ref("sim", "-seed", "13", "-R", "-l", "100", "-min-fraglen", "100", "-max-fraglen", "300", "-n", "3000",
+                 "-m", "0.02", "-b", "0.9", "-o", "tests/w12_rpe", "tests/rep.fa")
+        self._made.add("short")
 
     def map_with(self, tool, tag, args, pre=()):
         """Run `<tool> map <pre...> -s <stats> -o <sam> <args...>` from the workspace dir
