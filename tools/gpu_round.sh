@@ -16,6 +16,10 @@ if [ -z "$SKIP_REF" ]; then
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.log
   cat $OUT/bench_reference.json
 fi
+if [ -x tools/micro/gather_bench3 ]; then
+  # random-gather ceiling of this box: 8/32/64/128-byte units over a 3 GB and a 20 GB array
+  (timeout 120 tools/micro/gather_bench3 3e9; timeout 120 tools/micro/gather_bench3 2e10) > $OUT/gather_bench3.txt 2>&1
+fi
 if [ -z "$SKIP_NCU" ]; then
   # launch list of the bench command (cold-cache, serialised: shares must agree, not absolutes)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'seed_kernel|align_kernel|map_reads_kernel' \
