@@ -610,19 +610,26 @@ struct SeedRange {  // narrowed bucket [low, high) and the seed length reached
   uint32_t low, high, p;
 };
 
+// A read shorter than 25 + its seed offset never meets `p == read_lim`; the extension then stops inside the
+// genome's 32767-base end padding at the latest (only reachable on read lengths the reference handles by
+// reading past its buffers).
+constexpr uint32_t kMaxExtend = 32000u;
+
 // find_candidates<25> (abismal.cpp:1163-1194); `read_start` = qcode + i
 __device__ __noinline__ SeedRange find_candidates(uint32_t maxc, const uint8_t *read_start, uint32_t read_lim,
                                                   uint32_t low, uint32_t high) {
   const IndexDev &ix = params().ix;
   uint32_t p = 25;
   uint32_t prev_low = low, prev_high = high;
-  for (; p != read_lim && (high - low) > maxc; ++p) {
+  for (; p != read_lim && p < kMaxExtend && (high - low) > maxc; ++p) {
     prev_low = low;
     prev_high = high;
     const uint32_t first_1 = lower_bound_idx(ix.index, low, high, [&](uint32_t e) {
       return get_bit(genome_base(ix.genome, (uint64_t)e + p)) < 1u;
     });
-    const uint32_t the_bit = get_bit(read_start[p]);
+    // bases past the end of the read are 0 (the reference reads whatever follows its vector there: the
+    // specific phase of reads shorter than 2 * window_size + 8 runs offsets whose 25-mer overhangs the read)
+    const uint32_t the_bit = get_bit(p < read_lim ? read_start[p] : 0u);
     high = the_bit ? high : first_1;
     low = the_bit ? first_1 : low;
   }
@@ -642,7 +649,7 @@ __device__ __noinline__ SeedRange find_candidates_three(const uint32_t *index3, 
   uint32_t p = 16;
   uint32_t prev_low = low, prev_high = high;
   const uint32_t v1 = g_to_a ? 2u : 1u, v2 = g_to_a ? 8u : 4u;
-  for (; p != max_size && (high - low) > maxc; ++p) {
+  for (; p != max_size && p < kMaxExtend && (high - low) > maxc; ++p) {
     prev_low = low;
     prev_high = high;
     const uint32_t first_1 = lower_bound_idx(index3, low, high, [&](uint32_t e) {
@@ -651,7 +658,7 @@ __device__ __noinline__ SeedRange find_candidates_three(const uint32_t *index3, 
     const uint32_t first_2 = lower_bound_idx(index3, low, high, [&](uint32_t e) {
       return three_fast(g_to_a, genome_base(ix.genome, (uint64_t)e + p)) < v2;
     });
-    const uint32_t the_num = three_fast(g_to_a, read_start[p]);
+    const uint32_t the_num = three_fast(g_to_a, p < max_size ? read_start[p] : 0u);
     const uint32_t old_low = low, old_high = high;
     high = (the_num == 0u) ? first_1 : ((the_num == v1) ? first_2 : old_high);
     low = (the_num == 0u) ? old_low : ((the_num == v1) ? first_1 : first_2);
@@ -1226,7 +1233,10 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
       }
       __syncwarp();
       if (specific) {
-        const unsigned m2 = __ballot_sync(FULL, el2), m3 = __ballot_sync(FULL, el3);
+        // the sensitive phase only visits offsets below lim_two (reads shorter than 2 * window_size + 8 have
+        // specific offsets beyond it): their logged survivors must not be replayed
+        const bool in_sens = i < lim_two;
+        const unsigned m2 = __ballot_sync(FULL, el2 && in_sens), m3 = __ballot_sync(FULL, el3 && in_sens);
         if (lane == 0) {
           elig2[base_off >> 5] = m2;
           elig3[base_off >> 5] = m3;

@@ -12,9 +12,10 @@
  * the reference's golden md5s (data/md5sum.txt) 16/16.
  *
  * Deliberate deviations (unobservable or undefined in the reference):
- *  - reads of 44..47 bases make the reference read past the end of the
- *    encoded read while rolling its hash (src/abismal.cpp:1308,1333); here the
- *    bytes past the end are defined to be 0.
+ *  - reads of 44..47 bases (36..47 with window 12) make the reference read past
+ *    the end of the encoded read while rolling its hash (src/abismal.cpp:1308,
+ *    1333) and while extending over-full buckets (find_candidates, :1163-1259);
+ *    here the bytes past the end are defined to be 0, however far.
  *  - the heap sentinel's stale `flags` field (se_element::reset keeps it,
  *    src/abismal.cpp:286-290) is set to 0; sentinels have pos == 0 and are
  *    skipped wherever flags would be looked at.
@@ -358,18 +359,21 @@ uint32_t lower_bound_idx(const uint32_t *idx, uint32_t low, uint32_t high, Pred 
   return first;
 }
 
+/* bound of the seed extension for reads that never meet p == read_lim (stays inside the end padding) */
+constexpr uint32_t kMaxExtend = 32000u;
+
 /* find_candidates<25>, src/abismal.cpp:1163-1194 */
 uint32_t find_candidates(const abg_index_view &ix, uint32_t max_candidates, const uint8_t *read_start,
                          uint32_t read_lim, const uint32_t *idx, uint32_t &low, uint32_t &high) {
   uint32_t p = kKeyWeight;
   uint32_t prev_low = low, prev_high = high;
-  for (; p != read_lim && (high - low) > max_candidates; ++p) {
+  for (; p != read_lim && p < kMaxExtend && (high - low) > max_candidates; ++p) {
     prev_low = low;
     prev_high = high;
     const uint32_t first_1 = lower_bound_idx(idx, low, high, [&](uint32_t e) {
       return get_bit(genome_base(ix.genome, static_cast<uint64_t>(e) + p)) < 1u;
     });
-    const uint32_t the_bit = get_bit(read_start[p]);
+    const uint32_t the_bit = get_bit(p < read_lim ? read_start[p] : 0);  // past the end: 0 (see the header)
     high = the_bit ? high : first_1;
     low = the_bit ? first_1 : low;
   }
@@ -388,7 +392,7 @@ uint32_t find_candidates_three(const abg_index_view &ix, bool g_to_a, uint32_t m
   uint32_t p = kKeyWeightThree;
   uint32_t prev_low = low, prev_high = high;
   const uint32_t v1 = g_to_a ? 2 : 1, v2 = g_to_a ? 8 : 4;
-  for (; p != max_size && (high - low) > max_candidates; ++p) {
+  for (; p != max_size && p < kMaxExtend && (high - low) > max_candidates; ++p) {
     prev_low = low;
     prev_high = high;
     const auto less = [&](uint32_t val) {
@@ -398,7 +402,7 @@ uint32_t find_candidates_three(const abg_index_view &ix, bool g_to_a, uint32_t m
     };
     const uint32_t first_1 = lower_bound_idx(idx, low, high, less(v1));
     const uint32_t first_2 = lower_bound_idx(idx, low, high, less(v2));
-    const uint32_t the_num = three_fast(g_to_a, read_start[p]);
+    const uint32_t the_num = three_fast(g_to_a, p < max_size ? read_start[p] : 0);
     const uint32_t mid_val = g_to_a ? 2u : 1u;
     const uint32_t old_low = low, old_high = high;
     high = (the_num == 0) ? first_1 : ((the_num == mid_val) ? first_2 : old_high);

@@ -2,6 +2,7 @@
 (src/AbismalIndex.hpp:73-77).  The reference needs a differently configured binary for it
 (oracle/_ref/abismal_short); here the window is a property of the index file and a flag of the builder.
 Bit-exact: index bytes, records, SAM text, stats."""
+import numpy as np
 import pytest
 
 import helpers
@@ -34,22 +35,27 @@ def test_cli_map_g_enable_short(workspace):
     assert open(ref[1]).read() == open(got[1]).read()
 
 
-@pytest.mark.parametrize("mode,files", [(0, ("w12_se_1.fq",)), (1, ("w12_pe_1.fq", "w12_pe_2.fq")),
-                                        (1 | 4, ("w12_rpe_1.fq", "w12_rpe_2.fq"))])
-def test_records_equal_oracle_window_12(workspace, mode, files):
-    """Through the C ABI: abg_index_view.window_size = 12, reads of 36..47 bases included (the reference
-    reads past the end of those; the oracle and the kernels define the missing bases as 0)."""
+@pytest.mark.parametrize("window,mode,files", [(12, 0, ("w12_se_1.fq",)), (12, 1, ("w12_pe_1.fq", "w12_pe_2.fq")),
+                                               (12, 1 | 4, ("w12_rpe_1.fq", "w12_rpe_2.fq")),
+                                               (20, 0, ("w12_se_1.fq",)), (20, 1, ("w12_pe_1.fq", "w12_pe_2.fq"))])
+def test_records_equal_oracle_shortest_reads(workspace, window, mode, files):
+    """Through the C ABI (abg_index_view.window_size), with every fifth read (pair) cut down to the shortest
+    lengths the window admits: 36..47 bases for window 12, 44..55 for window 20.  Below 2 * window + 8 bases
+    the specific phase visits seed offsets whose 25-mer overhangs the read (the reference reads past the end
+    of its buffer there; the oracle and the kernels define the missing bases as 0) and which the sensitive
+    phase does not revisit."""
     from abismal_b200 import Index, IndexFile, Mapper, load_fastq
     from abismal_b200.reads import ReadBatch
     workspace.need_short()
-    ixf = IndexFile(workspace.path("rep_w12.idx"))
-    assert ixf.window_size == 12
-    b = [load_fastq(workspace.path(f), min_read_length=36) for f in files]
-    # cut every fifth read (pair) down to 36..47 bases: shorter than the default build accepts
+    workspace.need_repeat()
+    ixf = IndexFile(workspace.path("rep_w12.idx" if window == 12 else "rep.idx"))
+    assert ixf.window_size == window
+    lo = 25 + window - 1
+    b = [load_fastq(workspace.path(f), min_read_length=lo) for f in files]
     cut = []
     for x in b:
         seqs = [x.sequence(i) for i in range(x.n)]
-        seqs = [s[:36 + (i % 12)] if i % 5 == 0 else s for i, s in enumerate(seqs)]
+        seqs = [s[:lo + (i % 12)] if i % 5 == 0 else s for i, s in enumerate(seqs)]
         cut.append(ReadBatch(None, seqs))
     ix = Index(ixf, 0)
     m = Mapper(ix, mode=mode, max_batch=cut[0].n, max_read_len=128)
@@ -58,6 +64,8 @@ def test_records_equal_oracle_window_12(workspace, mode, files):
     helpers.assert_results_equal(got, want, bool(mode & 1))
     mapped = want.pe_r1["pos"] != 0 if mode & 1 else want.se1["pos"] != 0
     assert mapped.sum() > 50
+    short = np.array([i % 5 == 0 for i in range(cut[0].n)])
+    assert (mapped & short).sum() > 5  # some of the shortest reads do map
     m.close()
     o.close()
     ix.close()
