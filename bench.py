@@ -317,7 +317,12 @@ def main():
                           "ceiling_gsectors_per_s": float(tj["random_gather_ceiling_gsectors_per_s"]),
                           "frac": sect_s / float(tj["random_gather_ceiling_gsectors_per_s"]),
                           "note": "32-byte L1-miss sectors per second vs the random-gather ceiling measured with "
-                                  "tools/micro/gather_bench.cu; this, not streaming bandwidth, bounds the kernel"}
+                                  "tools/micro/gather_bench3.cu; this, not streaming bandwidth, bounds the kernel"}
+                if "dram_sectors_read_per_pair" in tj and "bucket_contiguous_ceiling_gsectors_per_s" in tj:
+                    dsec = float(tj["dram_sectors_read_per_pair"]) * b1.n / (ms_per_launch / 1e3) / 1e9
+                    gather["dram_gsectors_per_s"] = dsec
+                    gather["bucket_contiguous_ceiling_gsectors_per_s"] = float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
+                    gather["dram_frac_of_contiguous_ceiling"] = dsec / float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
             except Exception:
                 pass
             out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
