@@ -291,8 +291,16 @@ def main():
             n_o = min(4000, b1.n)
             o = helpers.OracleMapper(ixf, mode=mode)
             t = time.perf_counter()
-            o.map_batch(b1.slice(0, n_o), b2.slice(0, n_o))
+            want = o.map_batch(b1.slice(0, n_o), b2.slice(0, n_o))
             port_s = time.perf_counter() - t
+            # parity at the full configuration: the records the timed e2e leg produced for these pairs against
+            # the CPU oracle (checker only; position, flags, NM of pe.r1/pe.r2/se1/se2 and the CIGAR lengths)
+            bad = 0
+            for k in ("se1", "n_cigar1", "pe_r1", "pe_r2", "se2", "n_cigar2"):
+                bad += int((getattr(res, k)[:n_o] != getattr(want, k)[:n_o]).sum())
+            out["parity"] = {"pairs_checked": n_o, "mismatching_records": bad, "against": "CPU oracle (oracle/abismal_oracle.cpp)"}
+            if bad:
+                raise SystemExit("bench: %d result records differ from the oracle on the first %d pairs" % (bad, n_o))
             seed_bytes, dp_bytes = algorithmic_bytes(o.counters.as_dict(), n_o)
             o.close()
             # dominant kernel: seed_kernel (seed hashing, counter/index lookups, packed compare, candidate sets);
