@@ -2039,9 +2039,7 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
   }
   for (; j2 != j2_end && v2.get(j2).empty(); ++j2) {
   }
-  // The first alignment of each end records its traceback while scoring (later ones leave it alone): most pairs
-  // align exactly one candidate per end, and the traceback of the winner is then already there.
-  bool rec1 = true, rec2 = true;
+  const bool rec1 = (j1_end - j1) <= kTbCacheMaxCands, rec2 = (j2_end - j2) <= kTbCacheMaxCands;
   for (; j2 != j2_end && !best.sure_ambig(); ++j2) {
     const Hit s2 = v2.get(j2);
     int scr2 = 0;
@@ -2057,19 +2055,15 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
       if (scr2 == 0 && m1 == 0) {  // both ends to align: together, one per half warp
         align2(rec2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), scr2, rec1, e1, flags1, s1.diffs(),
                max_diffs1, (int)readlen1, s1.pos(), scr1);
-        rec1 = rec2 = false;
         m1 = scr1;
         __syncwarp();
         if (W.lane == 0) mem_scr[j1] = (int16_t)scr1;
         __syncwarp();
       }
-      else if (scr2 == 0) {
+      else if (scr2 == 0)
         scr2 = (int)(int16_t)align(rec2, false, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), ao);
-        rec2 = false;
-      }
       else if (m1 == 0) {
         scr1 = (int)(int16_t)align(rec1, false, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, s1.pos(), ao);
-        rec1 = false;
         m1 = scr1;
         __syncwarp();
         if (W.lane == 0) mem_scr[j1] = (int16_t)scr1;
@@ -2088,13 +2082,6 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
     Hit s1 = swap_ends ? best.r2 : best.r1;
     Hit s2 = swap_ends ? best.r1 : best.r2;
     uint32_t len1 = 0, len2 = 0;
-    {
-      // tracebacks of the winners that are not in their slots yet: both at once (align2 records them; the
-      // align() calls below then find them there)
-      int t1, t2;
-      align2(true, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, best_pos1, t1, true, e2, flags2, s2.diffs(),
-             max_diffs2, (int)readlen2, best_pos2, t2);
-    }
     ao.score = 0;
     align(false, true, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, best_pos1, ao);
     int nm = build_cigar(e1, s1.diffs(), ao, (int)readlen1, best_scr1, cgs[e1], len1, best_pos1);
