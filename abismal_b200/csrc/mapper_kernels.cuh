@@ -269,7 +269,7 @@ __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool pai
   L.o_qcode = o;
   o += 2u * (ml + 32u);
   L.o_refb = o;
-  if (aln) o += 2u * (ml + 64u + 32u);       // reference bytes of the DP, one region per half warp (align_wave2)
+  if (aln) o += ml + 64u + 32u;              // reference bytes of the DP
   L.total = (o + 15u) & ~15u;
   return L;
 }
@@ -304,9 +304,7 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   __device__ __forceinline__ uint32_t *plane(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_planes) + k * L.plane_words; }
   __device__ __forceinline__ uint8_t *base(int e) const { return base_ptr + L.o_base + (size_t)e * params().ml; }
   __device__ __forceinline__ uint8_t *qcode(int e) const { return base_ptr + L.o_qcode + (size_t)e * (params().ml + 32u); }
-  __device__ __forceinline__ uint8_t *refb(int half = 0) const {
-    return base_ptr + L.o_refb + (size_t)half * (params().ml + 64u + 32u);
-  }
+  __device__ __forceinline__ uint8_t *refb() const { return base_ptr + L.o_refb; }
   __device__ __forceinline__ uint32_t *masks(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_masks) + k * L.mask_words; }
   __device__ __forceinline__ uint32_t *log_pos() const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_log); }
   __device__ __forceinline__ uint32_t *log_meta() const { return log_pos() + kLogCap; }
@@ -1574,203 +1572,6 @@ __device__ __forceinline__ int align(bool record_tb, bool need_tb, int tb_slot, 
   return out.score;
 }
 
-// Two banded alignments at once, one per half warp (bands of at most 31 columns = 16 lanes x 2 columns).
-// Most alignments have bands of 3-11 columns and would keep 2-6 lanes of a full-warp wavefront busy; the two
-// ends of a pair are independent, so best_pair aligns them together.  Same cell recurrence, arrow codes,
-// traceback words and first-maximum rule as align_wave; request X = {end, band, query length, position,
-// traceback?}; the traceback slot of a request is its end.
-struct WaveReq {
-  int end, bw, q_sz, tb;
-  uint32_t t_pos;
-};
-template <bool TB>
-__device__ __noinline__ void align_wave2(WaveReq ra, WaveReq rb, AlnOut *out_a, AlnOut *out_b) {
-  const Warp W;
-  const KernelParams &P = params();
-  const int lane = W.lane, h = lane >> 4, l = lane & 15;
-  const WaveReq r = h ? rb : ra;
-  const int bw = r.bw, q_sz = r.q_sz;
-  const uint8_t *q = W.qcode(r.end);
-  uint8_t *refb = W.refb(h);
-  const uint32_t t_beg = r.t_pos - (uint32_t)((bw - 1) / 2);
-  const int t_shift = q_sz + bw;
-  {
-    const uint32_t w0 = t_beg >> 4;
-    const int n_ref = t_shift - 1;
-    const int nw = (int)(((t_beg + (uint32_t)n_ref - 1u) >> 4) - w0) + 1;
-    const int shift0 = (int)(t_beg & 15u);
-    __syncwarp();
-    for (int k = l; k < nw; k += 16) {
-      const uint64_t word = __ldg(P.ix.genome + w0 + k);
-#pragma unroll
-      for (int n = 0; n < 16; ++n) {
-        const int rr = 16 * k + n - shift0;
-        if (rr >= 0 && rr < n_ref) refb[rr] = (uint8_t)((word >> (4 * n)) & 15u);
-      }
-    }
-    __syncwarp();
-  }
-  const int nl = (bw + 1) >> 1;
-  const int my_iter = (t_shift - 1) + (nl - 1);
-  const int n_iter = max(__shfl_sync(FULL, my_iter, 0), __shfl_sync(FULL, my_iter, 16));
-  const unsigned limA = 2 * l < bw ? (unsigned)q_sz : 0u;
-  const unsigned limB = 2 * l + 1 < bw ? (unsigned)q_sz : 0u;
-  const int up_mask = l > 0 ? -1 : 0;     // first lane of a half: no left neighbour for its A column
-  const int down_mask = l < 15 ? -1 : 0;  // last lane of a half: the shuffle hands back its own value
-  const bool my_tb = TB && r.tb != 0;
-  uint64_t *tbs = W.tb_sm(r.end) + l;
-  uint64_t *tbg = W.tb_gm(r.end) + l;
-  int A = 0, B = 0;
-  int best = 0, best_at = 0;
-  uint64_t tbw = 0;
-  int qi = 1 + l - bw;
-  const uint8_t *rp = refb - l;
-  uint32_t qa = (unsigned)qi < limA ? (uint32_t)q[qi] : 0u;
-  for (int T = 1; T <= n_iter; ++T, ++qi) {
-    const bool okA = (unsigned)qi < limA, okB = (unsigned)(qi + 1) < limB;
-    const uint32_t ref = (okA || okB) ? (uint32_t)rp[T - 1] : 0u;
-    const uint32_t qb = (unsigned)(qi + 1) < (unsigned)q_sz ? (uint32_t)q[qi + 1] : 0u;
-    const int left_in = __shfl_up_sync(FULL, B, 1, 16) & up_mask;
-    int diag = A + ((qa & ref) ? 2 : -3);
-    int v = max(diag, 0);
-    int cA = diag >= 0 ? 0 : 3;
-    {
-      const int above = (qi + 1 < q_sz ? B : 0) - 4;
-      if (above >= v) {
-        v = above;
-        cA = 2;
-      }
-      const int left = left_in - 4;
-      if (left >= v) {
-        v = left;
-        cA = 1;
-      }
-    }
-    const int newA = okA ? v : 0;
-    if (TB) cA = newA > 0 ? cA : 3;
-    if (newA > best) {
-      best = newA;
-      best_at = 2 * T;
-    }
-    const int a_down = __shfl_down_sync(FULL, newA, 1, 16) & down_mask;
-    diag = B + ((qb & ref) ? 2 : -3);
-    v = max(diag, 0);
-    int cB = diag >= 0 ? 0 : 3;
-    {
-      const int above = (qi + 2 < q_sz ? a_down : 0) - 4;
-      if (above >= v) {
-        v = above;
-        cB = 2;
-      }
-      const int left = newA - 4;
-      if (left >= v) {
-        v = left;
-        cB = 1;
-      }
-    }
-    const int newB = okB ? v : 0;
-    if (TB) cB = newB > 0 ? cB : 3;
-    if (newB > best) {
-      best = newB;
-      best_at = 2 * T + 1;
-    }
-    A = newA;
-    B = newB;
-    qa = qb;
-    if (TB) {
-      tbw = (tbw >> 4) | ((uint64_t)(uint32_t)(cA | (cB << 2)) << 60);
-      if (((T & 15) == 15 && T < my_iter) || T == my_iter) {
-        if ((T & 15) != 15) tbw >>= 4 * (15 - (T & 15));
-        if (my_tb && l < nl) {
-          if (l < kTbLanesSm) tbs[(T >> 4) * kTbLanesSm] = tbw;
-          else tbg[(size_t)(T >> 4) * 32] = tbw;
-        }
-      }
-      if ((T & 15) == 15) tbw = 0;
-    }
-  }
-  int bv = best, br = (best_at >> 1) - l, bc = 2 * l + (best_at & 1);
-  if (best == 0) br = 0, bc = 0;
-#pragma unroll
-  for (int d = 8; d >= 1; d >>= 1) {
-    const int ov = __shfl_xor_sync(FULL, bv, d);
-    const int orow = __shfl_xor_sync(FULL, br, d);
-    const int oc = __shfl_xor_sync(FULL, bc, d);
-    const bool take = ov > bv || (ov == bv && (orow < br || (orow == br && oc < bc)));
-    if (take) {
-      bv = ov;
-      br = orow;
-      bc = oc;
-    }
-  }
-  out_a->score = __shfl_sync(FULL, bv, 0);
-  out_a->row = __shfl_sync(FULL, br, 0);
-  out_a->col = __shfl_sync(FULL, bc, 0);
-  out_a->bw = ra.bw;
-  out_b->score = __shfl_sync(FULL, bv, 16);
-  out_b->row = __shfl_sync(FULL, br, 16);
-  out_b->col = __shfl_sync(FULL, bc, 16);
-  out_b->bw = rb.bw;
-  __syncwarp();
-}
-
-// align() for two independent requests (request X: traceback slot = end X).  Falls back to two align() calls
-// unless both need a DP (diffs != 0, not the alignment cached in their slot) with bands of at most 31 columns.
-__device__ __forceinline__ void align2(bool rec_a, int end_a, uint32_t flags_a, int diffs_a, int max_diffs_a, int q_a,
-                                       uint32_t pos_a, int &scr_a, bool rec_b, int end_b, uint32_t flags_b, int diffs_b,
-                                       int max_diffs_b, int q_b, uint32_t pos_b, int &scr_b) {
-  const Warp W;
-  AlnOut oa, ob;
-  const int bw_a = band_width(diffs_a, max_diffs_a), bw_b = band_width(diffs_b, max_diffs_b);
-  TbKey *ta = &W.scal()->tbk[end_a], *tb = &W.scal()->tbk[end_b];
-  const uint32_t key_a = ((uint32_t)end_a << 16) | (flags_a & (ABG_FLAG_RC | ABG_FLAG_A_RICH));
-  const uint32_t key_b = ((uint32_t)end_b << 16) | (flags_b & (ABG_FLAG_RC | ABG_FLAG_A_RICH));
-  const bool need_a = diffs_a != 0 && !(ta->valid && ta->pos == pos_a && ta->key == key_a && ta->bw == bw_a);
-  const bool need_b = diffs_b != 0 && !(tb->valid && tb->pos == pos_b && tb->key == key_b && tb->bw == bw_b);
-  if (!(need_a && need_b && bw_a <= 31 && bw_b <= 31 && end_a != end_b)) {
-    scr_a = (int)(int16_t)align(rec_a, false, end_a, end_a, flags_a, diffs_a, max_diffs_a, q_a, pos_a, oa);
-    scr_b = (int)(int16_t)align(rec_b, false, end_b, end_b, flags_b, diffs_b, max_diffs_b, q_b, pos_b, ob);
-    return;
-  }
-  build_qcode(end_a, flags_a);
-  build_qcode(end_b, flags_b);
-  if (params().counters != nullptr && W.lane == 0) {
-    W.scal()->cnt[3] += 2;
-    W.scal()->cnt[4] += (unsigned long long)(q_a + bw_a + q_b + bw_b);
-  }
-  __syncwarp();
-  if (W.lane == 0) {
-    if (rec_a) ta->valid = 0;
-    if (rec_b) tb->valid = 0;
-  }
-  const WaveReq ra{end_a, bw_a, q_a, rec_a ? 1 : 0, pos_a}, rb{end_b, bw_b, q_b, rec_b ? 1 : 0, pos_b};
-  if (rec_a || rec_b) align_wave2<true>(ra, rb, &oa, &ob);
-  else align_wave2<false>(ra, rb, &oa, &ob);
-  if (W.lane == 0) {
-    if (rec_a) {
-      ta->pos = pos_a;
-      ta->key = key_a;
-      ta->score = oa.score;
-      ta->row = oa.row;
-      ta->col = oa.col;
-      ta->bw = bw_a;
-      ta->valid = 1;
-    }
-    if (rec_b) {
-      tb->pos = pos_b;
-      tb->key = key_b;
-      tb->score = ob.score;
-      tb->row = ob.row;
-      tb->col = ob.col;
-      tb->bw = bw_b;
-      tb->valid = 1;
-    }
-  }
-  __syncwarp();
-  scr_a = (int)(int16_t)oa.score;
-  scr_b = (int)(int16_t)ob.score;
-}
-
 struct CigarOut {
   uint32_t *ops;     // results array of this read (cigar_stride slots)
   uint32_t stride;
@@ -2051,18 +1852,10 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
     for (; j1 != j1_end && !best.sure_ambig(); ++j1) {
       const Hit s1 = v1.get(j1);
       if (!(s1.pos() + min_dist <= lim)) break;
-      int m1 = *(volatile int16_t *)(mem_scr + j1);
-      if (scr2 == 0 && m1 == 0) {  // both ends to align: together, one per half warp
-        align2(rec2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), scr2, rec1, e1, flags1, s1.diffs(),
-               max_diffs1, (int)readlen1, s1.pos(), scr1);
-        m1 = scr1;
-        __syncwarp();
-        if (W.lane == 0) mem_scr[j1] = (int16_t)scr1;
-        __syncwarp();
-      }
-      else if (scr2 == 0)
+      if (scr2 == 0)
         scr2 = (int)(int16_t)align(rec2, false, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), ao);
-      else if (m1 == 0) {
+      int m1 = *(volatile int16_t *)(mem_scr + j1);
+      if (m1 == 0) {
         scr1 = (int)(int16_t)align(rec1, false, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, s1.pos(), ao);
         m1 = scr1;
         __syncwarp();
