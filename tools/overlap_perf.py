@@ -1,5 +1,5 @@
 """Launch-shape timing on the bench workload: sequential vs overlapped seed/align launch, CTAs per SM.
-usage: overlap_perf.py [pairs] [configs]   config = OVERLAP[:SEED_BLOCKS[:AUX_BLOCKS[:MINB[:MINB_SEED]]]], comma separated
+usage: overlap_perf.py [pairs] [configs]   config = OVERLAP[:SEED_BLOCKS[:AUX_BLOCKS[:MINB[:MINB_SEED[:CHUNK]]]]], comma separated
 ABISMAL_B200_LIB selects a differently compiled library (one per process)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,7 +25,7 @@ for cfg in configs:
     f = cfg.split(":")
     os.environ["ABISMAL_B200_OVERLAP"] = f[0]
     for k, name in ((1, "ABISMAL_B200_SEED_BLOCKS"), (2, "ABISMAL_B200_AUX_BLOCKS"), (3, "ABISMAL_B200_MINB"),
-                    (4, "ABISMAL_B200_MINB_SEED")):
+                    (4, "ABISMAL_B200_MINB_SEED"), (5, "ABISMAL_B200_CHUNK")):
         if len(f) > k and f[k] != "":
             os.environ[name] = f[k]
         else:
