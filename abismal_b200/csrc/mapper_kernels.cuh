@@ -211,33 +211,18 @@ static_assert(sizeof(KernelParams) <= kParamBytes, "KernelParams must fit its sh
 __host__ __device__ __forceinline__ uint32_t tb_sm_words(uint32_t ml) { return (ml + 64u + 32u + 15u) / 16u; }
 
 // Shared-memory regions per warp.  The three kernels keep different subsets (layout_kind): the seeding kernel
-// needs no traceback words, no reference bytes and one candidate set, and spends the room on the staging
-// buffers of its asynchronous seed-context gathers; the alignment kernel needs no staging, log or planes.
+// needs no traceback words, no reference bytes and one candidate set; the alignment kernel needs no log, masks
+// or planes.
 constexpr uint32_t kLayoutFull = 0, kLayoutSeed = 1, kLayoutAlign = 2;
-#ifndef ABG_STAGES
-#define ABG_STAGES 4
-#endif
-// Measured on B200 (profiles/README.md): staging the records through shared memory with cp.async is SLOWER than
-// plain register gathers (seed_kernel 131-136 ms vs 105 ms per 2^20 pairs) -- the kernel is bound by the rate of
-// random DRAM sectors, not by loads in flight per warp -- so the staged path is compiled out by default.
-#ifndef ABG_STAGED
-#define ABG_STAGED 0
-#endif
 // Smaller instruction footprint (the kernels stall on instruction fetch: L0 ~6 KB, L1.5 32 KB against 100-160 KB
 // of code): one wavefront DP function with a run-time traceback flag, a rolled reference-staging loop,
 // out-of-line align() and deep compare.
 #ifndef ABG_SMALL_CODE
 #define ABG_SMALL_CODE 1  // measured: seed_kernel 96.0 vs 100.5 ms, align_kernel 47.7 vs 50.5 ms per 2^20 pairs
 #endif
-#ifndef ABG_CPASYNC_CA
-#define ABG_CPASYNC_CA 1
-#endif
-constexpr int kStages = ABG_STAGES;    // chunks of 32 seed-context records in flight per warp (cp.async groups)
-constexpr uint32_t kStageBytes = 32u * 32u + 2u * 32u * 4u;  // 32 records + {slot, sub} of their candidates
 
 struct WarpLayout {
-  uint32_t o_packed, o_masks, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, o_stage,
-      total;
+  uint32_t o_packed, o_masks, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, total;
   uint32_t plane_words, elig_words, mask_words;
 };
 
@@ -245,8 +230,6 @@ __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool pai
   WarpLayout L;
   const bool seed = kind != kLayoutAlign, aln = kind != kLayoutSeed;
   uint32_t o = 0;
-  L.o_stage = o;
-  if (seed && ABG_STAGED) o += (uint32_t)kStages * kStageBytes;  // first: 16-byte aligned cp.async destinations
   L.o_packed = o;
   o += ml / 2;                               // packed read, ml/16 u64
   L.o_se = o;
@@ -314,7 +297,6 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   __device__ __forceinline__ uint32_t *masks(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_masks) + k * L.mask_words; }
   __device__ __forceinline__ uint32_t *log_pos() const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_log); }
   __device__ __forceinline__ uint32_t *log_meta() const { return log_pos() + kLogCap; }
-  __device__ __forceinline__ unsigned char *stage(int k) const { return base_ptr + L.o_stage + (size_t)k * kStageBytes; }
   __device__ __forceinline__ uint32_t *elig(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_elig) + k * L.elig_words; }
   __device__ __forceinline__ size_t slot() const {
     return (size_t)params().slot_base + (size_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -843,7 +825,7 @@ __device__ __forceinline__ void compare_deep(const IndexDev &ix, const uint32_t 
 }
 
 // Out-of-line deep compare of one candidate per lane, everything by value (survivors of the prefilter are rare;
-// keeping this out of the staged loop keeps the loop small, and by-value keeps its state in registers).
+// keeping this out of the gather loop keeps the loop small, and by-value keeps its state in registers).
 struct Deep1 {
   int d, pm;
   uint32_t pos, n_entry, n_word;
@@ -951,120 +933,6 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
   }
 #endif
   compare_deep<KC, NC0>(ix, index3, mA, mC, mG, mT, n_words, bound, valid, slot, sub, d, pm, the_pos, n_entry, n_word);
-}
-
-// ---- asynchronous seed-context gathers (cp.async into the warp's staging buffers) ------------------------
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-#if ABG_CPASYNC_CA
-  // .ca: the two 16-byte halves of a record meet in L1 (one 32-byte sector request to L2)
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-#else
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-constexpr uint32_t kSubThree = 0x80000000u;  // candidate comes from the three-letter bucket
-constexpr uint32_t kSubRec = 0x40000000u;    // its seed-context record was requested (staged path)
-
-// Issue the gathers of chunk [c0, c0 + 32) of this round's candidates (canonical order) into staging buffer
-// `st`: lane l owns candidate c0 + l, finds its bucket by binary search over the lanes' inclusive bucket-size
-// sums, and copies its 32-byte record global -> shared without going through registers.  Always commits one
-// cp.async group (possibly empty) so that the caller's group accounting is uniform.
-__device__ __noinline__ void stage_issue(const IndexDev &ix, const uint4 *__restrict__ ctx3, unsigned char *st,
-                                            uint32_t c0, uint32_t total, uint32_t base_off, uint32_t incl,
-                                            uint32_t tot, uint32_t n2, uint32_t s2, uint32_t s3, int lane) {
-  uint32_t *meta = reinterpret_cast<uint32_t *>(st + 32u * 32u);
-  uint32_t slot = 0, sub = ~0u;
-  if (c0 < total) {
-    const uint32_t cidx = c0 + (uint32_t)lane;
-    int o = 0;
-#pragma unroll
-    for (int sft = 16; sft >= 1; sft >>= 1) {
-      const uint32_t vv = __shfl_sync(FULL, incl, (o + sft - 1) & 31);
-      if (vv <= cidx) o += sft;
-    }
-    o &= 31;
-    const uint32_t o_incl = __shfl_sync(FULL, incl, o);
-    const uint32_t o_tot = __shfl_sync(FULL, tot, o);
-    const uint32_t o_n2 = __shfl_sync(FULL, n2, o);
-    const uint32_t o_s2 = __shfl_sync(FULL, s2, o);
-    const uint32_t o_s3 = __shfl_sync(FULL, s3, o);
-    if (cidx < total) {
-      const uint32_t r = cidx - (o_incl - o_tot);
-      const bool three = r >= o_n2;
-      slot = three ? o_s3 + (r - o_n2) : o_s2 + r;
-      const uint32_t i_off = base_off + (uint32_t)o;
-      sub = i_off | (three ? kSubThree : 0u);
-      const uint4 *tab = three ? ctx3 : ix.ctx;
-      if (tab != nullptr) {
-        sub |= kSubRec;
-        const uint32_t a = min((uint32_t)(kCtxArrays - 1), i_off >> 5);
-        const uint4 *src = tab + 2 * ((uint64_t)a * (three ? ix.n_ctx3 : ix.n_ctx) + slot);
-        unsigned char *dst = st + 32u * (uint32_t)lane;
-        cp_async16(dst, src);
-        cp_async16(dst + 16, src + 1);
-      }
-    }
-  }
-  meta[lane] = slot;
-  meta[32 + lane] = sub;
-  cp_async_commit();
-}
-
-// Compare the chunk staged in `st` (its records have landed): seed-context prefilter from shared memory, then
-// the deep compare for what it could not reject.  Same results as compare_chunk<1, 4>.
-__device__ __forceinline__ void compare_staged(const uint32_t *__restrict__ index3, const unsigned char *st,
-                                               const uint32_t *mA, const uint32_t *mC, const uint32_t *mG,
-                                               const uint32_t *mT, int n_words, int bound, int lane, int &d, int &pm,
-                                               uint32_t &the_pos, uint32_t &sub, uint32_t &n_entry, uint32_t &n_word) {
-  const uint32_t *meta = reinterpret_cast<const uint32_t *>(st + 32u * 32u);
-  const int n_bases = 16 * n_words;
-  const uint32_t sub_m = meta[32 + lane];
-  const uint32_t slot = meta[lane];
-  bool valid = sub_m != ~0u;
-  sub = sub_m & ~kSubRec;
-  d = 0;
-  pm = 1 << 30;
-  the_pos = 0;
-  if (valid && (sub_m & kSubRec) != 0u) {
-    const uint4 *rec = reinterpret_cast<const uint4 *>(st + 32u * (uint32_t)lane);
-    const uint4 x = rec[0], y = rec[1];
-    const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-    const uint32_t i_off = sub_m & 0x3fffffffu;
-    const uint32_t a = min((uint32_t)(kCtxArrays - 1), i_off >> 5);
-    const uint32_t q0 = i_off - 32u * a;  // read position of the record's first base
-    int lb = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int qb = (int)q0 + 32 * c;
-      const int nb = n_bases - qb;
-      if (nb > 0) {
-        const uint32_t wi = (uint32_t)qb >> 5, sh = (uint32_t)qb & 31u;
-        const uint32_t a_ = __funnelshift_r(mA[wi], mA[wi + 1], sh), c_ = __funnelshift_r(mC[wi], mC[wi + 1], sh);
-        const uint32_t g_ = __funnelshift_r(mG[wi], mG[wi + 1], sh), t_ = __funnelshift_r(mT[wi], mT[wi + 1], sh);
-        const uint32_t mm = ~match_bits(w[2 * c], w[2 * c + 1], a_, c_, g_, t_);
-        lb += __popc(nb >= 32 ? mm : (mm & ((1u << nb) - 1u)));
-      }
-    }
-    if (lb > bound) {
-      valid = false;
-      n_entry += 1;
-      n_word += 4;
-    }
-  }
-  if (!__any_sync(FULL, valid)) return;
-  const Deep1 r = compare_deep_one(index3, n_words, bound, valid, slot, sub);
-  d = r.d;
-  pm = r.pm;
-  the_pos = r.pos;
-  n_entry += r.n_entry;
-  n_word += r.n_word;
 }
 
 // Ordered replay of the survivors of one compare round against candidate set `set_id`
@@ -1263,15 +1131,7 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
       const uint32_t incl = warp_incl_scan_add(tot, lane);
       const uint32_t total = __shfl_sync(FULL, incl, 31);
       bool stop = false;
-      // Staged path: the records of up to kStages chunks are in flight (cp.async) while one chunk is compared
-      const bool staged = ABG_STAGED != 0 && ix.ctx != nullptr && (ctx3 != nullptr || ix.n_ctx3 == 0);
-      if (staged) {
-#pragma unroll 1
-        for (int sg = 0; sg < kStages; ++sg)
-          stage_issue(ix, ctx3, W.stage(sg), 32u * sg, total, base_off, incl, tot, n2, s2, s3, lane);
-      }
-      int sg = 0;
-      for (uint32_t c0 = 0; c0 < total && !stop; c0 += 32u * (staged ? 1 : kCand)) {
+      for (uint32_t c0 = 0; c0 < total && !stop; c0 += 32u * kCand) {
         const int cutoff = st->cutoff;
         // In the specific phase compare against the looser bound the sensitive phase may use later (the heap
         // top only ever decreases) and log what survives it, unless the set is already full (then the
@@ -1289,25 +1149,8 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
         int d[kCand], pm[kCand];
         uint32_t the_pos[kCand];
         uint32_t sub[kCand];
-        if (staged) {
-          cp_async_wait<kStages - 1>();  // the oldest of the kStages groups in flight = this chunk
-          int d1, pm1;
-          uint32_t pos1, sub1;
-          compare_staged(index3, W.stage(sg), mA, mC, mG, mT, n_words, bound, lane, d1, pm1, pos1, sub1, c_entry, c_word);
-#pragma unroll
-          for (int k = 0; k < kCand; ++k) {
-            d[k] = k == 0 ? d1 : 0;
-            pm[k] = k == 0 ? pm1 : (1 << 30);
-            the_pos[k] = k == 0 ? pos1 : 0u;
-            sub[k] = k == 0 ? sub1 : 0u;
-          }
-          // refill the buffer just consumed with the chunk kStages ahead
-          stage_issue(ix, ctx3, W.stage(sg), c0 + 32u * kStages, total, base_off, incl, tot, n2, s2, s3, lane);
-          sg = (sg + 1) & (kStages - 1);
-        }
-        else
-          compare_chunk<kCand, 4>(ix, index3, ctx3, mA, mC, mG, mT, n_words, bound, c0, total, base_off, incl, tot, n2, s2,
-                                  s3, lane, d, pm, the_pos, sub, c_entry, c_word);
+        compare_chunk<kCand, 4>(ix, index3, ctx3, mA, mC, mG, mT, n_words, bound, c0, total, base_off, incl, tot, n2, s2,
+                                s3, lane, d, pm, the_pos, sub, c_entry, c_word);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < kCand; ++k) {
@@ -1330,7 +1173,6 @@ __device__ __noinline__ void process_seeds(int set_id, int end, uint32_t strand_
           }
         }
       }
-      if (staged) cp_async_wait<0>();  // nothing may land in a buffer the next round re-issues into
     }
     __syncwarp();
   }
