@@ -39,3 +39,22 @@ def test_window_changes_the_result(workspace):
     workspace.need_short()
     workspace.need_repeat()
     assert helpers.md5(workspace.path("rep_w12.idx")) != helpers.md5(workspace.path("rep.idx"))
+
+
+def test_index_readers_follow_the_window_in_the_file(workspace, tmp_path):
+    """Python and C++ readers accept window 12 and 20 and refuse anything else (seed::read,
+    src/AbismalIndex.cpp:1005-1013, accepts only the window the binary was configured with)."""
+    import struct
+    from abismal_b200 import IndexFile
+    workspace.need_short()
+    assert IndexFile(workspace.path("rep_w12.idx")).window_size == 12
+    bad = tmp_path / "w13.idx"
+    with open(workspace.path("rep_w12.idx"), "rb") as f:
+        blob = bytearray(f.read(4096))
+    blob[16:20] = struct.pack("<I", 13)
+    bad.write_bytes(bytes(blob))
+    with pytest.raises(ValueError):
+        IndexFile(str(bad))
+    p = helpers.run([helpers.ORACLE_MAP, "map", "-i", str(bad), "-o", str(tmp_path / "x.sam"),
+                     workspace.path("w12_se_1.fq")], check=False)
+    assert p.returncode != 0 and "window size" in p.stderr
