@@ -14,6 +14,10 @@ FLAG_RC = 0x10
 FLAG_AMBIG = 0x100
 FLAG_A_RICH = 0x1000
 
+FEATURE_SEED_CONTEXT = 1
+FEATURE_COMPACT_COUNTERS = 2
+FEATURE_GENOME_HAS_IUPAC = 4
+
 HIT_DTYPE = np.dtype([("diffs", "<i2"), ("flags", "<u2"), ("pos", "<u4")])
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -87,6 +91,8 @@ def load_library():
     lib.abg_index_destroy.restype = None
     lib.abg_index_device_bytes.argtypes = [C.c_void_p]
     lib.abg_index_device_bytes.restype = C.c_uint64
+    lib.abg_index_features.argtypes = [C.c_void_p]
+    lib.abg_index_features.restype = C.c_uint32
     lib.abg_mapper_create.argtypes = [C.c_void_p, C.POINTER(abg_params), C.c_uint32, C.c_uint32, C.c_int,
                                       C.POINTER(C.c_void_p)]
     lib.abg_mapper_destroy.argtypes = [C.c_void_p]
@@ -253,6 +259,11 @@ class Index:
     @property
     def device_bytes(self):
         return int(self.lib.abg_index_device_bytes(self._h))
+
+    @property
+    def features(self):
+        """FEATURE_* bits: which derived arrays (accelerators of the same lookups) the index holds."""
+        return int(self.lib.abg_index_features(self._h))
 
     def close(self):
         if self._h:

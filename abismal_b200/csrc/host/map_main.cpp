@@ -132,13 +132,20 @@ public:
     abg_mapper_destroy(mapper_);
 #endif
   }
-  void map(const abg_batch &b, abg_results &r) {
+  // false: a reported CIGAR did not fit cigar_stride operations (the caller retries with a larger stride)
+  bool map(const abg_batch &b, abg_results &r) {
 #ifdef ABISMAL_ENGINE_ORACLE
-    if (abo_map_batch(index_->oidx_, &params_, &b, &r, nullptr) != 0) throw std::runtime_error(abo_last_error());
+    const int rc = abo_map_batch(index_->oidx_, &params_, &b, &r, nullptr);
+    if (rc == ABG_ERR_CIGAR_OVERFLOW) return false;
+    if (rc != 0) throw std::runtime_error(abo_last_error());
 #else
-    if (abg_map_batch(mapper_, &b, &r) != 0) throw std::runtime_error(abg_last_error());
+    const int rc = abg_map_batch(mapper_, &b, &r);
+    if (rc == ABG_ERR_CIGAR_OVERFLOW) return false;
+    if (rc != 0) throw std::runtime_error(abg_last_error());
 #endif
+    return true;
   }
+  uint32_t cigar_stride() const { return params_.cigar_stride; }
 
 private:
   std::shared_ptr<DeviceIndex> index_;
@@ -226,7 +233,7 @@ public:
   ab2::SeStats se_stats;
   ab2::PeStats pe_stats;
   uint64_t n_done = 0;
-  StageClock t_read1, t_read2, t_map, t_format, t_write;
+  StageClock t_read1, t_read2, t_map, t_format, t_write, t_upload;
 
 private:
   template <class F>
@@ -294,6 +301,7 @@ private:
     // batches; the lead worker of a device uploads, the others wait for it.
     if (lead) {
       try {
+        StageClock::Scope sc(t_upload);
         lead->set_value(std::make_shared<DeviceIndex>(index_.view(), device));
       }
       catch (...) {
@@ -301,8 +309,12 @@ private:
       }
     }
     std::shared_ptr<DeviceIndex> dev_index = shared.get();
+    // The reference has no CIGAR length limit (bam_cigar_t is a vector).  The engine starts with 64 slots per
+    // read -- NM <= valid_frac * length keeps reported CIGARs of 150-base reads below 2 * 30 + 3 operations --
+    // and is rebuilt with twice as many whenever a batch reports one that did not fit.
     uint32_t engine_max_len = 256;
-    std::unique_ptr<Engine> engine(new Engine(dev_index, cfg_.params, cfg_.batch_size, engine_max_len));
+    abg_params params = cfg_.params;
+    std::unique_ptr<Engine> engine(new Engine(dev_index, params, cfg_.batch_size, engine_max_len));
     WorkItem *it = nullptr;
     while (!failed_ && to_map_.pop(it)) {
       const uint32_t n = it->b1.size();
@@ -312,9 +324,8 @@ private:
         if (max_len > engine_max_len) {
           engine.reset();
           engine_max_len = max_len;
-          engine.reset(new Engine(dev_index, cfg_.params, cfg_.batch_size, engine_max_len));
+          engine.reset(new Engine(dev_index, params, cfg_.batch_size, engine_max_len));
         }
-        it->rb.resize(n, cfg_.params.cigar_stride, cfg_.paired_end);
         abg_batch batch;
         std::memset(&batch, 0, sizeof batch);
         batch.n = n;
@@ -324,8 +335,16 @@ private:
           batch.seq2 = it->b2.seq.data();
           batch.off2 = it->b2.seq_off.data();
         }
-        abg_results res = it->rb.view(cfg_.paired_end);
-        engine->map(batch, res);
+        for (;;) {
+          it->rb.resize(n, params.cigar_stride, cfg_.paired_end);
+          abg_results res = it->rb.view(cfg_.paired_end);
+          if (engine->map(batch, res)) break;
+          if (params.cigar_stride >= 2u * engine_max_len + 3u)  // an alignment cannot have more operations
+            throw std::runtime_error("a CIGAR needed more operations than the read has bases");
+          params.cigar_stride = std::min(2u * params.cigar_stride, 2u * engine_max_len + 3u);
+          engine.reset();
+          engine.reset(new Engine(dev_index, params, cfg_.batch_size, engine_max_len));
+        }
       }
       if (!to_out_.push(it)) break;
     }
@@ -589,6 +608,8 @@ int map_main(int argc, char *argv[]) {
       const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_map).count();
       log_msg("reads mapped: " + std::to_string(pipe.n_done));
       log_msg("total mapping time: " + fmt_secs(secs));
+      // summed over the devices (they upload concurrently); the readers parse the first batches meanwhile
+      log_msg("index upload to HBM: " + fmt_secs(pipe.t_upload.secs() / static_cast<double>(cfg.devices.size())) + " per device");
       log_msg("stage busy time: read1 " + fmt_secs(pipe.t_read1.secs()) + ", read2 " + fmt_secs(pipe.t_read2.secs()) +
               ", map (" + std::to_string(cfg.devices.size()) + " GPU) " + fmt_secs(pipe.t_map.secs()) + ", format (" +
               std::to_string(n_threads) + " threads) " + fmt_secs(pipe.t_format.secs()) + ", write " +

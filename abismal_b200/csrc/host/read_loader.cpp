@@ -116,6 +116,10 @@ void FastqReader::push_read(ReadBatch &out, const char *name, size_t name_len, c
     if (b == e)  // reference: substr(npos) throws std::out_of_range
       throw std::runtime_error("basic_string::substr: __pos (which is 18446744073709551615) > "
                                "this->size() (which is " + std::to_string(e) + ")");
+    // Only reachable with characters outside ACGTN (lower case, IUPAC), on which the reference's own
+    // behaviour is undefined: the 5' trim left fewer than min_read_length bases.
+    // The kernels admit no such read; it is skipped like a read with too few non-N bases.
+    if (e - b < min_read_length) b = e = 0;
   }
   out.seq.append(line + b, e - b);
   out.seq_off.push_back(static_cast<uint32_t>(out.seq.size()));

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +37,17 @@ int fail(int code, const std::string &msg) {
       return fail(ABG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+// Grid of the one-off index preparation kernels: `per_sm` CTAs for every SM of the current device.
+int prep_grid(int per_sm) {
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      n_sm < 1) {
+    (void)cudaGetLastError();
+    n_sm = 148;
+  }
+  return n_sm * per_sm;
+}
+
 // Emptiness bitmap of one counter table (bit k = bucket k non-empty).  Kept only when the table is sparse
 // enough for the L2-resident filter to save HBM probes; *out stays null otherwise.
 int make_bitmap(const uint32_t *d_counter, uint64_t n_buckets, uint32_t **out) {
@@ -42,12 +56,18 @@ int make_bitmap(const uint32_t *d_counter, uint64_t n_buckets, uint32_t **out) {
   unsigned long long *d_n = nullptr, n_set = 0;
   const uint64_t words = (n_buckets + 31) / 32;
   ABG_CUDA(cudaMalloc(reinterpret_cast<void **>(&bits), words * 4));
-  ABG_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_n), 8));
-  ABG_CUDA(cudaMemset(d_n, 0, 8));
-  ab2dev::bucket_bitmap_kernel<<<148 * 8, 256>>>(d_counter, n_buckets, bits, d_n);
-  ABG_CUDA(cudaGetLastError());
-  ABG_CUDA(cudaMemcpy(&n_set, d_n, 8, cudaMemcpyDeviceToHost));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_n), 8);
+  if (e == cudaSuccess) e = cudaMemset(d_n, 0, 8);
+  if (e == cudaSuccess) {
+    ab2dev::bucket_bitmap_kernel<<<prep_grid(8), 256>>>(d_counter, n_buckets, bits, d_n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(&n_set, d_n, 8, cudaMemcpyDeviceToHost);
   cudaFree(d_n);
+  if (e != cudaSuccess) {
+    cudaFree(bits);
+    return fail(ABG_ERR_CUDA, std::string("bucket_bitmap_kernel: ") + cudaGetErrorString(e));
+  }
   if (n_set * 2 > n_buckets) {  // dense table: almost every probe would need the counters anyway
     cudaFree(bits);
     return ABG_OK;
@@ -77,6 +97,7 @@ struct abg_index {
   uint32_t *bits = nullptr, *bits_t = nullptr, *bits_a = nullptr;
   uint64_t *g2 = nullptr;
   uint32_t *gx = nullptr;
+  bool has_iupac = false;  // the genome holds multi-bit codes: records near them are sentinels (IndexDev::ctx)
   uint4 *ctx = nullptr, *ctx_t = nullptr, *ctx_a = nullptr;  // seed-context records (IndexDev::ctx)
   uint4 *cc = nullptr;                                        // compact two-letter counters (IndexDev::cc)
   uint64_t cc_bytes = 0;
@@ -143,6 +164,7 @@ struct abg_mapper {
   abg_work_counters counters{};
   uint32_t cur_n = 0;
   bool timed = false;  // ev0/ev1 have been recorded
+  bool run_pending = false;  // abg_mapper_run's error flag has not been looked at yet
 };
 
 namespace {
@@ -212,6 +234,21 @@ void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint
   P.work_counter = work;
   P.error_flag = m->d_work;
   P.counters = m->d_counters;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (kernel, device) pair, not to a mapper: mappers
+// created with different max_read_len on one device (the front end runs two workers per GPU and recreates
+// them as read lengths grow) must never lower it under another mapper's launches.  Only ever raise it.
+std::mutex g_smem_mu;
+std::map<std::pair<int, const void *>, size_t> g_smem_cap;
+
+cudaError_t raise_smem_cap(int device, const void *kernel, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_smem_mu);
+  size_t &cap = g_smem_cap[std::make_pair(device, kernel)];
+  if (bytes <= cap) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cap = bytes;
+  return e;
 }
 
 int launch_one(const void *kernel, int grid, size_t smem, ab2dev::KernelParams &P, cudaStream_t st) {
@@ -362,7 +399,7 @@ void scatter_results(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t
 // After everything has landed: error flag, CIGARs longer than kInlineOps (rare, fetched one by one).
 int finish_results(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t n) {
   if (m->h_flags[0] != 0u)
-    return fail(ABG_ERR_CIGAR_OVERFLOW, "abg_map_batch: a CIGAR needed more than cigar_stride operations");
+    return fail(ABG_ERR_CIGAR_OVERFLOW, "abg_map_batch: a reported CIGAR needed more than cigar_stride operations");
   const uint32_t stride = m->params.cigar_stride;
   const uint32_t w = std::min(kInlineOps, stride);
   uint32_t *const u_cig[2] = {r->cigar1, r->cigar2};
@@ -374,15 +411,16 @@ int finish_results(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t n
     if (n_long == 0) continue;
     if (n_long <= 256) {
       for (uint32_t i = 0; i < n; ++i)
-        if (nc[i] > w)
-          ABG_CUDA(cudaMemcpy(u_cig[e] + (size_t)i * stride, m->d_cigar[e] + (size_t)i * stride, (size_t)nc[i] * 4,
-                              cudaMemcpyDeviceToHost));
+        if (nc[i] > w)  // (a hit that is not reported may have a longer CIGAR than its row: the row is what exists)
+          ABG_CUDA(cudaMemcpy(u_cig[e] + (size_t)i * stride, m->d_cigar[e] + (size_t)i * stride,
+                              (size_t)std::min(nc[i], stride) * 4, cudaMemcpyDeviceToHost));
     }
     else {  // many long CIGARs (long reads, high indel rates): one bulk copy of the full-stride rows
       std::vector<uint32_t> tmp((size_t)n * stride);
       ABG_CUDA(cudaMemcpy(tmp.data(), m->d_cigar[e], tmp.size() * 4, cudaMemcpyDeviceToHost));
       for (uint32_t i = 0; i < n; ++i)
-        if (nc[i] > w) std::memcpy(u_cig[e] + (size_t)i * stride, tmp.data() + (size_t)i * stride, (size_t)nc[i] * 4);
+        if (nc[i] > w)
+          std::memcpy(u_cig[e] + (size_t)i * stride, tmp.data() + (size_t)i * stride, (size_t)std::min(nc[i], stride) * 4);
     }
   }
   return ABG_OK;
@@ -438,35 +476,43 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
   {  // 2-bit genome copy + exception bitmap for the candidate compare
     const uint64_t n2 = (v->genome_words + 1) / 2 + 8;  // spare zero words: look-ahead of the last windows
     const uint64_t nx = (n2 * 32 / 256 + 31) / 32 + 2;
+    uint32_t *d_gi = nullptr;  // blocks holding IUPAC codes; needed only while the records are built
     cudaError_t e1 = cudaMalloc(reinterpret_cast<void **>(&ix->g2), n2 * 8);
     cudaError_t e2 = cudaMalloc(reinterpret_cast<void **>(&ix->gx), nx * 4);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(reinterpret_cast<void **>(&d_gi), nx * 4);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      cudaFree(d_gi);
       abg_index_destroy(ix);
       return fail(ABG_ERR_CUDA, "abg_index_create: out of device memory for the 2-bit genome");
     }
     cudaMemset(ix->gx, 0, nx * 4);
+    cudaMemset(d_gi, 0, nx * 4);
     unsigned int *d_iupac = nullptr, h_iupac = 1;
     if (cudaMalloc(reinterpret_cast<void **>(&d_iupac), 4) != cudaSuccess) {
+      cudaFree(d_gi);
       abg_index_destroy(ix);
       return fail(ABG_ERR_CUDA, "abg_index_create: out of device memory");
     }
     cudaMemset(d_iupac, 0, 4);
-    ab2dev::pack_genome2_kernel<<<148 * 8, 256>>>(ix->genome, v->genome_words + 4, n2, ix->g2, ix->gx, d_iupac);
+    ab2dev::pack_genome2_kernel<<<prep_grid(8), 256>>>(ix->genome, v->genome_words + 4, n2, ix->g2, ix->gx, d_gi, d_iupac);
     cudaError_t e3 = cudaDeviceSynchronize();
     if (e3 == cudaSuccess) e3 = cudaMemcpy(&h_iupac, d_iupac, 4, cudaMemcpyDeviceToHost);
     cudaFree(d_iupac);
     if (e3 != cudaSuccess) {
+      cudaFree(d_gi);
       abg_index_destroy(ix);
       return fail(ABG_ERR_CUDA, std::string("pack_genome2_kernel: ") + cudaGetErrorString(e3));
     }
     ix->dev.g2 = ix->g2;
     ix->dev.gx = ix->gx;
     ix->bytes_extra = n2 * 8 + nx * 4;
+    ix->has_iupac = h_iupac != 0;
     // Seed-context records: 4 x 32 bytes per index entry (21 GB at 3.1 Gbp -- HBM is 180 GB).  They are an
-    // accelerator of the compare, not a different algorithm: without them (genome with IUPAC codes, not
-    // enough memory, ABISMAL_B200_CTX=0) every candidate takes the direct index + genome gather.
+    // accelerator of the compare, not a different algorithm: without them (not enough memory,
+    // ABISMAL_B200_CTX=0) every candidate takes the direct index + genome gather.  In a genome with IUPAC
+    // codes only the entries whose compare window can reach one take that route (sentinel records).
     const char *env = std::getenv("ABISMAL_B200_CTX");
-    if (!(env && env[0] == '0') && h_iupac == 0) {
+    if (!(env && env[0] == '0')) {
       struct Tab {
         const uint32_t *index;
         uint64_t n;
@@ -484,11 +530,13 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
           ok = false;
           break;
         }
-        ab2dev::seed_context_kernel<<<148 * 16, 256>>>(t.index, t.n, ix->g2, *t.dst);
+        ab2dev::seed_context_kernel<<<prep_grid(16), 256>>>(t.index, t.n, ix->g2, ix->has_iupac ? d_gi : nullptr,
+                                                            n2 * 32 / 256 + 1, *t.dst);
         ix->bytes_extra += bytes;
       }
       const cudaError_t e4 = cudaDeviceSynchronize();
       if (e4 != cudaSuccess) {
+        cudaFree(d_gi);
         abg_index_destroy(ix);
         return fail(ABG_ERR_CUDA, std::string("seed_context_kernel: ") + cudaGetErrorString(e4));
       }
@@ -505,13 +553,14 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
       ix->dev.n_ctx = v->index_size;
       ix->dev.n_ctx3 = v->index_size_three;
     }
+    cudaFree(d_gi);
   }
   {  // compact two-letter counters, pinned in L2 by the mappers' streams (ABISMAL_B200_CC=0 disables)
     const char *env = std::getenv("ABISMAL_B200_CC");
     if (!(env && env[0] == '0')) {
       const uint64_t n_blocks = (v->counter_size + ab2dev::kCcKeys - 1) / ab2dev::kCcKeys;
       if (cudaMalloc(reinterpret_cast<void **>(&ix->cc), n_blocks * 32) == cudaSuccess) {
-        ab2dev::compact_counter_kernel<<<148 * 8, 256>>>(ix->counter, v->counter_size, n_blocks, ix->cc);
+        ab2dev::compact_counter_kernel<<<prep_grid(8), 256>>>(ix->counter, v->counter_size, n_blocks, ix->cc);
         const cudaError_t e5 = cudaDeviceSynchronize();
         if (e5 != cudaSuccess) {
           abg_index_destroy(ix);
@@ -574,6 +623,16 @@ void abg_index_destroy(abg_index *ix) {
 }
 
 uint64_t abg_index_device_bytes(const abg_index *ix) { return ix ? ix->bytes + ix->bytes_extra : 0; }
+
+uint32_t abg_index_features(const abg_index *ix) {
+  if (!ix) return 0u;
+  uint32_t f = 0;
+  // the two-letter table always has entries; the three-letter tables may be empty (then they need no records)
+  if (ix->ctx != nullptr && (ix->dev.n_ctx3 == 0 || (ix->ctx_t != nullptr && ix->ctx_a != nullptr))) f |= ABG_FEATURE_SEED_CONTEXT;
+  if (ix->cc != nullptr) f |= ABG_FEATURE_COMPACT_COUNTERS;
+  if (ix->has_iupac) f |= ABG_FEATURE_GENOME_HAS_IUPAC;
+  return f;
+}
 
 int abg_host_alloc(size_t bytes, void **out) {
   if (!out) return fail(ABG_ERR_INVALID, "abg_host_alloc: null argument");
@@ -667,7 +726,7 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   m->kernel = m->minb == 2 ? (const void *)ab2dev::map_reads_kernel<2>
             : m->minb == 4 ? (const void *)ab2dev::map_reads_kernel<4>
                            : (const void *)ab2dev::map_reads_kernel<3>;
-  ABG_M(cudaFuncSetAttribute(m->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  ABG_M(raise_smem_cap(ix->device, m->kernel, m->smem));
   int n_sm = 0, per_sm = 0;
   ABG_M(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ix->device));
   ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->kernel, ab2dev::kThreadsPerBlock, m->smem));
@@ -703,8 +762,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     for (const void *k : {m->kernel, m->kernel_s, m->kernel_a})
       if (cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
         (void)cudaGetLastError();
-    ABG_M(cudaFuncSetAttribute(m->kernel_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_s));
-    ABG_M(cudaFuncSetAttribute(m->kernel_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_a));
+    ABG_M(raise_smem_cap(ix->device, m->kernel_s, m->smem_s));
+    ABG_M(raise_smem_cap(ix->device, m->kernel_a, m->smem_a));
     ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_s, m->kernel_s, ab2dev::kThreadsPerBlock, m->smem_s));
     ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_a, m->kernel_a, ab2dev::kThreadsPerBlock, m->smem_a));
     if (per_s < 1 || per_a < 1) {
@@ -888,7 +947,10 @@ int abg_mapper_run(abg_mapper *m) {
   int rc;
   if ((rc = launch(m, P, m->stream, m->ev_ph)) != ABG_OK) return rc;
   ABG_CUDA(cudaEventRecord(m->ev1, m->stream));
+  // the kernels' error flag travels behind them (4 bytes, outside the timed events); abg_mapper_sync reports it
+  ABG_CUDA(cudaMemcpyAsync(m->h_flags + 1, m->d_work, sizeof(unsigned int), cudaMemcpyDeviceToHost, m->stream));
   m->timed = true;
+  m->run_pending = true;
   return ABG_OK;
 }
 
@@ -920,6 +982,11 @@ int abg_mapper_sync(abg_mapper *m) {
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ABG_CUDA(cudaStreamSynchronize(m->stream));
   read_times(m);
+  if (m->run_pending) {
+    m->run_pending = false;
+    if (m->h_flags[1] != 0u)
+      return fail(ABG_ERR_CIGAR_OVERFLOW, "abg_mapper_run: a reported CIGAR needed more than cigar_stride operations");
+  }
   return ABG_OK;
 }
 
@@ -946,6 +1013,10 @@ int abg_mapper_download(abg_mapper *m, abg_results *r) {
 // H2D copy of chunk j+1 | kernel of chunk j | D2H copy of chunk j-1, so that only the first copy in and the
 // last copy out are exposed.  Pinned caller buffers (abg_host_alloc) are used in place; pageable ones are
 // staged through the mapper's pinned buffers chunk by chunk, which overlaps too.
+namespace {
+int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r);
+}
+
 int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
   int rc;
   if ((rc = check_batch(m, b, "abg_map_batch")) != ABG_OK) return rc;
@@ -953,6 +1024,22 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
   if (m->paired && (!r->pe_r1 || !r->pe_r2 || !r->se2 || !r->n_cigar2))
     return fail(ABG_ERR_INVALID, "abg_map_batch: paired results need pe_r1/pe_r2/se2/n_cigar2");
   ABG_CUDA(cudaSetDevice(m->idx->device));
+  rc = map_batch_impl(m, b, r);
+  if (rc != ABG_OK) {
+    // Nothing may still be in flight when the caller gets its buffers back: copies could be writing into them,
+    // and the front end recycles them.  (The message of the first failure is kept.)
+    const std::string msg = g_err;
+    for (cudaStream_t st : {m->s_h2d, m->s_run[0], m->s_run[1], m->s_d2h, m->s_aux[1], m->s_aux[2]})
+      if (st) (void)cudaStreamSynchronize(st);
+    (void)cudaGetLastError();
+    g_err = msg;
+  }
+  return rc;
+}
+
+namespace {
+int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
+  int rc;
   const uint32_t n = b->n;
   m->cur_n = n;
   m->timed = false;
@@ -971,10 +1058,7 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
     const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
     for (int e = 0; e < n_ends; ++e) {
       const uint32_t *off = offs[e];
-      if ((rc = stage_offsets(m, off, c0, c1, m->h_off[e])) != ABG_OK) {
-        cudaDeviceSynchronize();
-        return rc;
-      }
+      if ((rc = stage_offsets(m, off, c0, c1, m->h_off[e])) != ABG_OK) return rc;
       const size_t o0 = off[c0] - off[0], bytes = off[c1] - off[c0];
       const char *src = seqs[e] + off[c0];
       if (!seq_pinned[e]) {
@@ -1016,6 +1100,7 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
   ABG_CUDA(cudaStreamSynchronize(m->s_d2h));
   return finish_results(m, d, r, n);
 }
+}  // namespace
 
 float abg_mapper_last_kernel_ms(const abg_mapper *m) { return m ? m->last_ms : 0.f; }
 void abg_mapper_last_phase_ms(const abg_mapper *m, float out[3]) {

@@ -86,8 +86,8 @@ struct IndexDev {
   // ctx[a * n_ctx + j] (32 bytes = one sector, g2 word format) holds the 128 genome bases starting at
   // entry - 32 a, a = 0..kCtxArrays-1.  A candidate found at seed offset i reads ONE record (a = min(i / 32,
   // kCtxArrays - 1)) instead of its index entry plus a random genome window; buckets are contiguous in every
-  // array, so the candidates of a bucket share DRAM pages.  Null = not built (no memory, genome with IUPAC
-  // codes, or disabled): every candidate then takes the direct compare.
+  // array, so the candidates of a bucket share DRAM pages.  Null = not built (no memory, or disabled): every
+  // candidate then takes the direct compare.
   const uint4 *ctx, *ctx_t, *ctx_a;
   uint64_t n_ctx, n_ctx3;
   // Compact two-letter counters: block b (32 bytes = one sector) = {counter[28 b], 28 one-byte bucket sizes},
@@ -892,13 +892,16 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
     const uint4 *tab = three ? ctx3 : ix.ctx;
     if (valid[k] && tab != nullptr) {
       // Lower bound of the distance from the 128 genome bases of the record: every compared position adds 0
-      // or 1 (no IUPAC codes in a genome that has records; an N reads as A here and really mismatches), so
-      // more than `bound` mismatches on a subset of the positions already rejects the candidate.
+      // or 1 (entries whose window could hold an IUPAC code carry the sentinel record; an N reads as A here and
+      // really mismatches), so more than `bound` mismatches on a subset of the positions already rejects the
+      // candidate.
       const uint32_t i_off = base_off + (uint32_t)o;
       const uint32_t a = min((uint32_t)(kCtxArrays - 1), i_off >> 5);
       const uint32_t q0 = i_off - 32u * a;  // read position of the record's first base
       uint32_t w[8];
       load_ctx(tab + 2 * ((uint64_t)a * (three ? ix.n_ctx3 : ix.n_ctx) + slot[k]), w);
+      // all-ones = sentinel of an entry near an IUPAC code (seed_context_kernel): no lower bound, compare exactly
+      const bool sentinel = (w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) == ~0u;
       int lb = 0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -912,7 +915,7 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
           lb += __popc(nb >= 32 ? mm : (mm & ((1u << nb) - 1u)));
         }
       }
-      if (lb > bound) {
+      if (lb > bound && !sentinel) {
         valid[k] = false;
         n_entry += 1;
         n_word += 4;
@@ -1786,6 +1789,9 @@ __device__ __noinline__ void best_single(int pe_id, int se_id) {
   res.store(W, se_id);
 }
 
+// format_se's test for writing a record (abismal.cpp:486-487)
+__device__ __forceinline__ bool hit_reported(Hit h, bool allow_ambig) { return !h.empty() && (allow_ambig || !h.ambig()); }
+
 __device__ __forceinline__ abg_hit to_abg(Hit h) {
   abg_hit r;
   r.diffs = (int16_t)h.diffs();
@@ -1825,12 +1831,14 @@ __global__ void bucket_bitmap_kernel(const uint32_t *__restrict__ counter, uint6
 }
 
 // 2-bit copy of the 4-bit genome + exception bits (see IndexDev::g2 / gx).  One thread per 32 bases.
+// gi (same geometry as gx): the block holds a MULTI-bit code (IUPAC R, Y, ...; not N): such a base can match with
+// popcount 2-3 in full_compare, i.e. contribute a negative amount, which the records' lower bound cannot express.
 __global__ void pack_genome2_kernel(const uint64_t *__restrict__ genome, uint64_t n_words4, uint64_t n_words2,
-                                    uint64_t *g2, uint32_t *gx, unsigned int *iupac) {
+                                    uint64_t *g2, uint32_t *gx, uint32_t *gi, unsigned int *iupac) {
   bool multi = false;  // a multi-bit (IUPAC) code was seen: *iupac = 1
   for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words2; w += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = 0;
-    bool bad = false;
+    bool bad = false, multi_here = false;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint64_t x = (2 * w + h) < n_words4 ? genome[2 * w + h] : 0ull;
@@ -1842,13 +1850,15 @@ __global__ void pack_genome2_kernel(const uint64_t *__restrict__ genome, uint64_
         else if (nib == 4u) code = 2;
         else if (nib == 8u) code = 3;
         else if (nib != 1u) bad = true;
-        multi = multi || (nib & (nib - 1u)) != 0u;
+        multi_here = multi_here || (nib & (nib - 1u)) != 0u;
         lo |= (code & 1u) << (16 * h + j);
         hi |= (code >> 1) << (16 * h + j);
       }
     }
     g2[w] = (uint64_t)lo | ((uint64_t)hi << 32);
     if (bad) atomicOr(gx + (w >> 8), 1u << ((w >> 3) & 31u));  // block = (32 w) >> 8 = w >> 3
+    if (multi_here) atomicOr(gi + (w >> 8), 1u << ((w >> 3) & 31u));
+    multi = multi || multi_here;
   }
   if (multi) atomicOr(iupac, 1u);
 }
@@ -1882,14 +1892,35 @@ __global__ void compact_counter_kernel(const uint32_t *__restrict__ counter, uin
 // Seed-context records of one index table (IndexDev::ctx): one thread per (array a, entry j) writes the 128
 // genome bases starting at index[j] - 32 a in g2 word format.  The writes stream; the reads are one random
 // 40-byte window of the 2-bit genome per record (once per index load).
+//
+// gi != nullptr (the genome holds IUPAC codes): an entry whose compare window can reach a block with such a code
+// (any read of up to kCtxReach bases at any seed offset) gets the all-ones SENTINEL record instead, which the
+// prefilter never rejects -- the candidate then takes the exact 4-bit compare.  A real window of 128 T's reads
+// as the sentinel too, which only costs it the prefilter.
+constexpr uint32_t kCtxReach = 4096u + 64u;  // longest admitted read + the look-ahead of the last packed word
 __global__ void seed_context_kernel(const uint32_t *__restrict__ index, uint64_t n, const uint64_t *__restrict__ g2,
-                                    uint4 *ctx) {
+                                    const uint32_t *__restrict__ gi, uint64_t n_blocks, uint4 *ctx) {
   const uint64_t total = n * (uint64_t)kCtxArrays;
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t a = (uint32_t)(t / n);
     const uint32_t e = index[t - (uint64_t)a * n];
     uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    if (e >= 32u * a) {  // always: index entries lie beyond the 32 767-base padding
+    bool near_iupac = false;
+    if (gi != nullptr) {
+      const uint64_t b0 = (e > kCtxReach ? e - kCtxReach : 0u) >> 8;
+      const uint64_t b1 = min(((uint64_t)e + kCtxReach) >> 8, n_blocks - 1);
+      for (uint64_t wd = b0 >> 5; wd <= (b1 >> 5); ++wd) {
+        uint32_t m = __ldg(gi + wd);
+        if (wd == (b0 >> 5)) m &= ~0u << (b0 & 31u);
+        if (wd == (b1 >> 5)) m &= ~0u >> (31u - (uint32_t)(b1 & 31u));
+        near_iupac = near_iupac || m != 0u;
+      }
+    }
+    if (near_iupac) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = ~0u;
+    }
+    else if (e >= 32u * a) {  // always: index entries lie beyond the 32 767-base padding
       const uint32_t p = e - 32u * a, sh = p & 31u;
       const uint64_t *gp = g2 + (p >> 5);
       uint64_t cur = __ldg(gp);
@@ -2039,7 +2070,8 @@ __device__ __forceinline__ void map_one(const Warp &W, unsigned int item) {
     if (lane == 0) {
       P.se[0][item] = to_abg(best);
       P.n_cigar[0][item] = cg_n;
-      if (cg_n > P.cigar_stride) atomicExch(P.error_flag, 1u);
+      // only a CIGAR the caller will read is an error when it does not fit (rejected hits keep their length)
+      if (cg_n > P.cigar_stride && hit_reported(best, P.allow_ambig != 0u)) atomicExch(P.error_flag, 1u);
     }
     __syncwarp();
     if ((uint32_t)lane < P.inline_ops)
@@ -2123,7 +2155,11 @@ __device__ __forceinline__ void map_one(const Warp &W, unsigned int item) {
       P.se[1][item] = to_abg(best_se1);
       P.n_cigar[0][item] = cg[0].n;
       P.n_cigar[1][item] = cg[1].n;
-      if (cg[0].n > cg[0].stride || cg[1].n > cg[1].stride) atomicExch(P.error_flag, 1u);
+      const bool amb_ok = P.allow_ambig != 0u;
+      const bool pair_out = best.should_report(amb_ok);
+      if ((cg[0].n > cg[0].stride && (pair_out || hit_reported(best_se0, amb_ok))) ||
+          (cg[1].n > cg[1].stride && (pair_out || hit_reported(best_se1, amb_ok))))
+        atomicExch(P.error_flag, 1u);
     }
     __syncwarp();
     if ((uint32_t)lane < P.inline_ops) {

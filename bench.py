@@ -1,18 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the `abismal map` hot path on B200.
 
-Workload (BASELINE.json configs[3] shape): synthetic i.i.d. 3.1 Gbp genome,
-150 bp paired-end PBAT reads from the reference's `sim -a`, mapped with -P.
-A "step" maps one batch of --pairs read pairs per GPU; reads are sharded over
-GPUs with the index replicated (weak scaling, no data-path collective; NCCL
-only sums the mapping statistics).
+Workloads (--mode), all on a synthetic i.i.d. 3.1 Gbp genome with reads from the reference's own `sim`:
+  pbat   150 bp paired-end PBAT reads (`sim -a`), mapped with -P      BASELINE configs[3]  (default, the metric)
+  rpbat  150 bp paired-end random-PBAT reads (`sim -R`), mapped -R    BASELINE configs[4]
+  se     150 bp single-end reads (`sim -single`), default mode        BASELINE configs[2]
+A "step" maps one batch per GPU (--pairs read pairs, or 2 x --pairs single-end reads); reads are sharded over
+GPUs with the index replicated (weak scaling, no data-path collective; NCCL only sums the mapping statistics).
 
-  value  reads/s with the batch already resident in HBM (CUDA-event time of
-         the K launches, max over ranks)
-  e2e    reads/s through the public call (abg_map_batch: host buffers in,
-         host buffers out, H2D/D2H inside the timed region)
-  --impl reference   the unmodified reference binary (oracle/_ref/abismal map
-         -t <all cores>) on a bounded sample of the same reads and index.
+  value  reads/s with the batch already resident in HBM (CUDA-event time of the K launches, max over ranks)
+  e2e    reads/s through the public call (abg_map_batch: host buffers in, host buffers out, H2D/D2H inside
+         the timed region)
+  fastq_to_sam   (N = 1) reads/s of the whole front end, `abismal-b200 map` FASTQ -> SAM, i.e. what the
+         reference arm times
+  parity every rank checks the records of the first pairs of its timed batch against the CPU oracle; rank 0
+         (N = 1) also compares the SAM of `abismal-b200 map` with the SAM of the unmodified reference binary
+         on the cpu_baseline sample
+  --impl reference   the unmodified reference binary (oracle/_ref/abismal map -t <all cores>) on bounded
+         samples of the same reads and index.
+
+A rank that fails writes its traceback to stderr and to gpurun_out/bench_logs/rank<r>.log, and rank 0 prints
+a JSON line carrying every rank's error before the process group exits non-zero.
 """
 import argparse
 import json
@@ -22,17 +30,43 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "mapped reads/sec (150bp PE bisulfite, 3.1 Gbp genome)"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "abismal")
+CLI = os.path.join(ROOT, "abismal_b200", "bin", "abismal-b200")
+
+MODES = {
+    # sim flag, map flags, paired, metric, workload text
+    "pbat": ("-a", ["-P"], True, "mapped reads/sec (150bp PE bisulfite, 3.1 Gbp genome)",
+             "150bp PE PBAT reads (sim -a -m 0.01 -b 0.98, fragments 150-400), abismal map -P", "configs[3]"),
+    "rpbat": ("-R", ["-R"], True, "mapped reads/sec (150bp PE random-PBAT bisulfite, 3.1 Gbp genome)",
+              "150bp PE random-PBAT reads (sim -R -m 0.01 -b 0.98, fragments 150-400), abismal map -R", "configs[4]"),
+    "se": (None, [], False, "mapped reads/sec (150bp SE bisulfite, 3.1 Gbp genome)",
+           "150bp SE reads (sim -single -m 0.01 -b 0.98), abismal map", "configs[2]"),
+}
+
+RANK = int(os.environ.get("RANK", "0"))
 
 
 def log(*a):
-    if int(os.environ.get("RANK", "0")) == 0:
+    if RANK == 0:
         print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def rank_log(text):
+    """Every rank: stderr and a file that survives torchrun's summary."""
+    sys.stderr.write("[bench rank %d] %s\n" % (RANK, text))
+    sys.stderr.flush()
+    try:
+        d = os.path.join(ROOT, "gpurun_out", "bench_logs")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "rank%d.log" % RANK), "a") as f:
+            f.write(text + "\n")
+    except OSError:
+        pass
 
 
 def hbm_peak():
@@ -86,32 +120,63 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def sample_fastq(src, dst, n_records):
+def sample_fastq(src, dst, first, count):
+    """Records [first, first + count) of a 4-line-record FASTQ."""
     with open(src, "rb") as fi, open(dst, "wb") as fo:
         for k, ln in enumerate(fi):
-            if k >= 4 * n_records:
+            if k < 4 * first:
+                continue
+            if k >= 4 * (first + count):
                 break
             fo.write(ln)
 
 
-def run_reference_map(index_path, fq1, fq2, n_threads, extra=("-P",)):
-    """-> (mapping seconds, loading seconds); mapping = wall - index loading (-v log line)."""
-    out = os.path.join(os.path.dirname(fq1), "ref_sample.sam")
-    cmd = [REF_BIN, "map", "-v", "-t", str(n_threads)] + list(extra) + ["-i", index_path, "-o", out, fq1] + ([fq2] if fq2 else [])
+def _map_seconds(cmd):
+    """Run a `map -v` command -> (mapping seconds = wall - index loading, loading seconds, stderr)."""
     t = time.perf_counter()
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     wall = time.perf_counter() - t
     if p.returncode != 0:
-        raise RuntimeError("reference map failed: " + p.stderr[-500:])
+        raise RuntimeError("%s failed: %s" % (" ".join(cmd[:3]), p.stderr[-800:]))
     load = 0.0
     for ln in p.stderr.splitlines():
         if "loading time:" in ln:
             load = float(ln.split("loading time:")[1].strip().rstrip("s"))
-    try:
-        os.remove(out)
-    except OSError:
-        pass
-    return wall - load, load
+    return wall - load, load, p.stderr
+
+
+def run_reference_map(index_path, fqs, n_threads, flags, out_sam):
+    return _map_seconds([REF_BIN, "map", "-v", "-t", str(n_threads)] + list(flags) +
+                        ["-i", index_path, "-o", out_sam] + list(fqs))[:2]
+
+
+def run_cli_map(index_path, fqs, flags, out_sam, extra=()):
+    """`abismal-b200 map` FASTQ -> SAM.  -> (mapping seconds incl. the index upload to HBM, stage busy times text,
+    seconds of that upload)"""
+    secs, load, err = _map_seconds([CLI, "map", "-v"] + list(extra) + list(flags) + ["-i", index_path, "-o", out_sam] + list(fqs))
+    stages, upload = "", 0.0
+    for ln in err.splitlines():
+        if "total mapping time:" in ln:
+            secs = float(ln.split("total mapping time:")[1].strip().rstrip("s"))
+        if "index upload to HBM:" in ln:
+            upload = float(ln.split("index upload to HBM:")[1].split("s")[0])
+        if "stage busy time:" in ln:
+            stages = ln.split("stage busy time:")[1].strip()
+    return secs, stages, upload
+
+
+def sam_records_differing(a_path, b_path):
+    """SAM bodies (no @PG) compared as sorted multisets: the reference with -t > 1 writes its 1000-read batches in
+    the order its threads finish (Threading).  -> (records in a, records that differ)"""
+    def body(p):
+        with open(p, "rb") as f:
+            return sorted(ln for ln in f if not ln.startswith(b"@PG"))
+    a, b = body(a_path), body(b_path)
+    if a == b:
+        return len(a), 0
+    from collections import Counter
+    ca, cb = Counter(a), Counter(b)
+    return len(a), sum(((ca - cb) + (cb - ca)).values())
 
 
 def algorithmic_bytes(counters, units):
@@ -122,33 +187,75 @@ def algorithmic_bytes(counters, units):
             0.5 * c["n_dpref"] / units)
 
 
+class RankSync:
+    """Keeps the ranks in step through failures: after every phase all ranks learn whether any of them failed,
+    so nobody is left waiting in a barrier for a rank that raised."""
+
+    def __init__(self, dist, use_dist, world):
+        self.dist, self.use_dist, self.world = dist, use_dist, world
+        self.error = None
+
+    def run(self, what, fn):
+        """fn() on this rank unless an earlier phase failed somewhere; -> fn's value or None."""
+        val = None
+        if self.error is None:
+            try:
+                val = fn()
+            except BaseException:  # incl. SystemExit from helpers
+                self.error = "%s: %s" % (what, traceback.format_exc())
+                rank_log("FAILED in " + self.error)
+        self.check()
+        return val
+
+    def check(self):
+        if not self.use_dist:
+            if self.error is not None:
+                self.finish()
+            return
+        errs = [None] * self.world
+        self.dist.all_gather_object(errs, self.error)
+        if any(e is not None for e in errs):
+            self.finish(errs)
+
+    def finish(self, errs=None):
+        errs = errs if errs is not None else [self.error]
+        if RANK == 0:
+            print(json.dumps({"error": "bench failed", "ranks": {str(r): e for r, e in enumerate(errs) if e is not None}}))
+            sys.stdout.flush()
+        if self.use_dist:
+            try:
+                self.dist.destroy_process_group()
+            except Exception:
+                pass
+        sys.exit(1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="pbat", choices=sorted(MODES))
     ap.add_argument("--genome-bases", type=float, default=3.1e9)
-    ap.add_argument("--pairs", type=int, default=1 << 20, help="read pairs per GPU per step")
-    ap.add_argument("--cpu-sample-pairs", type=int, default=200000)
+    ap.add_argument("--pairs", type=int, default=1 << 20, help="read pairs (or pairs of single-end reads) per GPU per step")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=200000,
+                    help="pairs per run of the reference binary (cpu_baseline, and every step of --impl reference)")
+    ap.add_argument("--parity-pairs", type=int, default=4000, help="pairs per rank checked against the CPU oracle")
     ap.add_argument("--seed", type=int, default=20251017)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the FASTQ->SAM leg and the SAM comparison with the reference")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
 
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    genome_bases = int(args.genome_bases)
-    n_cpu = os.cpu_count() or 1
-
-    if args.impl == "reference" and rank != 0:
+    if args.impl == "reference" and RANK != 0:
         return 0
 
     import torch  # plumbing: device selection, NCCL, barriers
     import torch.distributed as dist
-    from abismal_b200 import workload
 
     if not torch.cuda.is_available():
         if args.impl == "reference":
@@ -159,46 +266,83 @@ def main():
     use_dist = world > 1 and args.impl == "ours"
     if use_dist:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sync = RankSync(dist, use_dist, world)
+    try:
+        return run(args, sync, torch, dist, local_rank, world, use_dist)
+    except SystemExit:
+        raise
+    except BaseException:
+        rank_log("FAILED outside a phase: " + traceback.format_exc())
+        raise
+
+
+def run(args, sync, torch, dist, local_rank, world, use_dist):
+    from abismal_b200 import workload
+    rank = RANK
+    sim_flag, map_flags, paired, metric, wl_text, cfg_name = MODES[args.mode]
+    genome_bases = int(args.genome_bases)
+    n_cpu = os.cpu_count() or 1
+    n_units = args.pairs if paired else 2 * args.pairs   # work items (pairs / single-end reads) per GPU per step
+    reads_per_unit = 2 if paired else 1
+    unit = "pairs" if paired else "reads"
 
     # ---- workload (untimed): genome, index, reads --------------------------------
-    paths = None
-    ixf = None
-    if rank == 0:
-        ixf, paths = workload.get_index(genome_bases, args.seed, device=local_rank, need_files=True, log=log)
-    if use_dist:
-        dist.barrier()
-    if ixf is None:
-        ixf, paths = workload.get_index(genome_bases, args.seed, device=local_rank, need_files=True, log=log)
-    sim_procs = max(1, min(16, n_cpu // max(world, 1)))
-    prefix = os.path.join(paths["dir"], "pbat_n%d_r%d" % (args.pairs, rank))
-    fq1, fq2 = workload.simulate_reads(REF_BIN, paths["fasta"], prefix, args.pairs, seed=args.seed % 1000 + rank,
-                                       paired=True, mode_flag="-a", n_procs=sim_procs, log=log)
+    state = {}
+
+    def prep_index():
+        if rank == 0:
+            state["ixf"], state["paths"] = workload.get_index(genome_bases, args.seed, device=local_rank, need_files=True, log=log)
+    sync.run("index preparation (rank 0)", prep_index)
+
+    def prep_reads():
+        if "ixf" not in state:
+            state["ixf"], state["paths"] = workload.get_index(genome_bases, args.seed, device=local_rank, need_files=True, log=log)
+        paths = state["paths"]
+        sim_procs = int(os.environ.get("ABISMAL_B200_SIM_PROCS", "0")) or max(1, min(16, n_cpu // max(world, 1)))
+        prefix = os.path.join(paths["dir"], "%s_n%d_r%d" % (args.mode, n_units, rank))
+        state["prefix"] = prefix
+        fq1, fq2 = workload.simulate_reads(REF_BIN, paths["fasta"], prefix, n_units, seed=args.seed % 1000 + rank,
+                                           paired=paired, mode_flag=sim_flag, n_procs=sim_procs, log=log)
+        state["fqs"] = [fq1, fq2] if paired else [fq1]
+    sync.run("read simulation", prep_reads)
+    paths, prefix, fqs, ixf = state["paths"], state["prefix"], state["fqs"], state["ixf"]
 
     config = {
-        "workload": "synthetic i.i.d. %.2f Gbp genome (24 chroms), 150bp PE PBAT reads (sim -a -m 0.01 -b 0.98, "
-                    "fragments 150-400), abismal map -P; one batch of %d pairs per GPU per step "
-                    "(BASELINE configs[3] shape)" % (genome_bases / 1e9, args.pairs),
-        "pairs_per_gpu_per_step": args.pairs,
+        "workload": "synthetic i.i.d. %.2f Gbp genome (24 chroms), %s; one batch of %d %s per GPU per step "
+                    "(BASELINE %s shape)" % (genome_bases / 1e9, wl_text, n_units, unit, cfg_name),
+        "%s_per_gpu_per_step" % unit: n_units,
         "index": "replicated per GPU, built on GPU (byte-identical to `abismal idx`)",
         "parallelism": "reads sharded x%d, no data-path collective" % world,
         "l2": "inputs larger than L2: %.1f GB index gathered at random + %.0f MB of reads per step"
-              % (2.7 * genome_bases / 3.1e9, args.pairs * 300 / 1e6),
+              % (2.7 * genome_bases / 3.1e9, n_units * reads_per_unit * 150 / 1e6),
     }
 
     if args.impl == "reference":
-        # ---- reference arm: unmodified reference binary, all host cores, bounded sample ----
-        n_s = min(args.cpu_sample_pairs, args.pairs)
-        s1, s2 = prefix + "_sample_1.fq", prefix + "_sample_2.fq"
-        sample_fastq(fq1, s1, n_s)
-        sample_fastq(fq2, s2, n_s)
-        for _ in range(args.warmup):
-            run_reference_map(paths["index"], s1, s2, n_cpu)
-        secs = [run_reference_map(paths["index"], s1, s2, n_cpu)[0] for _ in range(args.steps)]
+        # ---- reference arm: unmodified reference binary, all host cores, bounded samples -------------------
+        # every step maps the NEXT --cpu-sample-pairs units of the step batch (wrapping around), so K steps cover
+        # K x sample distinct reads of the same workload
+        n_s = min(args.cpu_sample_pairs, n_units)
+        out_sam = prefix + "_ref_step.sam"
+        secs = []
+        for k in range(args.warmup + args.steps):
+            first = (k * n_s) % max(1, n_units - n_s + 1)
+            s = [prefix + "_refstep_%d.fq" % (e + 1) for e in range(len(fqs))]
+            for src, dst in zip(fqs, s):
+                sample_fastq(src, dst, first, n_s)
+            t, _ = run_reference_map(paths["index"], s, n_cpu, map_flags, out_sam)
+            if k >= args.warmup:
+                secs.append(t)
+        for f in [out_sam] + s:
+            try:
+                os.remove(f)
+            except OSError:
+                pass
         total = sum(secs)
-        value = 2.0 * n_s * args.steps / total
-        sample = "first %d pairs of the step batch per step, abismal map -t %d -P (mapping time = wall - index loading)" % (n_s, n_cpu)
+        value = reads_per_unit * n_s * args.steps / total
+        sample = ("%d %s of the step batch per step (a different slice every step, %d %s timed in all), abismal map -t %d %s "
+                  "FASTQ -> SAM (mapping time = wall - index loading)" % (n_s, unit, n_s * args.steps, unit, n_cpu, " ".join(map_flags)))
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+            "impl": "reference", "metric": metric, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u64",
             "data": "synthetic", "config": config,
@@ -208,18 +352,23 @@ def main():
         return 0
 
     # ---- our arm -----------------------------------------------------------------
-    from abismal_b200 import Index, Mapper, MODE_A_RICH, MODE_PAIRED
+    from abismal_b200 import Index, Mapper, MODE_A_RICH, MODE_PAIRED, MODE_RANDOM_PBAT
     from abismal_b200.capi import Results
-    t = time.time()
-    b1, b2 = workload.load_fastq_fast(fq1), workload.load_fastq_fast(fq2)
-    log("reads loaded in %.1fs" % (time.time() - t))
-    t = time.time()
-    ix = Index(ixf, local_rank)
-    log("index resident in HBM: %.2f GB, uploaded in %.1fs" % (ix.device_bytes / 1e9, time.time() - t))
-    mode = MODE_PAIRED | MODE_A_RICH
-    m = Mapper(ix, mode=mode, max_batch=b1.n, max_read_len=max(b1.max_len, b2.max_len, 64))
-    res = Results(b1.n, True, m.stride, pinned=True)
-    b1, b2 = b1.to_pinned(), b2.to_pinned()  # the e2e leg copies each step's inputs from pinned host memory
+    mode = {"pbat": MODE_PAIRED | MODE_A_RICH, "rpbat": MODE_PAIRED | MODE_RANDOM_PBAT, "se": 0}[args.mode]
+
+    def setup():
+        t = time.time()
+        b = [workload.load_fastq_fast(f) for f in fqs]
+        log("reads loaded in %.1fs" % (time.time() - t))
+        t = time.time()
+        ix = Index(ixf, local_rank)
+        log("index resident in HBM: %.2f GB, uploaded in %.1fs, features %d" % (ix.device_bytes / 1e9, time.time() - t, ix.features))
+        m = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max([x.max_len for x in b] + [64]))
+        res = Results(b[0].n, paired, m.stride, pinned=True)
+        b = [x.to_pinned() for x in b]  # the e2e leg copies each step's inputs from pinned host memory
+        state.update(b=b, ix=ix, m=m, res=res)
+    sync.run("setup (reads, index upload, mapper)", setup)
+    b, ix, m, res = state["b"], state["ix"], state["m"], state["res"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -228,130 +377,206 @@ def main():
         torch.cuda.synchronize()
 
     # device-resident leg
-    m.upload(b1, b2)
-    m.sync()
-    for _ in range(args.warmup):
-        m.run()
+    def warm():
+        m.upload(*b)
         m.sync()
+        for _ in range(args.warmup):
+            m.run()
+            m.sync()
+    sync.run("upload + warm-up", warm)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    kernel_ms, phase_ms = [], [0.0, 0.0, 0.0]
-    for _ in range(args.steps):
-        m.run()
-        m.sync()
-        kernel_ms.append(m.last_kernel_ms)
-        phase_ms = [a + b for a, b in zip(phase_ms, m.last_phase_ms)]
+
+    def timed_device():
+        kernel_ms, phase_ms = [], [0.0, 0.0, 0.0]
+        for _ in range(args.steps):
+            m.run()
+            m.sync()
+            kernel_ms.append(m.last_kernel_ms)
+            phase_ms = [x + y for x, y in zip(phase_ms, m.last_phase_ms)]
+        state.update(dev_ms=sum(kernel_ms), phase_ms=phase_ms)
+    sync.run("device-resident leg", timed_device)
     barrier()
-    dev_ms = sum(kernel_ms)
+    dev_ms, phase_ms = state["dev_ms"], state["phase_ms"]
     launches = args.steps * m.launches_per_run
 
     # end-to-end leg through the public call
-    for _ in range(2):
-        m.map_batch(b1, b2, res)
+    def warm_e2e():
+        for _ in range(2):
+            m.map_batch(*b, results=res)
+    sync.run("e2e warm-up", warm_e2e)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        m.map_batch(b1, b2, res)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+
+    def timed_e2e():
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m.map_batch(*b, results=res)
+        torch.cuda.synchronize()
+        state["e2e_s"] = time.perf_counter() - t0
+    sync.run("e2e leg", timed_e2e)
     barrier()
+    e2e_s = state["e2e_s"]
     clocks = sampler.stop()
 
-    mapped_pairs = int((res.pe_r1["pos"] != 0).sum())
-    stats = torch.tensor([dev_ms, e2e_s, float(b1.n), float(mapped_pairs)], dtype=torch.float64, device="cuda")
+    # ---- parity of this rank's timed batch against the CPU oracle (checker only) -------------------------
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    n_o = min(args.parity_pairs, b[0].n)
+
+    def parity():
+        import helpers
+        o = helpers.OracleMapper(ixf, mode=mode)
+        t = time.perf_counter()
+        want = o.map_batch(*[x.slice(0, n_o) for x in b])
+        state["port_s"] = time.perf_counter() - t
+        keys = ("se1", "n_cigar1") + (("pe_r1", "pe_r2", "se2", "n_cigar2") if paired else ())
+        bad = 0
+        for k in keys:
+            bad += int((getattr(res, k)[:n_o] != getattr(want, k)[:n_o]).sum())
+        # CIGAR operations of the checked records
+        for e in (1, 2) if paired else (1,):
+            cg, ng = (res.cigar1, res.n_cigar1) if e == 1 else (res.cigar2, res.n_cigar2)
+            cw, nw = (want.cigar1, want.n_cigar1) if e == 1 else (want.cigar2, want.n_cigar2)
+            for i in range(n_o):
+                k = min(int(ng[i]), cg.shape[1])
+                if int(ng[i]) == int(nw[i]) and not (cg[i, :k] == cw[i, :k]).all():
+                    bad += 1
+        state["bad"] = bad
+        state["oracle_counters"] = o.counters.as_dict()
+        o.close()
+        if bad:
+            raise RuntimeError("%d result records differ from the CPU oracle on the first %d %s of rank %d's batch"
+                               % (bad, n_o, unit, rank))
+    sync.run("parity against the CPU oracle", parity)
+
+    mapped = int(((res.pe_r1 if paired else res.se1)["pos"] != 0).sum())
+    stats = torch.tensor([dev_ms, e2e_s, float(b[0].n), float(mapped), float(state["bad"]), float(n_o)],
+                         dtype=torch.float64, device="cuda")
     if use_dist:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)  # NCCL: the only collective (mapping statistics)
         dev_ms_max, e2e_max = float(mx[0]), float(mx[1])
-        total_pairs, total_mapped = float(sm[2]), float(sm[3])
+        total_units, total_mapped, total_bad, total_checked = float(sm[2]), float(sm[3]), int(sm[4]), int(sm[5])
     else:
-        dev_ms_max, e2e_max, total_pairs, total_mapped = dev_ms, e2e_s, float(b1.n), float(mapped_pairs)
+        dev_ms_max, e2e_max, total_units, total_mapped = dev_ms, e2e_s, float(b[0].n), float(mapped)
+        total_bad, total_checked = state["bad"], n_o
 
     if rank == 0:
-        value = 2.0 * total_pairs * args.steps / (dev_ms_max / 1e3)
-        e2e_value = 2.0 * total_pairs * args.steps / e2e_max
-        out = {
-            "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int16/u64", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": b1.h2d_bytes + b2.h2d_bytes,
-                    "d2h_bytes_per_step": res.d2h_bytes(), "ms_per_step": 1e3 * e2e_max / args.steps},
-            "gpu_launches": launches * world, "clocks": clocks,
-            "pairs_mapped_frac": total_mapped / total_pairs,
-        }
-        config["pairs_per_s"] = value / 2.0
-        # ---- roofline + CPU baseline (rank 0, N = 1) -----------------------------
-        if world == 1 and not args.no_cpu_baseline:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import helpers
-            peak, peak_src = hbm_peak()
-            n_o = min(4000, b1.n)
-            o = helpers.OracleMapper(ixf, mode=mode)
-            t = time.perf_counter()
-            want = o.map_batch(b1.slice(0, n_o), b2.slice(0, n_o))
-            port_s = time.perf_counter() - t
-            # parity at the full configuration: the records the timed e2e leg produced for these pairs against
-            # the CPU oracle (checker only; position, flags, NM of pe.r1/pe.r2/se1/se2 and the CIGAR lengths)
-            bad = 0
-            for k in ("se1", "n_cigar1", "pe_r1", "pe_r2", "se2", "n_cigar2"):
-                bad += int((getattr(res, k)[:n_o] != getattr(want, k)[:n_o]).sum())
-            out["parity"] = {"pairs_checked": n_o, "mismatching_records": bad, "against": "CPU oracle (oracle/abismal_oracle.cpp)"}
-            if bad:
-                raise SystemExit("bench: %d result records differ from the oracle on the first %d pairs" % (bad, n_o))
-            seed_bytes, dp_bytes = algorithmic_bytes(o.counters.as_dict(), n_o)
-            o.close()
-            # dominant kernel: seed_kernel (seed hashing, counter/index lookups, packed compare, candidate sets);
-            # its launch time comes from CUDA events recorded on the launching stream between the kernels
-            names = ("seed_kernel", "align_kernel", "map_reads_kernel(redo)")
-            per_kernel = {nm: {"ms_per_launch": t / args.steps, "share_of_step": t / dev_ms}
-                          for nm, t in zip(names, phase_ms)}
-            ms_per_launch = phase_ms[0] / args.steps
-            bytes_per_pair = seed_bytes
-            achieved = bytes_per_pair * b1.n / (ms_per_launch / 1e3) / 1e9
-            traffic, gather = None, None
-            try:
-                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    tj = json.load(f)
-                if not tj.get("kernel", "").startswith("seed_kernel"):
-                    raise KeyError("traffic.json is not a seed_kernel capture")
-                # ncu --set full capture of the same kernel on a 262144-pair batch of the same reads,
-                # scaled to this launch's batch (the kernel's work is linear in the number of pairs)
-                traffic = float(tj["dram_bytes_per_pair"]) * b1.n
-                sect_s = float(tj["l1_miss_sectors_per_pair"]) * b1.n / (ms_per_launch / 1e3) / 1e9
-                gather = {"achieved_gsectors_per_s": sect_s,
-                          "ceiling_gsectors_per_s": float(tj["random_gather_ceiling_gsectors_per_s"]),
-                          "frac": sect_s / float(tj["random_gather_ceiling_gsectors_per_s"]),
-                          "note": "32-byte L1-miss sectors per second vs the random-gather ceiling measured with "
-                                  "tools/micro/gather_bench3.cu; this, not streaming bandwidth, bounds the kernel"}
-                if "dram_sectors_read_per_pair" in tj and "bucket_contiguous_ceiling_gsectors_per_s" in tj:
-                    dsec = float(tj["dram_sectors_read_per_pair"]) * b1.n / (ms_per_launch / 1e3) / 1e9
-                    gather["dram_gsectors_per_s"] = dsec
-                    gather["bucket_contiguous_ceiling_gsectors_per_s"] = float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
-                    gather["dram_frac_of_contiguous_ceiling"] = dsec / float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
-            except Exception:
-                pass
-            out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                               "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                               "algorithmic_bytes_per_pair": bytes_per_pair,
-                               "algorithmic_bytes_per_pair_whole_path": seed_bytes + dp_bytes,
-                               "kernel": "seed_kernel", "ms_per_launch": ms_per_launch, "kernels": per_kernel,
-                               "counters_from": "CPU oracle on the first %d pairs of the batch" % n_o,
-                               "random_gather": gather}
-            n_s = min(args.cpu_sample_pairs, b1.n)
-            s1, s2 = prefix + "_sample_1.fq", prefix + "_sample_2.fq"
-            sample_fastq(fq1, s1, n_s)
-            sample_fastq(fq2, s2, n_s)
-            secs, load = run_reference_map(paths["index"], s1, s2, n_cpu)
-            out["cpu_baseline"] = {
-                "value": 2.0 * n_s / secs, "unit": "reads/s", "cores": n_cpu, "kind": "reference",
-                "sample": "first %d pairs of the batch, oracle/_ref/abismal map -t %d -P, mapping time = wall - "
-                          "index loading (%.1fs)" % (n_s, n_cpu, load),
-                "port_single_thread_reads_per_s": 2.0 * n_o / port_s,
+        def finish_line():
+            value = reads_per_unit * total_units * args.steps / (dev_ms_max / 1e3)
+            e2e_value = reads_per_unit * total_units * args.steps / e2e_max
+            out = {
+                "metric": metric, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int16/u64", "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": sum(x.h2d_bytes for x in b),
+                        "d2h_bytes_per_step": res.d2h_bytes(), "ms_per_step": 1e3 * e2e_max / args.steps,
+                        "through": "abg_map_batch (C ABI): host buffers in, host buffers out; the reference arm it is divided "
+                                   "by also parses FASTQ and writes SAM -- see fastq_to_sam for the like-for-like number"},
+                "gpu_launches": launches * world, "clocks": clocks,
+                "%s_per_s" % unit: value / reads_per_unit,
+                "%s_mapped_frac" % unit: total_mapped / total_units,
+                "parity": {"%s_checked" % unit: total_checked, "ranks_checked": world, "mismatching_records": total_bad,
+                           "against": "CPU oracle (oracle/abismal_oracle.cpp), first %d %s of every rank's timed batch" % (n_o, unit)},
             }
-        print(json.dumps(out))
+            names = ("seed_kernel", "align_kernel", "map_reads_kernel(redo)")
+            out["kernels"] = {nm: {"ms_per_launch": t / args.steps, "share_of_step": t / dev_ms}
+                              for nm, t in zip(names, phase_ms)}
+            # ---- roofline + CPU baseline + front end (rank 0, N = 1) -------------------
+            if world == 1 and not args.no_cpu_baseline:
+                peak, peak_src = hbm_peak()
+                seed_bytes, dp_bytes = algorithmic_bytes(state["oracle_counters"], n_o)
+                # dominant kernel: seed_kernel (seed hashing, counter/index lookups, packed compare, candidate sets);
+                # its launch time comes from CUDA events recorded on the launching stream between the kernels
+                ms_per_launch = phase_ms[0] / args.steps
+                achieved = seed_bytes * b[0].n / (ms_per_launch / 1e3) / 1e9
+                traffic, gather = None, None
+                try:
+                    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                        tj = json.load(f)
+                    tj = tj.get(args.mode, tj if args.mode == "pbat" else None)
+                    if tj is None or not tj.get("kernel", "").startswith("seed_kernel"):
+                        raise KeyError("traffic.json holds no seed_kernel capture for this mode")
+                    # ncu --set full capture of the same kernel on a smaller batch of the same reads, scaled to
+                    # this launch's batch (the kernel's work is linear in the number of pairs)
+                    per = float(tj.get("units_per_pair", 1.0))
+                    traffic = float(tj["dram_bytes_per_pair"]) * b[0].n / per
+                    sect_s = float(tj["l1_miss_sectors_per_pair"]) * b[0].n / per / (ms_per_launch / 1e3) / 1e9
+                    gather = {"achieved_gsectors_per_s": sect_s,
+                              "ceiling_gsectors_per_s": float(tj["random_gather_ceiling_gsectors_per_s"]),
+                              "frac": sect_s / float(tj["random_gather_ceiling_gsectors_per_s"]),
+                              "note": "32-byte L1-miss sectors per second vs the random-gather ceiling measured with "
+                                      "tools/micro/gather_bench3.cu; this, not streaming bandwidth, bounds the kernel"}
+                    if "dram_sectors_read_per_pair" in tj and "bucket_contiguous_ceiling_gsectors_per_s" in tj:
+                        dsec = float(tj["dram_sectors_read_per_pair"]) * b[0].n / per / (ms_per_launch / 1e3) / 1e9
+                        gather["dram_gsectors_per_s"] = dsec
+                        gather["bucket_contiguous_ceiling_gsectors_per_s"] = float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
+                        gather["dram_frac_of_contiguous_ceiling"] = dsec / float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
+                except Exception:
+                    pass
+                out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                   "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                                   "algorithmic_bytes_per_%s" % unit[:-1]: seed_bytes,
+                                   "algorithmic_bytes_per_%s_whole_path" % unit[:-1]: seed_bytes + dp_bytes,
+                                   "whole_step_frac": (seed_bytes + dp_bytes) * b[0].n / (dev_ms / args.steps / 1e3) / 1e9 / peak,
+                                   "kernel": "seed_kernel", "ms_per_launch": ms_per_launch, "kernels": out["kernels"],
+                                   "counters_from": "CPU oracle on the first %d %s of the batch" % (n_o, unit),
+                                   "random_gather": gather}
+                n_s = min(args.cpu_sample_pairs, b[0].n)
+                s = [prefix + "_sample_%d.fq" % (e + 1) for e in range(len(fqs))]
+                for src, dst in zip(fqs, s):
+                    sample_fastq(src, dst, 0, n_s)
+                ref_sam = prefix + "_sample_ref.sam"
+                secs, load = run_reference_map(paths["index"], s, n_cpu, map_flags, ref_sam)
+                out["cpu_baseline"] = {
+                    "value": reads_per_unit * n_s / secs, "unit": "reads/s", "cores": n_cpu, "kind": "reference",
+                    "sample": "first %d %s of the batch, oracle/_ref/abismal map -t %d %s, FASTQ -> SAM, mapping time = wall - "
+                              "index loading (%.1fs)" % (n_s, unit, n_cpu, " ".join(map_flags), load),
+                    "port_single_thread_reads_per_s": reads_per_unit * n_o / state["port_s"],
+                }
+                if not args.no_cli:
+                    # the same sample through `abismal-b200 map`: SAM identical to the reference binary's (modulo @PG)?
+                    ours_sam = prefix + "_sample_ours.sam"
+                    run_cli_map(paths["index"], s, map_flags, ours_sam)  # raises when the front end fails
+                    n_rec, n_diff = sam_records_differing(ref_sam, ours_sam)
+                    out["parity"]["reference_binary"] = {
+                        "%s_checked" % unit: n_s, "sam_records": n_rec, "mismatching_records": n_diff,
+                        "against": "SAM of the unmodified reference binary (oracle/_ref/abismal map -t %d) on the same FASTQ "
+                                   "sample and index, records compared as a sorted multiset, @PG excluded" % n_cpu}
+                    # the whole front end on the whole step batch: FASTQ -> SAM (what the reference arm times)
+                    big_sam = prefix + "_cli.sam"
+                    best = None
+                    for _ in range(2):
+                        r = run_cli_map(paths["index"], fqs, map_flags, big_sam)
+                        if best is None or r[0] < best[0]:
+                            best = r
+                    out["fastq_to_sam"] = {"value": reads_per_unit * b[0].n / best[0], "unit": "reads/s",
+                                           "value_excluding_index_upload": reads_per_unit * b[0].n / max(best[0] - best[2], 1e-9),
+                                           "%s" % unit: b[0].n, "seconds": best[0], "index_upload_seconds": best[2],
+                                           "stage_busy_time": best[1],
+                                           "through": "abismal-b200 map -v %s -i <index> -o <sam> <fastq...>, files on %s; seconds = "
+                                                      "the front end's total mapping time, which includes copying the index to "
+                                                      "HBM and deriving the seed-context records (a fixed cost per run that "
+                                                      "the reference's loading time corresponds to)"
+                                                      % (" ".join(map_flags), os.path.dirname(big_sam))}
+                    for f in (ours_sam, big_sam):
+                        try:
+                            os.remove(f)
+                        except OSError:
+                            pass
+                    if n_diff:
+                        raise RuntimeError("%d SAM records differ from the reference binary on %d %s" % (n_diff, n_s, unit))
+                try:
+                    os.remove(ref_sam)
+                except OSError:
+                    pass
+            print(json.dumps(out))
+            sys.stdout.flush()
+        sync.run("result line (roofline, cpu_baseline, front end)", finish_line)
+    else:
+        sync.check()
     m.close()
     ix.close()
     if use_dist:

@@ -145,6 +145,14 @@ int abg_device_count(void);
 int abg_index_create(const abg_index_view *view, int device, abg_index **out);
 void abg_index_destroy(abg_index *idx);
 uint64_t abg_index_device_bytes(const abg_index *idx);
+/* Which derived arrays the index holds next to the file's seven (they only accelerate the same lookups; results
+ * never depend on them): bit set = present.  GENOME_HAS_IUPAC: the genome holds multi-bit codes, the candidates
+ * whose compare window can reach one take the exact 4-bit full_compare (abismal.cpp:1105-1122) instead of the
+ * seed-context prefilter. */
+#define ABG_FEATURE_SEED_CONTEXT 1u
+#define ABG_FEATURE_COMPACT_COUNTERS 2u
+#define ABG_FEATURE_GENOME_HAS_IUPAC 4u
+uint32_t abg_index_features(const abg_index *idx);
 
 /* max_batch: largest abg_batch.n; max_read_len: longest read accepted. */
 int abg_mapper_create(abg_index *idx, const abg_params *params, uint32_t max_batch,

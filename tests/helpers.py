@@ -77,37 +77,42 @@ class Workspace:
         self.ref("sim", "-R", "-o", "tests/reads_rpbat_pe", *common)
         self._made.add("trex")
 
-    def need_repeat(self):
-        if "rep" in self._made:
+    def need_repeat(self, kind="rep"):
+        """kind "rep": the repeat genome with N runs and IUPAC codes; "plain": the same without IUPAC codes.
+        Files are <kind>.fa, <kind>.idx, <kind>_pe_1.fq, ..."""
+        if kind in self._made:
             return
         import make_genome
-        make_genome.write_fasta(make_genome.repeat_genome(), self.path("rep.fa"))
-        self.ref("idx", "-t", "4", "tests/rep.fa", "tests/rep.idx")
+        k = kind
+        make_genome.write_fasta(make_genome.repeat_genome(iupac=(kind == "rep")), self.path(k + ".fa"))
+        self.ref("idx", "-t", "4", "tests/%s.fa" % k, "tests/%s.idx" % k)
         self.ref("sim", "-seed", "3", "-l", "150", "-min-fraglen", "150", "-max-fraglen", "400", "-n", "6000",
-                 "-m", "0.02", "-b", "0.98", "-o", "tests/rep_pe", "tests/rep.fa")
+                 "-m", "0.02", "-b", "0.98", "-o", "tests/%s_pe" % k, "tests/%s.fa" % k)
         self.ref("sim", "-seed", "4", "-R", "-l", "120", "-min-fraglen", "120", "-max-fraglen", "300", "-n", "4000",
-                 "-m", "0.03", "-b", "0.9", "-o", "tests/rep_rpe", "tests/rep.fa")
+                 "-m", "0.03", "-b", "0.9", "-o", "tests/%s_rpe" % k, "tests/%s.fa" % k)
         self.ref("sim", "-seed", "5", "-single", "-l", "75", "-n", "5000", "-m", "0.05", "-b", "0.95",
-                 "-o", "tests/rep_se", "tests/rep.fa")
+                 "-o", "tests/%s_se" % k, "tests/%s.fa" % k)
         self.ref("sim", "-seed", "6", "-a", "-l", "100", "-min-fraglen", "100", "-max-fraglen", "250", "-n", "4000",
-                 "-m", "0.01", "-b", "0.98", "-o", "tests/rep_pbat", "tests/rep.fa")
-        self._made.add("rep")
+                 "-m", "0.01", "-b", "0.98", "-o", "tests/%s_pbat" % k, "tests/%s.fa" % k)
+        self._made.add(kind)
 
-    def need_short(self):
+    def need_short(self, kind="rep"):
         """Window-12 index (the --enable-short reference) of the repeat genome + reads down to 48 bases."""
-        if "short" in self._made:
+        if "short_" + kind in self._made:
             return
         import make_genome
-        if not os.path.exists(self.path("rep.fa")):
-            make_genome.write_fasta(make_genome.repeat_genome(), self.path("rep.fa"))
-        run([REF_BIN_SHORT, "idx", "-t", "4", "tests/rep.fa", "tests/rep_w12.idx"], cwd=self.dir)
+        k = kind
+        if not os.path.exists(self.path(k + ".fa")):
+            make_genome.write_fasta(make_genome.repeat_genome(iupac=(kind == "rep")), self.path(k + ".fa"))
+        pre = "w12" if kind == "rep" else "w12" + kind
+        run([REF_BIN_SHORT, "idx", "-t", "4", "tests/%s.fa" % k, "tests/%s_w12.idx" % k], cwd=self.dir)
         self.ref("sim", "-seed", "11", "-single", "-l", "50", "-n", "5000", "-m", "0.03", "-b", "0.95",
-                 "-o", "tests/w12_se", "tests/rep.fa")
+                 "-o", "tests/%s_se" % pre, "tests/%s.fa" % k)
         self.ref("sim", "-seed", "12", "-l", "60", "-min-fraglen", "60", "-max-fraglen", "250", "-n", "4000",
-                 "-m", "0.02", "-b", "0.98", "-o", "tests/w12_pe", "tests/rep.fa")
+                 "-m", "0.02", "-b", "0.98", "-o", "tests/%s_pe" % pre, "tests/%s.fa" % k)
         self.ref("sim", "-seed", "13", "-R", "-l", "100", "-min-fraglen", "100", "-max-fraglen", "300", "-n", "3000",
-                 "-m", "0.02", "-b", "0.9", "-o", "tests/w12_rpe", "tests/rep.fa")
-        self._made.add("short")
+                 "-m", "0.02", "-b", "0.9", "-o", "tests/%s_rpe" % pre, "tests/%s.fa" % k)
+        self._made.add("short_" + kind)
 
     def map_with(self, tool, tag, args, pre=()):
         """Run `<tool> map <pre...> -s <stats> -o <sam> <args...>` from the workspace dir
@@ -162,6 +167,13 @@ class OracleMapper:
         if self.h:
             self.lib.abo_index_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def for_kind(args, kind):
+    """File arguments written for the "rep" fixture, renamed for fixture `kind`."""
+    if kind == "rep":
+        return list(args)
+    return [a.replace("tests/rep", "tests/" + kind).replace("tests/w12_", "tests/w12%s_" % kind) for a in args]
 
 
 def assert_results_equal(a, b, paired):

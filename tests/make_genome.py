@@ -6,6 +6,8 @@ pairs), microsatellites and homopolymers (seed buckets > max_candidates, so
 the binary-search narrowing runs and PE candidate heaps grow), N runs of both
 kinds (<=256: replaced by random bases at index time; longer: stay N), IUPAC
 codes, and several chromosomes (reads crossing chromosome ends).
+`repeat_genome(iupac=False)` is the same genome without the IUPAC codes (real
+assemblies hold few or none): no compare window there takes the exact 4-bit route.
 """
 import numpy as np
 
@@ -21,7 +23,7 @@ def _mutate(rng, s, rate):
     return "".join(a)
 
 
-def repeat_genome(seed=7, scale=1.0):
+def repeat_genome(seed=7, scale=1.0, iupac=True):
     rng = np.random.default_rng(seed)
     chroms = []
     unit = _rand_seq(rng, int(30000 * scale))
@@ -46,9 +48,10 @@ def repeat_genome(seed=7, scale=1.0):
     # chrC: N runs and IUPAC codes
     parts = [_rand_seq(rng, 50000), "N" * 100, _rand_seq(rng, 30000), "N" * 2000, _rand_seq(rng, 40000)]
     s = list("".join(parts))
-    for p in rng.integers(0, len(s), size=40):
-        if s[p] != "N":
-            s[p] = "RYKMSW"[int(rng.integers(0, 6))]
+    for p in rng.integers(0, len(s), size=40):  # (drawn in both variants: the rest of the genome stays the same)
+        code = "RYKMSW"[int(rng.integers(0, 6))]
+        if s[p] != "N" and iupac:
+            s[p] = code
     chroms.append(("chrC", "".join(s)))
     # a few short chromosomes (reads run off their ends)
     for k in range(4):

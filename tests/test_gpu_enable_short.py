@@ -35,10 +35,11 @@ def test_cli_map_g_enable_short(workspace):
     assert open(ref[1]).read() == open(got[1]).read()
 
 
+@pytest.mark.parametrize("kind", ["rep", "plain"])
 @pytest.mark.parametrize("window,mode,files", [(12, 0, ("w12_se_1.fq",)), (12, 1, ("w12_pe_1.fq", "w12_pe_2.fq")),
                                                (12, 1 | 4, ("w12_rpe_1.fq", "w12_rpe_2.fq")),
                                                (20, 0, ("w12_se_1.fq",)), (20, 1, ("w12_pe_1.fq", "w12_pe_2.fq"))])
-def test_records_equal_oracle_shortest_reads(workspace, window, mode, files):
+def test_records_equal_oracle_shortest_reads(workspace, window, mode, files, kind):
     """Through the C ABI (abg_index_view.window_size), with every fifth read (pair) cut down to the shortest
     lengths the window admits: 36..47 bases for window 12, 44..55 for window 20.  Below 2 * window + 8 bases
     the specific phase visits seed offsets whose 25-mer overhangs the read (the reference reads past the end
@@ -46,11 +47,13 @@ def test_records_equal_oracle_shortest_reads(workspace, window, mode, files):
     phase does not revisit."""
     from abismal_b200 import Index, IndexFile, Mapper, load_fastq
     from abismal_b200.reads import ReadBatch
-    workspace.need_short()
-    workspace.need_repeat()
-    ixf = IndexFile(workspace.path("rep_w12.idx" if window == 12 else "rep.idx"))
+    from abismal_b200 import capi
+    workspace.need_short(kind)
+    workspace.need_repeat(kind)
+    ixf = IndexFile(workspace.path(kind + ("_w12.idx" if window == 12 else ".idx")))
     assert ixf.window_size == window
     lo = 25 + window - 1
+    files = [f.replace("w12_", "w12_" if kind == "rep" else "w12%s_" % kind) for f in files]
     b = [load_fastq(workspace.path(f), min_read_length=lo) for f in files]
     cut = []
     for x in b:
@@ -58,6 +61,7 @@ def test_records_equal_oracle_shortest_reads(workspace, window, mode, files):
         seqs = [s[:lo + (i % 12)] if i % 5 == 0 else s for i, s in enumerate(seqs)]
         cut.append(ReadBatch(None, seqs))
     ix = Index(ixf, 0)
+    assert ix.features & capi.FEATURE_SEED_CONTEXT
     m = Mapper(ix, mode=mode, max_batch=cut[0].n, max_read_len=128)
     o = helpers.OracleMapper(ixf, mode=mode)
     got, want = m.map_batch(*cut), o.map_batch(*cut)

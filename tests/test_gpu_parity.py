@@ -25,19 +25,28 @@ def gpu():
     return capi
 
 
-@pytest.fixture(scope="module")
-def rep_index(workspace, gpu):
+KINDS = ["rep", "plain"]  # repeat genome with / without IUPAC codes (helpers.Workspace.need_repeat)
+
+
+@pytest.fixture(scope="module", params=KINDS)
+def rep_index(request, workspace, gpu):
+    """(index file, index in HBM, fixture kind).  Both variants must run the benchmarked compare: the
+    seed-context prefilter is on (in the IUPAC variant only the windows near such a code take the exact route)."""
     from abismal_b200 import Index, IndexFile
-    workspace.need_repeat()
-    ixf = IndexFile(workspace.path("rep.idx"))
+    kind = request.param
+    workspace.need_repeat(kind)
+    ixf = IndexFile(workspace.path(kind + ".idx"))
     ix = Index(ixf, 0)
-    yield ixf, ix
+    f = ix.features
+    assert f & gpu.FEATURE_SEED_CONTEXT, "seed-context records were not built"
+    assert bool(f & gpu.FEATURE_GENOME_HAS_IUPAC) == (kind == "rep")
+    yield ixf, ix, kind
     ix.close()
 
 
-def _fq(workspace, name, limit=None):
+def _fq(workspace, name, limit=None, kind="rep"):
     from abismal_b200 import load_fastq
-    return load_fastq(workspace.path(name), limit)
+    return load_fastq(workspace.path(name.replace("rep_", kind + "_", 1)), limit)
 
 
 RECORD_CASES = [
@@ -59,8 +68,8 @@ RECORD_CASES = [
 @pytest.mark.parametrize("tag,mode,kw,files", RECORD_CASES, ids=[c[0] for c in RECORD_CASES])
 def test_records_equal_oracle(workspace, rep_index, gpu, tag, mode, kw, files):
     from abismal_b200 import Mapper
-    ixf, ix = rep_index
-    b = [_fq(workspace, f) for f in files]
+    ixf, ix, kind = rep_index
+    b = [_fq(workspace, f, kind=kind) for f in files]
     max_len = max(x.max_len for x in b)
     m = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max(max_len, 64), **kw)
     o = helpers.OracleMapper(ixf, mode=mode, **kw)
@@ -77,8 +86,8 @@ def test_batch_split_and_repeat_invariance(workspace, rep_index, gpu):
     """Size-independent properties: results do not depend on how reads are
     batched, on their order, or on how often a batch is mapped."""
     from abismal_b200 import Mapper
-    ixf, ix = rep_index
-    b1, b2 = _fq(workspace, "rep_pe_1.fq"), _fq(workspace, "rep_pe_2.fq")
+    ixf, ix, kind = rep_index
+    b1, b2 = _fq(workspace, "rep_pe_1.fq", kind=kind), _fq(workspace, "rep_pe_2.fq", kind=kind)
     m = Mapper(ix, mode=1, max_batch=b1.n, max_read_len=160)
     full = m.map_batch(b1, b2)
     again = m.map_batch(b1, b2)
@@ -93,8 +102,8 @@ def test_batch_split_and_repeat_invariance(workspace, rep_index, gpu):
 
 def test_empty_and_ragged_batches(workspace, rep_index, gpu):
     from abismal_b200 import Mapper, ReadBatch
-    ixf, ix = rep_index
-    src = _fq(workspace, "rep_pe_1.fq", 64)
+    ixf, ix, kind = rep_index
+    src = _fq(workspace, "rep_pe_1.fq", 64, kind=kind)
     seqs = [src.sequence(i) for i in range(src.n)]
     # ragged: skipped reads (empty), trimmed reads of different lengths, an all-N-masked read
     seqs[0] = ""
@@ -126,7 +135,7 @@ def test_empty_and_ragged_batches(workspace, rep_index, gpu):
 
 def test_bad_arguments_fail_loudly(rep_index, gpu):
     from abismal_b200 import AbgError, Mapper, ReadBatch
-    ixf, ix = rep_index
+    ixf, ix, kind = rep_index
     m = Mapper(ix, mode=0, max_batch=8, max_read_len=100)
     with pytest.raises(AbgError):
         m.map_batch(ReadBatch(["x"], ["ACGT" * 50]))  # longer than max_read_len
@@ -147,11 +156,13 @@ def test_cli_golden_md5(workspace, gpu, tag):
     assert helpers.md5(st) == g["tests/%s.mstats" % tag]
 
 
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("tag,args", UNPINNED, ids=[u[0] for u in UNPINNED])
-def test_cli_equals_reference_binary(workspace, gpu, tag, args):
-    workspace.need_repeat()
-    rsam, rst, _ = workspace.map_with(helpers.REF_BIN, "ref_" + tag, args)
-    gsam, gst, _ = workspace.map_with(helpers.CLI, "gpu_" + tag, args)
+def test_cli_equals_reference_binary(workspace, gpu, tag, args, kind):
+    workspace.need_repeat(kind)
+    args = helpers.for_kind(args, kind)
+    rsam, rst, _ = workspace.map_with(helpers.REF_BIN, "ref_%s_%s" % (kind, tag), args)
+    gsam, gst, _ = workspace.map_with(helpers.CLI, "gpu_%s_%s" % (kind, tag), args)
     assert helpers.sam_body(rsam) == helpers.sam_body(gsam)
     assert open(rst).read() == open(gst).read()
 
@@ -176,8 +187,8 @@ def test_pipelined_chunks_and_pinned_buffers(workspace, rep_index, gpu, monkeypa
     sub-batch size nor on whether the caller's buffers are pinned (DMA in place) or pageable (staged)."""
     from abismal_b200 import Mapper
     from abismal_b200.capi import Results
-    ixf, ix = rep_index
-    b1, b2 = _fq(workspace, "rep_pe_1.fq"), _fq(workspace, "rep_pe_2.fq")
+    ixf, ix, kind = rep_index
+    b1, b2 = _fq(workspace, "rep_pe_1.fq", kind=kind), _fq(workspace, "rep_pe_2.fq", kind=kind)
     m = Mapper(ix, mode=1, max_batch=b1.n, max_read_len=160)
     want = m.map_batch(b1, b2)
     m.close()

@@ -73,3 +73,19 @@ def test_oracle_equals_reference_on_unpinned_modes(workspace, tag, args):
     assert helpers.sam_body(rsam) == helpers.sam_body(osam)
     assert open(rst).read() == open(ost).read()
     assert len(helpers.sam_body(rsam)) > 10
+
+
+PLAIN = [u for u in UNPINNED if u[0] in ("se_R", "pe", "pe_P", "pe_R_a")]
+
+
+@pytest.mark.parametrize("tag,args", PLAIN, ids=[u[0] for u in PLAIN])
+def test_oracle_equals_reference_on_the_plain_repeat_genome(workspace, tag, args):
+    """The same repeat genome without IUPAC codes (the fixture on which every compare window of the CUDA path
+    goes through the seed-context prefilter): the restatement is pinned there too."""
+    workspace.need_repeat("plain")
+    args = helpers.for_kind(args, "plain")
+    rsam, rst, _ = workspace.map_with(helpers.REF_BIN, "ref_plain_" + tag, args)
+    osam, ost, _ = workspace.map_with(helpers.ORACLE_MAP, "or_plain_" + tag, args)
+    assert helpers.sam_body(rsam) == helpers.sam_body(osam)
+    assert open(rst).read() == open(ost).read()
+    assert len(helpers.sam_body(rsam)) > 10
