@@ -106,6 +106,8 @@ def load_library():
     lib.abg_mapper_last_kernel_ms.restype = C.c_float
     lib.abg_mapper_last_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.abg_mapper_last_phase_ms.restype = None
+    lib.abg_mapper_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.abg_mapper_last_kernel_times.restype = None
     lib.abg_mapper_launches_per_run.argtypes = [C.c_void_p]
     lib.abg_mapper_launches_per_run.restype = C.c_uint32
     lib.abg_mapper_get_counters.argtypes = [C.c_void_p, C.POINTER(abg_work_counters)]
@@ -329,6 +331,15 @@ class Mapper:
         """(seed_kernel, align_kernel, redo map_reads_kernel) CUDA-event ms of the last run()."""
         out = (C.c_float * 3)()
         self.lib.abg_mapper_last_phase_ms(self._h, out)
+        return [float(x) for x in out]
+
+    KERNELS = ("seed_kernel", "enum_kernel", "dp_kernel", "align_kernel", "map_reads_kernel(redo)")
+
+    @property
+    def last_kernel_times(self):
+        """CUDA-event ms of the five kernels of the last run(), in the order of Mapper.KERNELS."""
+        out = (C.c_float * 5)()
+        self.lib.abg_mapper_last_kernel_times(self._h, out)
         return [float(x) for x in out]
 
     @property

@@ -17,6 +17,7 @@
 
 #include "abismal_b200.h"
 #include "mapper_kernels.cuh"
+#include "align_tasks.cuh"
 
 namespace {
 
@@ -105,7 +106,14 @@ struct abg_index {
 
 constexpr uint32_t kInlineOps = 16;   // CIGAR ops per read copied back with the batch; longer ones are fetched afterwards
 constexpr uint32_t kMaxChunks = 256;  // sub-batches one abg_map_batch call is pipelined over
-constexpr uint32_t kWorkWords = 1 + 4 * kMaxChunks;
+// device words per sub-batch: work counters of map / seed / align, redo count, work counter of enum_kernel,
+// task slots handed out per class [3] + traceback units, dp_kernel's cursors [3]
+constexpr uint32_t kChunkWords = 12;
+constexpr uint32_t kWorkWords = 1 + kChunkWords * kMaxChunks;
+// task-parallel alignment: slots per read / pair in the three task lists (bands <= 16 / <= 32 / <= 61 columns) and
+// traceback allocations per read / pair (in tasks of the first class); beyond these the alignment runs in the warp
+constexpr uint32_t kTaskCapPe[3] = {5, 2, 1}, kTaskCapSe[3] = {3, 1, 1};
+constexpr uint32_t kTbTasksPe = 4, kTbTasksSe = 2;
 
 struct abg_mapper {
   abg_index *idx = nullptr;
@@ -137,6 +145,19 @@ struct abg_mapper {
   cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};          // partners of stream, s_run[0], s_run[1]
   cudaEvent_t ev_go[3] = {nullptr, nullptr, nullptr}, ev_aux[3] = {nullptr, nullptr, nullptr};
   uint32_t n_pass = 1, set_slots = 0;
+  // task-parallel alignment (align_tasks.cuh): enum_kernel -> dp_kernel between seed_kernel and align_kernel
+  bool use_tasks = false;
+  const void *kernel_e = nullptr;
+  int grid_e = 0, grid_d = 0;
+  size_t smem_d = 0;
+  uint32_t task_cap_item[3] = {0, 0, 0}, task_slack = 0, tb_cap_item = 0, tb_slack = 0, n_chunks_max = 1;
+  uint64_t task_class_off[3] = {0, 0, 0};
+  ab2dev::AlignTask *d_tasks = nullptr;
+  ab2dev::TaskResult *d_task_res = nullptr;
+  uint64_t *d_task_tb = nullptr;
+  uint32_t *d_task_of = nullptr;
+  cudaEvent_t ev_t[2] = {nullptr, nullptr};  // abg_mapper_run: after enum_kernel, after dp_kernel
+  float task_ms[2] = {0.f, 0.f};
   uint64_t *d_sets = nullptr;
   unsigned int *d_redo_flag = nullptr;
   uint32_t *d_redo_list = nullptr;
@@ -195,7 +216,21 @@ int stage_offsets(abg_mapper *m, const uint32_t *off, uint32_t c0, uint32_t c1, 
 
 void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint32_t n, uint32_t chunk_idx) {
   std::memset(&P, 0, sizeof P);
-  unsigned int *work = m->d_work + 1 + 4 * chunk_idx;
+  unsigned int *work = m->d_work + 1 + kChunkWords * chunk_idx;
+  if (m->use_tasks) {
+    // the sub-batch's own regions of the task lists, results, traceback arena: items [c0, c0 + n) + its slack
+    P.tasks = m->d_tasks;
+    P.task_res = m->d_task_res;
+    P.task_of = m->d_task_of + (size_t)c0 * m->n_pass * m->set_slots;
+    for (int c = 0; c < 3; ++c) {
+      P.task_base[c] = (uint32_t)(m->task_class_off[c] + (uint64_t)c0 * m->task_cap_item[c] + (uint64_t)chunk_idx * m->task_slack);
+      P.task_cap[c] = n * m->task_cap_item[c] + m->task_slack;
+    }
+    P.task_tb = m->d_task_tb + ((uint64_t)c0 * m->tb_cap_item + (uint64_t)chunk_idx * m->tb_slack) * 8u;
+    P.task_tb_cap = n * m->tb_cap_item + m->tb_slack;
+    P.task_count = work + 5;
+    P.task_cursor = work + 9;
+  }
   if (m->split) {
     P.sets = m->d_sets + (size_t)c0 * m->n_pass * (ab2dev::kSetStateWords + m->set_slots);
     P.set_slots = m->set_slots;
@@ -293,9 +328,17 @@ int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const 
   Q.slot_base = P.slot_base;
   if ((rc = launch_one(m->kernel_s, grid_s, m->smem_s, Q, st))) return rc;
   if (ev_ph) ABG_CUDA(cudaEventRecord(ev_ph[0], st));
-  Q.work_counter = work + 2;
   Q.layout_kind = ab2dev::kLayoutAlign;
   const uint64_t a_blocks = ((uint64_t)P.n + wpb - 1) / wpb;
+  if (m->use_tasks) {
+    // enumerate the alignments (sorted sets + task lists), run them task-parallel; align_kernel then looks them up
+    Q.work_counter = work + 4;
+    if ((rc = launch_one(m->kernel_e, (int)std::min<uint64_t>((uint64_t)m->grid_e, a_blocks), m->smem_a, Q, st))) return rc;
+    if (ev_ph) ABG_CUDA(cudaEventRecord(m->ev_t[0], st));
+    if ((rc = launch_one((const void *)ab2dev::dp_kernel, m->grid_d, m->smem_d, Q, st))) return rc;
+    if (ev_ph) ABG_CUDA(cudaEventRecord(m->ev_t[1], st));
+  }
+  Q.work_counter = work + 2;
   if (overlap) {
     ab2dev::KernelParams A = Q;
     A.slot_base = P.slot_base + (uint32_t)m->grid_s * (uint32_t)wpb;  // disjoint from the seeding kernel's slots
@@ -314,6 +357,7 @@ int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const 
   Q.n_items_ptr = P.redo_count;
   Q.layout_kind = ab2dev::kLayoutFull;
   Q.slot_base = P.slot_base;
+  Q.tasks = nullptr;  // the redo kernel maps its pairs from scratch, alignments in the warp
   return launch_one(m->kernel, m->grid, m->smem, Q, st);
 }
 
@@ -706,6 +750,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
   ABG_M(cudaEventCreate(&m->ev1));
   ABG_M(cudaEventCreate(&m->ev_ph[0]));
   ABG_M(cudaEventCreate(&m->ev_ph[1]));
+  ABG_M(cudaEventCreate(&m->ev_t[0]));
+  ABG_M(cudaEventCreate(&m->ev_t[1]));
   ABG_M(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
   for (uint32_t k = 0; k < kMaxChunks; ++k) {
     ABG_M(cudaEventCreateWithFlags(&m->ev_in[k], cudaEventDisableTiming));
@@ -799,13 +845,61 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
         }
       }
     }
-    grid_max = std::max(grid_max, std::max(m->grid_s + m->grid_a_aux, m->grid_a));
+    {
+      // task-parallel alignment (default for reads up to kDpMaxMl bases; ABISMAL_B200_TASKS=0 keeps every DP in
+      // the warp of its pair)
+      const char *e = std::getenv("ABISMAL_B200_TASKS");
+      m->use_tasks = !(e && std::atoi(e) == 0) && !m->overlap && m->ml <= ab2dev::kDpMaxMl;
+    }
+    if (m->use_tasks) {
+      m->kernel_e = m->minb == 2 ? (const void *)ab2dev::enum_kernel<2>
+                  : m->minb == 4 ? (const void *)ab2dev::enum_kernel<4>
+                                 : (const void *)ab2dev::enum_kernel<3>;
+      m->smem_d = ab2dev::dp_block_smem_bytes(m->ml);
+      int per_e = 0, per_d = 0;
+      for (const void *k : {m->kernel_e, (const void *)ab2dev::dp_kernel})
+        if (cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+          (void)cudaGetLastError();
+      ABG_M(raise_smem_cap(ix->device, m->kernel_e, m->smem_a));
+      ABG_M(raise_smem_cap(ix->device, (const void *)ab2dev::dp_kernel, m->smem_d));
+      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_e, m->kernel_e, ab2dev::kThreadsPerBlock, m->smem_a));
+      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_d, (const void *)ab2dev::dp_kernel, ab2dev::kThreadsPerBlock, m->smem_d));
+      if (per_e < 1 || per_d < 1) m->use_tasks = false;
+      m->grid_e = n_sm * std::max(per_e, 1);
+      m->grid_d = n_sm * std::max(per_d, 1);
+    }
+    grid_max = std::max(grid_max, std::max(std::max(m->grid_s + m->grid_a_aux, m->grid_a), m->grid_e));
     const bool rpbat = (p->mode & ABG_MODE_RANDOM_PBAT) != 0;
     m->n_pass = m->paired ? (rpbat ? 8u : 4u) : 1u;
     m->set_slots = m->paired ? ab2dev::kSetSlotsPe : ab2dev::kSetSlotsSe;
     ABG_M(cudaMalloc(&m->d_sets, (size_t)max_batch * m->n_pass * (ab2dev::kSetStateWords + m->set_slots) * sizeof(uint64_t)));
     ABG_M(cudaMalloc(&m->d_redo_flag, (size_t)max_batch * sizeof(unsigned int)));
     ABG_M(cudaMalloc(&m->d_redo_list, (size_t)max_batch * sizeof(uint32_t)));
+    if (m->use_tasks) {
+      // every sub-batch owns the part of the arenas that belongs to its items plus one slack region (task slots
+      // and traceback words are handed to the warps of enum_kernel in blocks; a warp's last block stays part empty)
+      const uint32_t chunk_now = std::max(m->chunk, (max_batch + kMaxChunks - 1) / kMaxChunks);
+      m->n_chunks_max = std::max(1u, (max_batch + chunk_now - 1) / chunk_now);
+      const uint32_t warps = (uint32_t)m->grid_e * ab2dev::kWarpsPerBlock;
+      m->task_slack = warps * 32u;  // a warp's last block holds at most 31 unused slots (one task per lane at a time)
+      m->tb_slack = warps * ab2dev::kTbGrabTasks * ab2dev::tb_sm_words(m->ml);
+      const uint32_t *cap = m->paired ? kTaskCapPe : kTaskCapSe;
+      uint64_t off = 0;
+      for (int c = 0; c < 3; ++c) {
+        m->task_cap_item[c] = cap[c] * (rpbat ? 2u : 1u);
+        m->task_class_off[c] = off;
+        off += (uint64_t)max_batch * m->task_cap_item[c] + (uint64_t)m->n_chunks_max * m->task_slack;
+      }
+      m->tb_cap_item = (m->paired ? kTbTasksPe : kTbTasksSe) * (rpbat ? 2u : 1u) * ab2dev::tb_sm_words(m->ml);
+      const uint64_t tb_units = (uint64_t)max_batch * m->tb_cap_item + (uint64_t)m->n_chunks_max * m->tb_slack;
+      if (off >= 0xffffffffull || tb_units >= 0xffffffffull) m->use_tasks = false;  // ids are 32 bits
+      else {
+        ABG_M(cudaMalloc(&m->d_tasks, off * sizeof(ab2dev::AlignTask)));
+        ABG_M(cudaMalloc(&m->d_task_res, off * sizeof(ab2dev::TaskResult)));
+        ABG_M(cudaMalloc(&m->d_task_tb, tb_units * 64u));
+        ABG_M(cudaMalloc(&m->d_task_of, (size_t)max_batch * m->n_pass * m->set_slots * sizeof(uint32_t)));
+      }
+    }
   }
   // two scratch sets: consecutive chunks run on alternating streams and may overlap at their tails
   m->grid_scratch = grid_max;
@@ -879,6 +973,12 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFree(m->d_sets);
   cudaFree(m->d_redo_flag);
   cudaFree(m->d_redo_list);
+  cudaFree(m->d_tasks);
+  cudaFree(m->d_task_res);
+  cudaFree(m->d_task_tb);
+  cudaFree(m->d_task_of);
+  for (cudaEvent_t e : m->ev_t)
+    if (e) cudaEventDestroy(e);
   cudaFreeHost(m->h_flags);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
@@ -941,7 +1041,7 @@ int abg_mapper_run(abg_mapper *m) {
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ab2dev::KernelParams P;
   fill_params(m, P, 0, m->cur_n, 0);
-  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, 5 * sizeof(unsigned int), m->stream));
+  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, (1 + kChunkWords) * sizeof(unsigned int), m->stream));
   if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->stream));
   ABG_CUDA(cudaEventRecord(m->ev0, m->stream));
   int rc;
@@ -970,6 +1070,16 @@ void read_times(abg_mapper *m) {
       m->phase_ms[0] = a;
       m->phase_ms[1] = b;
       m->phase_ms[2] = c;
+      m->task_ms[0] = m->task_ms[1] = 0.f;
+      if (m->use_tasks) {
+        float e = 0.f, d = 0.f;
+        if (cudaEventElapsedTime(&e, m->ev_ph[0], m->ev_t[0]) == cudaSuccess && cudaEventElapsedTime(&d, m->ev_t[0], m->ev_t[1]) == cudaSuccess) {
+          m->task_ms[0] = e;
+          m->task_ms[1] = d;
+        }
+        else
+          (void)cudaGetLastError();
+      }
     }
     else
       (void)cudaGetLastError();
@@ -1106,8 +1216,17 @@ float abg_mapper_last_kernel_ms(const abg_mapper *m) { return m ? m->last_ms : 0
 void abg_mapper_last_phase_ms(const abg_mapper *m, float out[3]) {
   for (int k = 0; k < 3; ++k) out[k] = m ? m->phase_ms[k] : 0.f;
 }
+void abg_mapper_last_kernel_times(const abg_mapper *m, float out[5]) {
+  for (int k = 0; k < 5; ++k) out[k] = 0.f;
+  if (!m) return;
+  out[0] = m->phase_ms[0];
+  out[1] = m->task_ms[0];
+  out[2] = m->task_ms[1];
+  out[3] = m->phase_ms[1] - m->task_ms[0] - m->task_ms[1];
+  out[4] = m->phase_ms[2];
+}
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m) {
-  return (m && m->cur_n) ? (m->split ? (m->overlap ? 4u : 3u) : 1u) : 0u;
+  return (m && m->cur_n) ? (m->split ? (m->overlap ? 4u : (m->use_tasks ? 5u : 3u)) : 1u) : 0u;
 }
 uint32_t abg_mapper_chunk(const abg_mapper *m) { return m ? m->chunk : 0u; }
 

@@ -100,6 +100,18 @@ struct IndexDev {
 constexpr int kCtxArrays = 4;
 constexpr uint32_t kCcKeys = 28;
 
+// One banded alignment handed from enum_kernel to dp_kernel (align_tasks.cuh)
+struct AlignTask {
+  uint32_t t_pos;     // candidate position (centre diagonal of the band)
+  uint32_t item;      // read / pair of the sub-batch
+  uint32_t meta;      // bit 0: end; bit 1: reverse-complemented; bit 2: a-rich flag; bits 8..15: band width (0 = empty slot)
+  uint32_t tb_index;  // traceback words at task_tb + 8 * tb_index, or kNoTask when not recorded
+};
+struct TaskResult {   // AlnOut of the task
+  int16_t score, row, col, bw;
+};
+constexpr uint32_t kNoTask = 0xffffffffu;
+
 struct KernelParams {
   IndexDev ix;
   // batch
@@ -140,6 +152,15 @@ struct KernelParams {
   unsigned int *ready;       // [n]: stored sets of the item so far (seed_kernel increments, release); null = stream order
   uint32_t ready_need;       // sets per item
   uint32_t wait_ns;          // how long an align warp waits for an item before leaving it to the redo kernel
+  // task-parallel alignment (align_tasks.cuh); tasks == nullptr: every alignment runs in the warp of its pair
+  AlignTask *tasks;          // three lists: class c (groups of 8 << c lanes) at task_base[c], task_cap[c] slots
+  TaskResult *task_res;      // [task id]
+  uint64_t *task_tb;         // traceback arena, addressed in units of 8 words
+  uint32_t *task_of;         // [n][n_pass][set_slots]: task id of entry j of the sorted stored set, or kNoTask
+  unsigned int *task_count;  // [0..2] slots handed out per class, [3] traceback units handed out
+  unsigned int *task_cursor; // [0..2] dp_kernel's work cursors
+  uint32_t task_base[3], task_cap[3];
+  uint32_t task_tb_cap;      // units of 8 words
 };
 
 // ---- 64-bit view of se_element {int16 diffs; uint16 flags; uint32 pos} -------
@@ -192,7 +213,7 @@ struct AlnOut {
 struct TbKey {  // which alignment the traceback words of a slot belong to
   uint32_t pos, key, valid;
   int score, row, col, bw;
-  uint32_t pad;
+  uint32_t tb_index;  // kNoTask: the words are in the slot's own storage; else in the task arena (align_tasks.cuh)
 };
 
 struct WarpScalars {
@@ -204,7 +225,7 @@ struct WarpScalars {
   unsigned long long cnt[6];
 };
 
-constexpr int kParamBytes = 512;
+constexpr int kParamBytes = 640;
 constexpr int kTab3Bytes = 2 * 256 * 4;
 static_assert(sizeof(KernelParams) <= kParamBytes, "KernelParams must fit its shared-memory slot");
 
@@ -1412,7 +1433,7 @@ __device__ __noinline__
 __device__ __forceinline__
 #endif
 int align(bool record_tb, bool need_tb, int tb_slot, int end, uint32_t flags, int diffs,
-                                     int max_diffs, int q_sz, uint32_t t_pos, AlnOut &out) {
+                                     int max_diffs, int q_sz, uint32_t t_pos, AlnOut &out, uint32_t task_id = kNoTask) {
   if (diffs == 0) return 2 * q_sz;  // AbismalAlign.hpp:329-330
   const Warp W;
   const int bw = band_width(diffs, max_diffs);
@@ -1424,6 +1445,33 @@ int align(bool record_tb, bool need_tb, int tb_slot, int end, uint32_t flags, in
     out.col = tk->col;
     out.bw = bw;
     return out.score;
+  }
+  if (task_id != kNoTask) {
+    // dp_kernel has run this very alignment (same read strand, position and band): take its result
+    const KernelParams &P = params();
+    const uint2 rr = __ldcg(reinterpret_cast<const uint2 *>(P.task_res + task_id));
+    const uint32_t tbi = __ldcg(&P.tasks[task_id].tb_index);
+    if ((int)(int16_t)(rr.y >> 16) == bw && (tbi != kNoTask || !need_tb)) {
+      out.score = (int)(int16_t)(rr.x & 0xffffu);
+      out.row = (int)(int16_t)(rr.x >> 16);
+      out.col = (int)(int16_t)(rr.y & 0xffffu);
+      out.bw = bw;
+      if (tbi != kNoTask) {  // its traceback words are on record: the slot now describes this alignment
+        __syncwarp();
+        if (W.lane == 0) {
+          tk->pos = t_pos;
+          tk->key = key;
+          tk->score = out.score;
+          tk->row = out.row;
+          tk->col = out.col;
+          tk->bw = bw;
+          tk->tb_index = tbi;
+          tk->valid = 1;
+        }
+        __syncwarp();
+      }
+      return out.score;
+    }
   }
   build_qcode(end, flags);
   const bool tb = record_tb || need_tb;
@@ -1446,6 +1494,7 @@ int align(bool record_tb, bool need_tb, int tb_slot, int end, uint32_t flags, in
     tk->row = out.row;
     tk->col = out.col;
     tk->bw = bw;
+    tk->tb_index = kNoTask;
     tk->valid = 1;
   }
   __syncwarp();
@@ -1485,11 +1534,16 @@ __device__ __noinline__ int build_cigar(int tb_slot, int diffs, int a_score, int
   else {
     const uint64_t *tbs = W.tb_sm(tb_slot);
     const uint64_t *tbg = W.tb_gm(tb_slot);
+    // words of an alignment dp_kernel ran: [block of 16 iterations][lane of its group of 8 / 16 / 32]
+    const uint32_t tbi = W.scal()->tbk[tb_slot].tb_index;
+    const uint64_t *tba = tbi != kNoTask ? params().task_tb + (size_t)tbi * 8u : nullptr;
+    const int tbG = bw <= 16 ? 8 : (bw <= 32 ? 16 : 32);
     int row = a_row, col = a_col;
     const int clip_bottom = (q_sz + (bw - 1)) - (row + col);
     __syncwarp();
     // traceback word holding cell (r, cc): lane l = cc / 2, iteration T = r + l
     const auto word_at = [&](int T, int l) -> uint64_t {
+      if (tba != nullptr) return __ldcg(tba + (size_t)(T >> 4) * tbG + l);
       return l < kTbLanesSm ? tbs[(T >> 4) * kTbLanesSm + l] : *(volatile const uint64_t *)(tbg + (size_t)(T >> 4) * 32 + l);
     };
     const auto code_at = [&](int r, int cc) -> int {
@@ -1600,8 +1654,10 @@ __device__ __forceinline__ int build_cigar(int tb_slot, int diffs, const AlnOut 
 __device__ __forceinline__ bool same_pos(uint32_t a, uint32_t b) { return (a > b ? a - b : b - a) <= 3u; }
 
 // align_se_candidates (abismal.cpp:1435-1497) on se set `end`
+// task_of: task ids of the entries of the (already sorted + uniqued) set, or nullptr: align in the warp
 __device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uint32_t *ops, uint32_t stride,
-                                                     uint32_t *cg_n, uint32_t *cg_ref_len, uint64_t best_in) {
+                                                     uint32_t *cg_n, uint32_t *cg_ref_len, uint64_t best_in,
+                                                     const uint32_t *task_of = nullptr) {
   const Warp W;
   const uint32_t readlen_u = W.scal()->len[end];
   const int readlen = (int)(int16_t)readlen_u;
@@ -1618,9 +1674,10 @@ __device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uin
     return best.w;
   }
   int best_scr = 0;
-  uint32_t best_pos = 0;
-  sort_unique(end);
+  uint32_t best_pos = 0, best_task = kNoTask;
+  if (task_of == nullptr) sort_unique(end);  // enum_kernel has done it otherwise
   const HeapRef v = heap_of(W, end);
+  const uint32_t n_slots = params().set_slots;
   int it = 0;
   const int lim = st->sz;
   for (; it != lim && v.get(it).empty(); ++it) {
@@ -1633,12 +1690,14 @@ __device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uin
     const Hit h = v.get(it);
     if (h.diffs() < invalid) {
       const uint32_t cand_pos = h.pos();
+      const uint32_t tid = (task_of != nullptr && (uint32_t)it < n_slots) ? __ldcg(task_of + it) : kNoTask;
       const int cand_scr =
-        (int)(int16_t)align(record_tb, false, 0, end, h.flags(), h.diffs(), max_diffs, q_sz, cand_pos, ao);
+        (int)(int16_t)align(record_tb, false, 0, end, h.flags(), h.diffs(), max_diffs, q_sz, cand_pos, ao, tid);
       if (cand_scr > best_scr) {
         best = h;
         best_scr = cand_scr;
         best_pos = cand_pos;
+        best_task = tid;
       }
       else if (cand_scr == best_scr && (cand_scr == max_scr ? cand_pos != best_pos : !same_pos(cand_pos, best_pos)))
         best.set_ambig();
@@ -1646,7 +1705,7 @@ __device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uin
   }
   if (best.pos() != 0) {
     ao.score = 0;
-    align(false, true, 0, end, best.flags(), best.diffs(), max_diffs, q_sz, best.pos(), ao);
+    align(false, true, 0, end, best.flags(), best.diffs(), max_diffs, q_sz, best.pos(), ao, best_task);
     uint32_t len = 0, pos = best.pos();
     CigarOut cg{ops, stride, 0u, 0u};
     const int nm = build_cigar(0, best.diffs(), ao, q_sz, best_scr, cg, len, pos);
@@ -1695,8 +1754,9 @@ struct PeBest {
 
 // best_pair<swap_ends> (abismal.cpp:1722-1831) over pe sets 2 (end e1, un-reversed) and 3 (end e2, reversed).
 // The traceback slot of an end is its end number.
+// tof1 / tof2: task ids of the entries of sets 2 / 3 (enum_kernel), or nullptr
 __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, uint32_t flags2, CigarOut *cgs,
-                                       PeBest *best_io) {
+                                       PeBest *best_io, const uint32_t *tof1 = nullptr, const uint32_t *tof2 = nullptr) {
   const Warp W;
   const KernelParams &P = params();
   const int e2 = 1 - e1;
@@ -1713,7 +1773,8 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
   const int max_diffs2 = frac_of(P.valid_frac, readlen2);
   const uint32_t min_dist = P.min_dist, max_dist = P.max_dist;
   int scr1 = 0, best_scr1 = 0, best_scr2 = 0;
-  uint32_t best_pos1 = 0, best_pos2 = 0;
+  uint32_t best_pos1 = 0, best_pos2 = 0, best_t1 = kNoTask, best_t2 = kNoTask;
+  const uint32_t n_slots = P.set_slots;
   AlnOut ao;
 
   for (; j1 != j1_end && v1.get(j1).empty(); ++j1) {
@@ -1732,11 +1793,13 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
     for (; j1 != j1_end && !best.sure_ambig(); ++j1) {
       const Hit s1 = v1.get(j1);
       if (!(s1.pos() + min_dist <= lim)) break;
+      const uint32_t t2 = (tof2 != nullptr && (uint32_t)j2 < n_slots) ? __ldcg(tof2 + j2) : kNoTask;
+      const uint32_t t1 = (tof1 != nullptr && (uint32_t)j1 < n_slots) ? __ldcg(tof1 + j1) : kNoTask;
       if (scr2 == 0)
-        scr2 = (int)(int16_t)align(rec2, false, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), ao);
+        scr2 = (int)(int16_t)align(rec2, false, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), ao, t2);
       int m1 = *(volatile int16_t *)(mem_scr + j1);
       if (m1 == 0) {
-        scr1 = (int)(int16_t)align(rec1, false, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, s1.pos(), ao);
+        scr1 = (int)(int16_t)align(rec1, false, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, s1.pos(), ao, t1);
         m1 = scr1;
         __syncwarp();
         if (W.lane == 0) mem_scr[j1] = (int16_t)scr1;
@@ -1748,6 +1811,8 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
         best_scr2 = scr2;
         best_pos1 = s1.pos();
         best_pos2 = s2.pos();
+        best_t1 = t1;
+        best_t2 = t2;
       }
     }
   }
@@ -1756,12 +1821,12 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
     Hit s2 = swap_ends ? best.r1 : best.r2;
     uint32_t len1 = 0, len2 = 0;
     ao.score = 0;
-    align(false, true, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, best_pos1, ao);
+    align(false, true, e1, e1, flags1, s1.diffs(), max_diffs1, (int)readlen1, best_pos1, ao, best_t1);
     int nm = build_cigar(e1, s1.diffs(), ao, (int)readlen1, best_scr1, cgs[e1], len1, best_pos1);
     s1.set_pos(best_pos1);
     s1.set_diffs(nm);
     ao.score = 0;
-    align(false, true, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, best_pos2, ao);
+    align(false, true, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, best_pos2, ao, best_t2);
     nm = build_cigar(e2, s2.diffs(), ao, (int)readlen2, best_scr2, cgs[e2], len2, best_pos2);
     s2.set_pos(best_pos2);
     s2.set_diffs(nm);
@@ -2064,8 +2129,9 @@ __device__ __forceinline__ void map_one(const Warp &W, unsigned int item) {
         process_seeds(0, 0, cv);
         process_seeds(0, 0, cv | RC);
       }
+      const uint32_t *tof = (FROM_SETS && P.tasks != nullptr) ? P.task_of + (size_t)item * P.n_pass * P.set_slots : nullptr;
       best = Hit(align_se_candidates(0, P.valid_frac, P.cigar[0] + (size_t)item * P.cigar_stride, P.cigar_stride,
-                                     &cg_n, &cg_ref, best.w));
+                                     &cg_n, &cg_ref, best.w, tof));
     }
     if (lane == 0) {
       P.se[0][item] = to_abg(best);
@@ -2124,9 +2190,15 @@ __device__ __forceinline__ void map_one(const Warp &W, unsigned int item) {
       t0.load(W, 2);
       t1.load(W, 3);
       if (t0.should_align() && t1.should_align()) {
-        sort_unique(2);
-        sort_unique(3);
-        best_pair(swap_ends, e1, f1, f2, cg, &best);
+        if (FROM_SETS && P.tasks != nullptr) {  // enum_kernel has sorted + uniqued the stored sets and emitted the tasks
+          const uint32_t *tof = P.task_of + ((size_t)item * P.n_pass + 2u * call) * P.set_slots;
+          best_pair(swap_ends, e1, f1, f2, cg, &best, tof, tof + P.set_slots);
+        }
+        else {
+          sort_unique(2);
+          sort_unique(3);
+          best_pair(swap_ends, e1, f1, f2, cg, &best);
+        }
       }
       best_single(2, e1);
       best_single(3, e2);

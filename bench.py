@@ -389,12 +389,12 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
     barrier()
 
     def timed_device():
-        kernel_ms, phase_ms = [], [0.0, 0.0, 0.0]
+        kernel_ms, phase_ms = [], [0.0] * 5
         for _ in range(args.steps):
             m.run()
             m.sync()
             kernel_ms.append(m.last_kernel_ms)
-            phase_ms = [x + y for x, y in zip(phase_ms, m.last_phase_ms)]
+            phase_ms = [x + y for x, y in zip(phase_ms, m.last_kernel_times)]
         state.update(dev_ms=sum(kernel_ms), phase_ms=phase_ms)
     sync.run("device-resident leg", timed_device)
     barrier()
@@ -481,7 +481,7 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
                 "parity": {"%s_checked" % unit: total_checked, "ranks_checked": world, "mismatching_records": total_bad,
                            "against": "CPU oracle (oracle/abismal_oracle.cpp), first %d %s of every rank's timed batch" % (n_o, unit)},
             }
-            names = ("seed_kernel", "align_kernel", "map_reads_kernel(redo)")
+            names = m.KERNELS
             out["kernels"] = {nm: {"ms_per_launch": t / args.steps, "share_of_step": t / dev_ms}
                               for nm, t in zip(names, phase_ms)}
             # ---- roofline + CPU baseline + front end (rank 0, N = 1) -------------------

@@ -184,6 +184,9 @@ float abg_mapper_last_kernel_ms(const abg_mapper *m);
  * out[0] seed_kernel, out[1] align_kernel, out[2] map_reads_kernel over the redo list.
  * Single-kernel mode (ABISMAL_B200_SPLIT=0): out[0] = the whole run. */
 void abg_mapper_last_phase_ms(const abg_mapper *m, float out[3]);
+/* All five kernels of a run: out[0] seed_kernel, out[1] enum_kernel, out[2] dp_kernel, out[3] align_kernel,
+ * out[4] map_reads_kernel over the redo list (out[1] = out[2] = 0 without the task-parallel alignment). */
+void abg_mapper_last_kernel_times(const abg_mapper *m, float out[5]);
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m);
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out);
 

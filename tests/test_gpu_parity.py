@@ -77,9 +77,32 @@ def test_records_equal_oracle(workspace, rep_index, gpu, tag, mode, kw, files):
     want = o.map_batch(*b)
     helpers.assert_results_equal(got, want, bool(mode & 1))
     mapped = want.pe_r1["pos"] != 0 if mode & 1 else want.se1["pos"] != 0
-    assert mapped.sum() > 50  # the case is not vacuous
+    assert mapped.sum() > 30  # the case is not vacuous
     m.close()
     o.close()
+
+
+@pytest.mark.parametrize("tag,mode,kw,files", [c for c in RECORD_CASES if c[0] in ("se", "pe", "pe_rpbat_ambig")],
+                         ids=["se", "pe", "pe_rpbat_ambig"])
+def test_records_equal_oracle_with_alignments_in_the_warp(workspace, rep_index, gpu, monkeypatch, tag, mode, kw, files):
+    """ABISMAL_B200_TASKS=0: every banded alignment runs in the warp of its read / pair (the path reads longer
+    than 512 bases, the single-end fallback of a pair and the redo kernel always take) instead of the
+    enum_kernel -> dp_kernel task lists."""
+    from abismal_b200 import Mapper
+    ixf, ix, kind = rep_index
+    monkeypatch.setenv("ABISMAL_B200_TASKS", "0")
+    b = [_fq(workspace, f, kind=kind) for f in files]
+    m = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max([x.max_len for x in b] + [64]), **kw)
+    monkeypatch.delenv("ABISMAL_B200_TASKS")
+    mt = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max([x.max_len for x in b] + [64]), **kw)
+    got, got_t = m.map_batch(*b), mt.map_batch(*b)
+    assert m.launches_per_run == 3 and mt.launches_per_run == 5
+    helpers.assert_results_equal(got, got_t, bool(mode & 1))
+    o = helpers.OracleMapper(ixf, mode=mode, **kw)
+    helpers.assert_results_equal(got, o.map_batch(*b), bool(mode & 1))
+    o.close()
+    m.close()
+    mt.close()
 
 
 def test_batch_split_and_repeat_invariance(workspace, rep_index, gpu):
