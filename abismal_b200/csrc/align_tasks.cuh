@@ -291,6 +291,7 @@ __device__ __forceinline__ void enumerate_set(const Warp &W, TaskAlloc &al, int 
   const KernelParams &P = params();
   const HeapRef v = heap_of(W, set_id);
   const int sz = W.cs(set_id)->sz;
+  const uint32_t ovf = W.cs(set_id)->ovf;
   const int n = max(sz, (int)slots);
   for (int j0 = 0; j0 < n; j0 += 32) {
     const int j = j0 + W.lane;
@@ -303,6 +304,7 @@ __device__ __forceinline__ void enumerate_set(const Warp &W, TaskAlloc &al, int 
     const int bw = want ? band_width(h.diffs(), max_diffs) : 0;
     const uint32_t id = emit_task(P, al, want, bw, h.pos(), item, want ? meta_fn(h) : 0u, want_tb, W.lane);
     if (j < (int)slots) task_of[j] = id;
+    else if (j < sz && ovf != 0u) P.task_ovf[(ovf - 1u) + (uint32_t)(j - (int)slots)] = id;
   }
 }
 

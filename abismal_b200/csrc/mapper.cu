@@ -109,7 +109,8 @@ constexpr uint32_t kMaxChunks = 256;  // sub-batches one abg_map_batch call is p
 // device words per sub-batch: work counters of map / seed / align, redo count, work counter of enum_kernel,
 // task slots handed out per class [3] + traceback units, dp_kernel's cursors [3]
 constexpr uint32_t kChunkWords = 12;
-constexpr uint32_t kWorkWords = 1 + kChunkWords * kMaxChunks;
+constexpr uint32_t kWorkWords = 2 + kChunkWords * kMaxChunks;  // [0] error flag, [1] cursor of the set overflow arena
+constexpr uint32_t kOvfPerItem = 32;  // overflow arena entries per pair of max_batch (sets beyond set_slots entries)
 // task-parallel alignment: slots per read / pair in the three task lists (bands <= 16 / <= 32 / <= 61 columns) and
 // traceback allocations per read / pair (in tasks of the first class); beyond these the alignment runs in the warp
 constexpr uint32_t kTaskCapPe[3] = {5, 2, 1}, kTaskCapSe[3] = {3, 1, 1};
@@ -156,6 +157,9 @@ struct abg_mapper {
   ab2dev::TaskResult *d_task_res = nullptr;
   uint64_t *d_task_tb = nullptr;
   uint32_t *d_task_of = nullptr;
+  uint64_t *d_set_ovf = nullptr;   // entries of stored paired-end sets beyond set_slots
+  uint32_t *d_task_ovf = nullptr;  // their task ids
+  uint32_t ovf_cap = 0;
   cudaEvent_t ev_t[2] = {nullptr, nullptr};  // abg_mapper_run: after enum_kernel, after dp_kernel
   float task_ms[2] = {0.f, 0.f};
   uint64_t *d_sets = nullptr;
@@ -174,7 +178,7 @@ struct abg_mapper {
   int16_t *d_mem_scr = nullptr;
   uint64_t *d_tb = nullptr;
   uint32_t tb_words = 0;
-  unsigned int *d_work = nullptr;   // [0] error flag, [1 + 4j ..] chunk j: work counters of map / seed / align, redo count
+  unsigned int *d_work = nullptr;   // [0] error flag, [1] overflow arena cursor, [2 + kChunkWords j ..] sub-batch j (see kChunkWords)
   unsigned long long *d_counters = nullptr;
   // pinned staging (used when the caller's buffers are pageable)
   char *h_seq[2] = {nullptr, nullptr};
@@ -216,7 +220,11 @@ int stage_offsets(abg_mapper *m, const uint32_t *off, uint32_t c0, uint32_t c1, 
 
 void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint32_t n, uint32_t chunk_idx) {
   std::memset(&P, 0, sizeof P);
-  unsigned int *work = m->d_work + 1 + kChunkWords * chunk_idx;
+  unsigned int *work = m->d_work + 2 + kChunkWords * chunk_idx;
+  P.set_ovf = m->d_set_ovf;
+  P.task_ovf = m->d_task_ovf;
+  P.ovf_count = m->d_work + 1;
+  P.ovf_cap = m->ovf_cap;
   if (m->use_tasks) {
     // the sub-batch's own regions of the task lists, results, traceback arena: items [c0, c0 + n) + its slack
     P.tasks = m->d_tasks;
@@ -875,6 +883,12 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     ABG_M(cudaMalloc(&m->d_sets, (size_t)max_batch * m->n_pass * (ab2dev::kSetStateWords + m->set_slots) * sizeof(uint64_t)));
     ABG_M(cudaMalloc(&m->d_redo_flag, (size_t)max_batch * sizeof(unsigned int)));
     ABG_M(cudaMalloc(&m->d_redo_list, (size_t)max_batch * sizeof(uint32_t)));
+    if (m->paired) {
+      const uint64_t cap = std::min<uint64_t>((uint64_t)max_batch * kOvfPerItem + (1u << 20), 0x7fffffffull);
+      m->ovf_cap = (uint32_t)cap;
+      ABG_M(cudaMalloc(&m->d_set_ovf, cap * sizeof(uint64_t)));
+      ABG_M(cudaMalloc(&m->d_task_ovf, cap * sizeof(uint32_t)));
+    }
     if (m->use_tasks) {
       // every sub-batch owns the part of the arenas that belongs to its items plus one slack region (task slots
       // and traceback words are handed to the warps of enum_kernel in blocks; a warp's last block stays part empty)
@@ -977,6 +991,8 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFree(m->d_task_res);
   cudaFree(m->d_task_tb);
   cudaFree(m->d_task_of);
+  cudaFree(m->d_set_ovf);
+  cudaFree(m->d_task_ovf);
   for (cudaEvent_t e : m->ev_t)
     if (e) cudaEventDestroy(e);
   cudaFreeHost(m->h_flags);
@@ -1041,7 +1057,7 @@ int abg_mapper_run(abg_mapper *m) {
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ab2dev::KernelParams P;
   fill_params(m, P, 0, m->cur_n, 0);
-  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, (1 + kChunkWords) * sizeof(unsigned int), m->stream));
+  ABG_CUDA(cudaMemsetAsync(m->d_work, 0, (2 + kChunkWords) * sizeof(unsigned int), m->stream));
   if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->stream));
   ABG_CUDA(cudaEventRecord(m->ev0, m->stream));
   int rc;

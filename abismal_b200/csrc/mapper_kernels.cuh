@@ -161,6 +161,12 @@ struct KernelParams {
   unsigned int *task_cursor; // [0..2] dp_kernel's work cursors
   uint32_t task_base[3], task_cap[3];
   uint32_t task_tb_cap;      // units of 8 words
+  // stored candidate sets larger than set_slots entries (repeats): the entries beyond live in an arena that the
+  // seeding kernel allocates from; task_ovf holds their task ids at the same offsets
+  uint64_t *set_ovf;
+  uint32_t *task_ovf;
+  unsigned int *ovf_count;
+  uint32_t ovf_cap;
 };
 
 // ---- 64-bit view of se_element {int16 diffs; uint16 flags; uint32 pos} -------
@@ -204,6 +210,8 @@ struct CandState {  // scalar state of one se_candidates / pe_candidates
   int sz, cutoff, good_cutoff, capacity;
   int sure_ambig, is_pe;
   uint64_t best;  // SE only
+  uint32_t ovf;   // stored PE set: 1 + offset of its entries beyond set_slots in KernelParams::set_ovf, 0 = none
+  uint32_t pad;
 };
 
 struct AlnOut {
@@ -243,7 +251,7 @@ constexpr uint32_t kLayoutFull = 0, kLayoutSeed = 1, kLayoutAlign = 2;
 #endif
 
 struct WarpLayout {
-  uint32_t o_packed, o_masks, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, total;
+  uint32_t o_packed, o_masks, o_planes, o_se, o_pe, o_cs, o_scal, o_tb, o_log, o_elig, o_base, o_qcode, o_refb, o_stage, total;
   uint32_t plane_words, elig_words, mask_words;
 };
 
@@ -265,6 +273,8 @@ __host__ __device__ __forceinline__ WarpLayout warp_layout(uint32_t ml, bool pai
   if (aln) o += 2u * tb_sm_words(ml) * kTbLanesSm * 8u;  // traceback words of 2 slots
   L.o_log = o;
   if (seed) o += 2u * kLogCap * 4u;          // survivor log: positions + packed (d, pm, table, offset)
+  L.o_stage = o;
+  if (seed) o += 32u * 12u;                  // survivors of one compare round, staged for the single-lane heap replay
   L.elig_words = ml / 64u + 1u;              // specific offsets are < readlen / 2
   L.o_elig = o;
   if (seed) o += 2u * L.elig_words * 4u;
@@ -318,6 +328,7 @@ struct Warp {  // view of this warp's shared memory; rebuilt (cheaply) inside ev
   __device__ __forceinline__ uint32_t *masks(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_masks) + k * L.mask_words; }
   __device__ __forceinline__ uint32_t *log_pos() const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_log); }
   __device__ __forceinline__ uint32_t *log_meta() const { return log_pos() + kLogCap; }
+  __device__ __forceinline__ uint32_t *stage() const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_stage); }
   __device__ __forceinline__ uint32_t *elig(int k) const { return reinterpret_cast<uint32_t *>(base_ptr + L.o_elig) + k * L.elig_words; }
   __device__ __forceinline__ size_t slot() const {
     return (size_t)params().slot_base + (size_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -377,6 +388,17 @@ struct CandSet {
       s->best = best.w;
     }
     __syncwarp();
+  }
+
+  __device__ __forceinline__ void store_one_lane(const Warp &W, int id) const {  // caller: one lane, syncs around it
+    CandState *s = W.cs(id);
+    s->sz = sz;
+    s->cutoff = cutoff;
+    s->good_cutoff = good_cutoff;
+    s->capacity = capacity;
+    s->sure_ambig = sure_ambig;
+    s->is_pe = is_pe;
+    s->best = best.w;
   }
 
   __device__ __forceinline__ bool full() const { return sz == (is_pe ? capacity : kSeMax); }
@@ -962,19 +984,29 @@ __device__ __forceinline__ void compare_chunk(const IndexDev &ix, const uint32_t
 // Ordered replay of the survivors of one compare round against candidate set `set_id`
 // (check_hits' `if (diffs <= res.cutoff) res.update(...)`, abismal.cpp:1146-1147, in bucket order).
 // Kept out of line: survivors are rare, and the heap code must not bloat the gather loop.
+// The candidate sets are mutated by ONE lane (between warp syncs): the heap routines read and write the same
+// shared-memory words many times over, which is only well defined within a single thread.
 __device__ __noinline__ void replay_hits(int set_id, uint32_t strand_code, unsigned mask, int d, int pm, uint32_t pos) {
   const Warp W;
-  CandSet res;
-  res.load(W, set_id);
-  while (mask != 0u && !res.sure_ambig) {
-    const int l = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const int dd = __shfl_sync(FULL, d, l);
-    const int mm = __shfl_sync(FULL, pm, l);
-    const uint32_t pp = __shfl_sync(FULL, pos, l);
-    if (mm <= res.cutoff) res.update(true, dd, strand_code, pp);  // check_hits<.., true> in both phases
+  uint32_t *stg = W.stage();  // [32][3]: d, pm, pos of the survivors in lane (= canonical) order
+  __syncwarp();
+  if ((mask >> W.lane) & 1u) {
+    const int k = __popc(mask & ((1u << W.lane) - 1u));
+    stg[3 * k] = (uint32_t)d;
+    stg[3 * k + 1] = (uint32_t)pm;
+    stg[3 * k + 2] = pos;
   }
-  res.store(W, set_id);
+  __syncwarp();
+  if (W.lane == 0) {
+    const int n = __popc(mask);
+    CandSet res;
+    res.load(W, set_id);
+    for (int k = 0; k < n && !res.sure_ambig; ++k)
+      if ((int)stg[3 * k + 1] <= res.cutoff)
+        res.update(true, (int)stg[3 * k], strand_code, stg[3 * k + 2]);  // check_hits<.., true> in both phases
+    res.store_one_lane(W, set_id);
+  }
+  __syncwarp();
 }
 
 // survivor-log entry: d (11 bits) | pm (11 bits) | three-letter table (1 bit) | seed offset (9 bits)
@@ -989,17 +1021,21 @@ __device__ __noinline__ void replay_log(int set_id, uint32_t strand_code, int n_
   const Warp W;
   const uint32_t *lp = W.log_pos(), *lm = W.log_meta();
   const uint32_t *e2 = W.elig(0), *e3 = W.elig(1);
-  CandSet res;
-  res.load(W, set_id);
-  for (int k = 0; k < n_log && !res.sure_ambig; ++k) {
-    const uint32_t m = lm[k];
-    const uint32_t off = m >> 23, is3 = (m >> 22) & 1u;
-    const uint32_t ew = (is3 ? e3 : e2)[off >> 5];
-    if (((ew >> (off & 31u)) & 1u) == 0u) continue;  // bucket not examined by the sensitive phase
-    const int d = (int)(m & 2047u), pm = (int)((m >> 11) & 2047u);
-    if (pm <= res.cutoff) res.update(true, d, strand_code, lp[k]);
+  __syncwarp();
+  if (W.lane == 0) {  // one lane mutates the set (see replay_hits)
+    CandSet res;
+    res.load(W, set_id);
+    for (int k = 0; k < n_log && !res.sure_ambig; ++k) {
+      const uint32_t m = lm[k];
+      const uint32_t off = m >> 23, is3 = (m >> 22) & 1u;
+      const uint32_t ew = (is3 ? e3 : e2)[off >> 5];
+      if (((ew >> (off & 31u)) & 1u) == 0u) continue;  // bucket not examined by the sensitive phase
+      const int d = (int)(m & 2047u), pm = (int)((m >> 11) & 2047u);
+      if (pm <= res.cutoff) res.update(true, d, strand_code, lp[k]);
+    }
+    res.store_one_lane(W, set_id);
   }
-  res.store(W, set_id);
+  __syncwarp();
 }
 
 // 2 adjacent counters of bucket k; the L2-resident emptiness bitmap (when present) filters out empty buckets
@@ -1651,6 +1687,14 @@ __device__ __forceinline__ int build_cigar(int tb_slot, int diffs, const AlnOut 
   return nm;
 }
 
+// task id of entry j of a stored set (tof: its set_slots ids; entries beyond: the overflow arena at the set's offset)
+__device__ __forceinline__ uint32_t task_id_of(const uint32_t *tof, int j, uint32_t ovf) {
+  if (tof == nullptr) return kNoTask;
+  const KernelParams &P = params();
+  if ((uint32_t)j < P.set_slots) return __ldcg(tof + j);
+  return ovf != 0u ? __ldcg(P.task_ovf + (ovf - 1u) + ((uint32_t)j - P.set_slots)) : kNoTask;
+}
+
 __device__ __forceinline__ bool same_pos(uint32_t a, uint32_t b) { return (a > b ? a - b : b - a) <= 3u; }
 
 // align_se_candidates (abismal.cpp:1435-1497) on se set `end`
@@ -1677,7 +1721,6 @@ __device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uin
   uint32_t best_pos = 0, best_task = kNoTask;
   if (task_of == nullptr) sort_unique(end);  // enum_kernel has done it otherwise
   const HeapRef v = heap_of(W, end);
-  const uint32_t n_slots = params().set_slots;
   int it = 0;
   const int lim = st->sz;
   for (; it != lim && v.get(it).empty(); ++it) {
@@ -1690,7 +1733,7 @@ __device__ __noinline__ uint64_t align_se_candidates(int end, double cutoff, uin
     const Hit h = v.get(it);
     if (h.diffs() < invalid) {
       const uint32_t cand_pos = h.pos();
-      const uint32_t tid = (task_of != nullptr && (uint32_t)it < n_slots) ? __ldcg(task_of + it) : kNoTask;
+      const uint32_t tid = task_id_of(task_of, it, 0u);
       const int cand_scr =
         (int)(int16_t)align(record_tb, false, 0, end, h.flags(), h.diffs(), max_diffs, q_sz, cand_pos, ao, tid);
       if (cand_scr > best_scr) {
@@ -1774,7 +1817,7 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
   const uint32_t min_dist = P.min_dist, max_dist = P.max_dist;
   int scr1 = 0, best_scr1 = 0, best_scr2 = 0;
   uint32_t best_pos1 = 0, best_pos2 = 0, best_t1 = kNoTask, best_t2 = kNoTask;
-  const uint32_t n_slots = P.set_slots;
+  const uint32_t ovf1 = W.cs(2)->ovf, ovf2 = W.cs(3)->ovf;
   AlnOut ao;
 
   for (; j1 != j1_end && v1.get(j1).empty(); ++j1) {
@@ -1793,8 +1836,7 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
     for (; j1 != j1_end && !best.sure_ambig(); ++j1) {
       const Hit s1 = v1.get(j1);
       if (!(s1.pos() + min_dist <= lim)) break;
-      const uint32_t t2 = (tof2 != nullptr && (uint32_t)j2 < n_slots) ? __ldcg(tof2 + j2) : kNoTask;
-      const uint32_t t1 = (tof1 != nullptr && (uint32_t)j1 < n_slots) ? __ldcg(tof1 + j1) : kNoTask;
+      const uint32_t t2 = task_id_of(tof2, j2, ovf2), t1 = task_id_of(tof1, j1, ovf1);
       if (scr2 == 0)
         scr2 = (int)(int16_t)align(rec2, false, e2, e2, flags2, s2.diffs(), max_diffs2, (int)readlen2, s2.pos(), ao, t2);
       int m1 = *(volatile int16_t *)(mem_scr + j1);
@@ -1845,13 +1887,17 @@ __device__ __noinline__ void best_single(int pe_id, int se_id) {
   const Warp W;
   const HeapRef pv = heap_of(W, pe_id);
   const int n = W.cs(pe_id)->sz;
-  CandSet res;
-  res.load(W, se_id);
-  for (int i = 0; i != n && !res.sure_ambig; ++i) {
-    const Hit h = pv.get(i);
-    res.update(false, h.diffs(), h.flags(), h.pos());
+  __syncwarp();
+  if (W.lane == 0) {  // one lane mutates the set (see replay_hits)
+    CandSet res;
+    res.load(W, se_id);
+    for (int i = 0; i != n && !res.sure_ambig; ++i) {
+      const Hit h = pv.get(i);
+      res.update(false, h.diffs(), h.flags(), h.pos());
+    }
+    res.store_one_lane(W, se_id);
   }
-  res.store(W, se_id);
+  __syncwarp();
 }
 
 // format_se's test for writing a record (abismal.cpp:486-487)
@@ -1866,17 +1912,22 @@ __device__ __forceinline__ abg_hit to_abg(Hit h) {
 }
 
 __device__ __forceinline__ void reset_set(const Warp &W, int id, int kind, uint32_t readlen) {
-  CandSet s;
-  s.v = heap_of(W, id);
-  s.capacity = kSeMax;
-  s.good_cutoff = 0;
-  if (kind == 0) s.reset_se(readlen);
-  else if (kind == 1) s.reset_pe(readlen);
-  else {
-    s.load(W, id);
-    s.reset_se_noarg();
+  __syncwarp();
+  if (W.lane == 0) {
+    CandSet s;
+    s.v = heap_of(W, id);
+    s.capacity = kSeMax;
+    s.good_cutoff = 0;
+    if (kind == 0) s.reset_se(readlen);
+    else if (kind == 1) s.reset_pe(readlen);
+    else {
+      s.load(W, id);
+      s.reset_se_noarg();
+    }
+    s.store_one_lane(W, id);
+    W.cs(id)->ovf = 0u;
   }
-  s.store(W, id);
+  __syncwarp();
 }
 
 // bit k of `bits` = bucket k is non-empty; *n_set += number of non-empty buckets (n = counter_size)
@@ -2048,39 +2099,70 @@ __device__ __forceinline__ CallPlan call_plan(int call, bool rpbat, bool a_rich)
   return c;
 }
 
-// candidate set `id` <-> its stored form (kSetStateWords of state, then the heap entries)
-__device__ __forceinline__ void store_set(const Warp &W, int id, uint64_t *dst, int slots) {
+// candidate set `id` <-> its stored form (kSetStateWords of state, then the first `slots` heap entries; a paired-end
+// set with more entries keeps the rest in the overflow arena).  alloc: reserve arena space when the set needs
+// it and has none yet (the seeding kernel; later stores reuse the reservation, sets only shrink).  Returns
+// false when the set does not fit (arena full): the caller leaves the pair to the redo kernel.
+__device__ __forceinline__ bool store_set(const Warp &W, int id, uint64_t *dst, int slots, bool alloc = false) {
   __syncwarp();
-  const CandState *st = W.cs(id);
+  const KernelParams &P = params();
+  CandState *st = W.cs(id);
   const HeapRef v = heap_of(W, id);
   const int sz = st->sz;
+  uint32_t ovf = st->is_pe ? st->ovf : 0u;
+  bool ok = true;
+  if (sz > slots) {
+    if (ovf == 0u && alloc && st->is_pe && P.set_ovf != nullptr) {
+      uint32_t off = 0;
+      if (W.lane == 0) off = atomicAdd(P.ovf_count, (unsigned int)(sz - slots));
+      off = __shfl_sync(FULL, off, 0);
+      if (off + (uint32_t)(sz - slots) <= P.ovf_cap) ovf = off + 1u;
+    }
+    ok = ovf != 0u;
+  }
+  __syncwarp();
   if (W.lane == 0) {
+    st->ovf = ovf;
     dst[0] = (uint64_t)(uint32_t)st->sz | ((uint64_t)(uint32_t)st->cutoff << 32);
     dst[1] = (uint64_t)(uint32_t)st->good_cutoff | ((uint64_t)(uint32_t)st->capacity << 32);
     dst[2] = (uint64_t)(uint32_t)st->sure_ambig | ((uint64_t)(uint32_t)st->is_pe << 32);
-    dst[3] = st->best;
+    dst[3] = st->is_pe ? (uint64_t)ovf : st->best;
   }
   for (int i = W.lane; i < sz && i < slots; i += 32) dst[kSetStateWords + i] = v.get(i).w;
+  if (ovf != 0u) {
+    uint64_t *o = P.set_ovf + (ovf - 1u);
+    for (int i = slots + W.lane; i < sz; i += 32) o[i - slots] = v.get(i).w;
+  }
   __syncwarp();
+  return ok;
 }
 __device__ __forceinline__ void load_set(const Warp &W, int id, const uint64_t *src) {
   __syncwarp();
+  const KernelParams &P = params();
   CandState *st = W.cs(id);
   const HeapRef v = heap_of(W, id);
   // __ldcg: the sets may have been written by seed_kernel on another SM while this kernel was already
   // running (overlapped launch); a neighbouring item's 128-byte line in L1 could predate them.
   const uint64_t w0 = __ldcg(src), w1 = __ldcg(src + 1), w2 = __ldcg(src + 2), w3 = __ldcg(src + 3);
   const int sz = (int)(uint32_t)w0;
+  const int is_pe = (int)(uint32_t)(w2 >> 32);
+  const uint32_t ovf = is_pe ? (uint32_t)w3 : 0u;
   if (W.lane == 0) {
     st->sz = sz;
     st->cutoff = (int)(uint32_t)(w0 >> 32);
     st->good_cutoff = (int)(uint32_t)w1;
     st->capacity = (int)(uint32_t)(w1 >> 32);
     st->sure_ambig = (int)(uint32_t)w2;
-    st->is_pe = (int)(uint32_t)(w2 >> 32);
-    st->best = w3;
+    st->is_pe = is_pe;
+    st->best = is_pe ? 0ull : w3;
+    st->ovf = ovf;
   }
-  for (int i = W.lane; i < sz; i += 32) v.set(i, Hit(__ldcg(src + kSetStateWords + i)));
+  const int slots = (int)P.set_slots;
+  for (int i = W.lane; i < sz && i < slots; i += 32) v.set(i, Hit(__ldcg(src + kSetStateWords + i)));
+  if (ovf != 0u) {
+    const uint64_t *o = P.set_ovf + (ovf - 1u);
+    for (int i = slots + W.lane; i < sz; i += 32) v.set(i, Hit(__ldcg(o + (i - slots))));
+  }
   __syncwarp();
 }
 
@@ -2408,10 +2490,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
         load_end(W, end, P.seq[end] + o, len);
         process_seeds(2, end, flags);
       }
-      if (W.cs(2)->sz > (int)P.set_slots) {  // grew beyond the stored form (repeats): the whole pair is redone
+      if (!store_set(W, 2, stored_set(P, item, pass), (int)P.set_slots, true)) {
+        // grew beyond the stored form and the overflow arena is full (or absent): the whole pair is redone
         if (lane == 0 && atomicExch(P.redo_flag + item, 1u) == 0u) P.redo_list[atomicAdd(P.redo_count, 1u)] = item;
       }
-      store_set(W, 2, stored_set(P, item, pass), (int)P.set_slots);
       publish_set(P, item, lane);
     }
   }
