@@ -202,14 +202,19 @@ class MapPipeline {
 public:
   MapPipeline(const MapConfig &cfg, const ab2::IndexFile &index, const std::string &fq1, const std::string &fq2,
               FILE *out)
-    : cfg_(cfg), index_(index), out_(out), rl1_(fq1), n_items_(4 + 2 * cfg.devices.size() * cfg.workers_per_gpu),
-      free_(n_items_), q12_(n_items_), to_map_(n_items_), to_out_(n_items_), pool_(cfg.n_threads) {
-    if (cfg.paired_end) rl2_.reset(new ab2::FastqReader(fq2));
+    : cfg_(cfg), index_(index), out_(out), rl1_(fq1, parse_helpers(cfg)),
+      n_items_(4 + 2 * cfg.devices.size() * cfg.workers_per_gpu), free_(n_items_), q12_(n_items_), to_map_(n_items_),
+      to_out_(n_items_), pool_(cfg.n_threads), free_blocks_(kOutBlocks), to_disk_(kOutBlocks) {
+    if (cfg.paired_end) rl2_.reset(new ab2::FastqReader(fq2, parse_helpers(cfg)));
     rl1_.set_window_size(index.window_size);
     if (rl2_) rl2_->set_window_size(index.window_size);
     items_.resize(n_items_);
     for (WorkItem &it : items_) free_.push(&it);
+    for (OutBlock &b : blocks_) free_blocks_.push(&b);
   }
+
+  // threads each FASTQ reader parses whole records with (a quarter of -t per file, at least one)
+  static unsigned parse_helpers(const MapConfig &cfg) { return std::max(1u, cfg.n_threads / 4u); }
 
   void run() {
     std::vector<std::thread> th;
@@ -225,6 +230,7 @@ public:
       for (uint32_t w = 0; w < cfg_.workers_per_gpu; ++w)
         th.emplace_back([this, dev, w, pr, fut] { guarded([&] { map_on(dev, w == 0 ? pr.get() : nullptr, fut); }); });
     }
+    th.emplace_back([this] { guarded([this] { format_out(); }); });
     th.emplace_back([this] { guarded([this] { write_out(); }); });
     for (std::thread &t : th) t.join();
     if (error_) std::rethrow_exception(error_);
@@ -251,6 +257,8 @@ private:
       q12_.close();
       to_map_.close();
       to_out_.close();
+      free_blocks_.close();
+      to_disk_.close();
     }
   }
 
@@ -380,11 +388,12 @@ private:
     if (cfg_.write_bam) packer.finish();
   }
 
-  void write_out() {
-    std::map<uint64_t, WorkItem *> waiting;  // multi-GPU: batches finish out of order
+  // Formatter stage: batches in input order (multi-GPU: they finish out of order), each formatted by the pool
+  // into one output block, which the writer thread puts on disk while the next batch is being formatted.
+  void format_out() {
+    std::map<uint64_t, WorkItem *> waiting;
     uint64_t next = 0;
     const unsigned n_slices = std::max(1u, pool_.size() * 2);
-    std::vector<std::string> bytes(n_slices);
     std::vector<ab2::SeStats> ss(n_slices);
     std::vector<ab2::PeStats> ps(n_slices);
     WorkItem *in = nullptr;
@@ -396,30 +405,46 @@ private:
         ++next;
         const uint32_t n = w->b1.size();
         if (n != 0) {
+          OutBlock *blk = nullptr;
+          if (!free_blocks_.pop(blk)) return;
+          blk->bytes.resize(n_slices);
           {
             StageClock::Scope sc(t_format);
             pool_.run(n_slices, [&](unsigned k) {
               const uint32_t i0 = static_cast<uint32_t>(static_cast<uint64_t>(n) * k / n_slices);
               const uint32_t i1 = static_cast<uint32_t>(static_cast<uint64_t>(n) * (k + 1) / n_slices);
-              bytes[k].clear();
+              blk->bytes[k].clear();
               ss[k] = ab2::SeStats();
               ps[k] = ab2::PeStats();
-              format_slice(*w, i0, i1, bytes[k], ss[k], ps[k]);
+              format_slice(*w, i0, i1, blk->bytes[k], ss[k], ps[k]);
             });
           }
-          StageClock::Scope sc(t_write);
           for (unsigned k = 0; k < n_slices; ++k) {
-            if (!bytes[k].empty() && std::fwrite(bytes[k].data(), 1, bytes[k].size(), out_) != bytes[k].size())
-              throw std::runtime_error("failed to write bam");
             se_stats.add(ss[k]);
             pe_stats.add(ps[k]);
           }
           n_done += n;
+          if (!to_disk_.push(blk)) return;
         }
         free_.push(w);
       }
     }
     free_.close();
+    to_disk_.close();
+  }
+
+  void write_out() {
+    OutBlock *blk = nullptr;
+    while (!failed_ && to_disk_.pop(blk)) {
+      {
+        StageClock::Scope sc(t_write);
+        for (const std::string &b : blk->bytes)
+          if (!b.empty() && std::fwrite(b.data(), 1, b.size(), out_) != b.size())
+            throw std::runtime_error("failed to write bam");
+      }
+      free_blocks_.push(blk);
+    }
+    free_blocks_.close();
   }
 
   const MapConfig &cfg_;
@@ -431,6 +456,12 @@ private:
   std::vector<WorkItem> items_;
   ab2::BoundedQueue<WorkItem *> free_, q12_, to_map_, to_out_;
   ab2::WorkerPool pool_;
+  static constexpr size_t kOutBlocks = 3;
+  struct OutBlock {
+    std::vector<std::string> bytes;  // one slice per formatter job, in order
+  };
+  OutBlock blocks_[kOutBlocks];
+  ab2::BoundedQueue<OutBlock *> free_blocks_, to_disk_;
   std::atomic<bool> failed_{false}, stop_reading_{false};
   std::atomic<int> n_mappers_live_{0};
   std::mutex err_mu_;

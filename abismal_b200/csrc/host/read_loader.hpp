@@ -4,6 +4,7 @@
 #define ABISMAL_B200_READ_LOADER_HPP
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -32,12 +33,14 @@ public:
   void set_window_size(uint32_t w) { min_read_length = 25 + w - 1; }
   static constexpr size_t padding_size = 32767;              // seed::padding_size
 
-  explicit FastqReader(const std::string &filename);
+  // n_helpers > 1: whole records already in the buffer are parsed by that many threads at a time (the trim rules
+  // and the copies into the batch are independent per record; results and errors are those of the serial path)
+  explicit FastqReader(const std::string &filename, unsigned n_helpers = 1);
   ~FastqReader();
   FastqReader(const FastqReader &) = delete;
   FastqReader &operator=(const FastqReader &) = delete;
 
-  bool is_open() const { return file_ != nullptr; }
+  bool is_open() const { return file_ != nullptr || map_ != nullptr; }
   // true until a read attempt has hit end of file (ReadLoader::operator bool)
   bool good() const { return !eof_; }
   // Appends up to max_reads reads to `out` (cleared first).  Throws
@@ -50,10 +53,21 @@ private:
   bool fill();
   bool fill_more();
   bool fast_record(ReadBatch &out);
+  size_t parse_block(ReadBatch &out, size_t max_records);
   void push_read(ReadBatch &out, const char *name, size_t name_len, const char *line, size_t len);
 
   std::string filename_;
-  void *file_ = nullptr;  // gzFile
+  std::unique_ptr<WorkerPool> pool_;
+  std::vector<std::vector<uint32_t>> nl_parts_;  // newline offsets found by each helper
+  std::vector<uint32_t> nl_;
+  struct Span {
+    uint32_t name_at, name_len, seq_at, seq_len;
+  };
+  std::vector<Span> spans_;
+  void *file_ = nullptr;  // gzFile (compressed input, pipes)
+  const char *map_ = nullptr;  // read-only mapping of a plain file
+  size_t map_len_ = 0;
+  const char *data_ = nullptr;  // buf_.data() or map_
   std::vector<char> buf_;
   size_t beg_ = 0, end_ = 0;
   std::string carry_;

@@ -88,6 +88,16 @@ def test_fastq_rules_equal_reference(workspace):
     for k, f in enumerate(("tests/rules_1.fq.gz", "tests/rules_crlf_1.fq")):
         out = helpers.sam_body(workspace.map_with(helpers.ORACLE_MAP, "g%d" % (k + 1), ["-i", "tests/tRex1.idx", f])[0])
         assert out[3:] == base[3:]
+    # block mode of the FASTQ readers (-t 8 and up: several threads parse whole records of a mapped file or of
+    # the zlib buffer): same records, same skips, for plain, gz and CRLF input, single and paired
+    for k, f in enumerate(("tests/rules_1.fq", "tests/rules_1.fq.gz", "tests/rules_crlf_1.fq")):
+        out = helpers.sam_body(workspace.map_with(helpers.ORACLE_MAP, "h%d" % k, ["-i", "tests/tRex1.idx", f],
+                                                  pre=["-t", "16", "-gpu-batch", "7"])[0])
+        assert out[3:] == base[3:]
+    ref = workspace.map_with(helpers.REF_BIN, "ref_rules_pe", ["-i", "tests/tRex1.idx", "tests/rules_1.fq", "tests/rules_2.fq"])
+    got = workspace.map_with(helpers.ORACLE_MAP, "or_rules_pe_t16",
+                             ["-i", "tests/tRex1.idx", "tests/rules_1.fq", "tests/rules_2.fq"], pre=["-t", "16"])
+    assert helpers.sam_body(ref[0]) == helpers.sam_body(got[0]) and open(ref[1]).read() == open(got[1]).read()
 
 
 def test_pe_count_mismatch_is_an_error(workspace):

@@ -47,6 +47,18 @@ int main(int argc, char **argv) {
   const double parse_s = now() - t;
   std::printf("parse   : %zu reads (%zu bases) in %.3f s -> %.2f M reads/s per thread\n", n_reads, n_bases, parse_s,
               n_reads / parse_s / 1e6);
+  for (unsigned helpers : {2u, 4u, 8u}) {  // block mode: whole records parsed by several threads per reader
+    t = now();
+    size_t n_par = 0;
+    ab2::FastqReader r1(argv[2], helpers);
+    ab2::ReadBatch tmp;
+    while (r1.good()) {
+      r1.load_reads(tmp, 1u << 18);
+      n_par += tmp.size();
+    }
+    const double s = now() - t;
+    std::printf("parse x%u: %zu reads in %.3f s -> %.2f M reads/s per reader\n", helpers, n_par, s, n_par / s / 1e6);
+  }
 
   // ---- records to format: the oracle's results on the first n_map pairs ----
   {
