@@ -114,6 +114,14 @@ def load_library():
     lib.abg_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.abg_host_free.argtypes = [C.c_void_p]
     lib.abg_host_free.restype = None
+    lib.abg_mapper_last_seed_times.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.abg_mapper_last_seed_times.restype = None
+    lib.abg_mapper_binned.argtypes = [C.c_void_p]
+    lib.abg_mapper_binned.restype = C.c_int
+    lib.abg_mapper_bin_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.abg_mapper_bin_stats.restype = C.c_int
+    lib.abg_mapper_last_run_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.abg_mapper_last_run_stats.restype = C.c_int
     lib.abg_mapper_chunk.argtypes = [C.c_void_p]
     lib.abg_mapper_chunk.restype = C.c_uint32
     _lib = lib
@@ -345,6 +353,34 @@ class Mapper:
     @property
     def launches_per_run(self):
         return int(self.lib.abg_mapper_launches_per_run(self._h))
+
+    SEED_KERNELS = ("hash_kernel", "scatter_kernel", "filter_kernel", "seed_kernel")
+
+    @property
+    def last_seed_times(self):
+        """CUDA-event ms of the seeding kernels of the last run(), in the order of Mapper.SEED_KERNELS (binned
+        seeding; their sum is last_kernel_times[0])."""
+        out = (C.c_float * 4)()
+        self.lib.abg_mapper_last_seed_times(self._h, out)
+        return [float(x) for x in out]
+
+    @property
+    def binned(self):
+        """True when the mapper seeds through the binned kernels (seed_bins.cuh)."""
+        return bool(self.lib.abg_mapper_binned(self._h))
+
+    def bin_stats(self):
+        out = (C.c_uint64 * 6)()
+        self._check(self.lib.abg_mapper_bin_stats(self._h, out))
+        keys = ("strands", "strands_direct", "tuples", "survivors", "bins", "tuple_cap")
+        return dict(zip(keys, [int(x) for x in out]))
+
+    def last_run_stats(self):
+        """Diagnostics of the last run(): redo pairs, set-arena use, tasks per band class (abg_mapper_last_run_stats)."""
+        out = (C.c_uint32 * 8)()
+        self._check(self.lib.abg_mapper_last_run_stats(self._h, out))
+        keys = ("redo_pairs", "set_arena_used", "set_arena_cap", "tasks_bw16", "tasks_bw32", "tasks_bw61", "tb_units", "error_flag")
+        return dict(zip(keys, [int(x) for x in out]))
 
     def counters(self):
         c = abg_work_counters()

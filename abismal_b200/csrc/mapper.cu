@@ -18,6 +18,7 @@
 #include "abismal_b200.h"
 #include "mapper_kernels.cuh"
 #include "align_tasks.cuh"
+#include "seed_bins.cuh"
 
 namespace {
 
@@ -108,7 +109,7 @@ constexpr uint32_t kInlineOps = 16;   // CIGAR ops per read copied back with the
 constexpr uint32_t kMaxChunks = 256;  // sub-batches one abg_map_batch call is pipelined over
 // device words per sub-batch: work counters of map / seed / align, redo count, work counter of enum_kernel,
 // task slots handed out per class [3] + traceback units, dp_kernel's cursors [3]
-constexpr uint32_t kChunkWords = 12;
+constexpr uint32_t kChunkWords = 14;  // ... [12] hash_kernel's work counter (binned seeding), [13] spare
 constexpr uint32_t kWorkWords = 2 + kChunkWords * kMaxChunks;  // [0] error flag, [1] cursor of the set overflow arena
 constexpr uint32_t kOvfPerItem = 32;  // overflow arena entries per pair of max_batch (sets beyond set_slots entries)
 // task-parallel alignment: slots per read / pair in the three task lists (bands <= 16 / <= 32 / <= 61 columns) and
@@ -162,6 +163,20 @@ struct abg_mapper {
   uint32_t ovf_cap = 0;
   cudaEvent_t ev_t[2] = {nullptr, nullptr};  // abg_mapper_run: after enum_kernel, after dp_kernel
   float task_ms[2] = {0.f, 0.f};
+  // binned seeding (seed_bins.cuh): hash_kernel -> scatter_kernel -> filter_kernel in front of seed_kernel
+  bool use_bins = false;
+  uint32_t spi = 1, bin_shift = 0, n_bins = 0, tup_cap = 0, pw = 0, surv_cap = 0;
+  const void *kernel_h = nullptr;
+  int grid_h = 0, grid_sc = 0, grid_f = 0;
+  ab2dev::SeedTuple *d_tup = nullptr, *d_tup_b = nullptr;
+  uint4 *d_pay_b = nullptr;
+  uint32_t *d_planes = nullptr, *d_bin_hist = nullptr, *d_surv_count = nullptr;
+  uint8_t *d_strand_flag = nullptr;
+  uint2 *d_surv = nullptr;
+  unsigned int *d_bin_work = nullptr;  // [0] tuple slots handed out, [1] tuples binned, [2] filter_kernel's work cursor
+  cudaEvent_t ev_b[3] = {nullptr, nullptr, nullptr};  // abg_mapper_run: after hash_kernel, scatter_kernel, filter_kernel
+  cudaEvent_t ev_bins = nullptr;                      // abg_map_batch: the batch's tuples are filtered
+  float bin_ms[3] = {0.f, 0.f, 0.f};
   uint64_t *d_sets = nullptr;
   unsigned int *d_redo_flag = nullptr;
   uint32_t *d_redo_list = nullptr;
@@ -247,6 +262,26 @@ void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint
     P.redo_list = m->d_redo_list + c0;
     P.redo_count = work + 3;
   }
+  if (m->use_bins) {
+    ab2dev::BinParams &B = P.bp;
+    B.tup = m->d_tup;
+    B.tup_count = m->d_bin_work;
+    B.tup_cap = m->tup_cap;
+    B.pw = m->pw;
+    B.planes = m->d_planes;
+    B.strand_flag = m->d_strand_flag;
+    B.bin_hist = m->d_bin_hist;
+    B.bin_shift = m->bin_shift;
+    B.n_bins = m->n_bins;
+    B.rec_base[0] = 0;
+    B.rec_base[1] = (uint64_t)ab2dev::kCtxArrays * m->idx->dev.n_ctx;
+    B.rec_base[2] = B.rec_base[1] + (uint64_t)ab2dev::kCtxArrays * m->idx->dev.n_ctx3;
+    B.surv_count = m->d_surv_count;
+    B.surv = m->d_surv;
+    B.surv_cap = m->surv_cap;
+    B.spi = m->spi;
+    B.sid_base = c0 * m->spi;
+  }
   P.ix = m->idx->dev;
   P.n = n;
   const uint32_t stride = m->params.cigar_stride;
@@ -300,13 +335,86 @@ int launch_one(const void *kernel, int grid, size_t smem, ab2dev::KernelParams &
   return ABG_OK;
 }
 
+// ---- binned seeding (seed_bins.cuh) ----
+ab2dev::FilterParams filter_params(const abg_mapper *m) {
+  ab2dev::FilterParams F;
+  std::memset(&F, 0, sizeof F);
+  const ab2dev::IndexDev &ix = m->idx->dev;
+  F.tup = m->d_tup;
+  F.tup_count = m->d_bin_work;
+  F.tup_cap = m->tup_cap;
+  F.planes = m->d_planes;
+  F.pw = m->pw;
+  F.bin_shift = m->bin_shift;
+  F.n_bins = m->n_bins;
+  F.rec_base[0] = 0;
+  F.rec_base[1] = (uint64_t)ab2dev::kCtxArrays * ix.n_ctx;
+  F.rec_base[2] = F.rec_base[1] + (uint64_t)ab2dev::kCtxArrays * ix.n_ctx3;
+  F.bin_hist = m->d_bin_hist;
+  F.n_binned = m->d_bin_work + 1;
+  F.tup_b = m->d_tup_b;
+  F.pay_b = m->d_pay_b;
+  F.ctx[0] = ix.ctx;
+  F.ctx[1] = ix.ctx_t;
+  F.ctx[2] = ix.ctx_a;
+  F.n_tab[0] = ix.n_ctx;
+  F.n_tab[1] = F.n_tab[2] = ix.n_ctx3;
+  F.surv_count = m->d_surv_count;
+  F.surv = m->d_surv;
+  F.surv_cap = m->surv_cap;
+  F.work = m->d_bin_work + 2;
+  return F;
+}
+
+// clears the batch-wide state of the binned kernels (n = reads / pairs of the whole batch)
+int reset_bins(const abg_mapper *m, uint32_t n, cudaStream_t st) {
+  ABG_CUDA(cudaMemsetAsync(m->d_bin_work, 0, 4 * sizeof(unsigned int), st));
+  ABG_CUDA(cudaMemsetAsync(m->d_surv_count, 0, (size_t)n * m->spi * 4, st));
+  return ABG_OK;
+}
+
+// hash_kernel over the strands of sub-batch P: appends to the batch's tuple buffer and histogram
+int launch_hash(const abg_mapper *m, const ab2dev::KernelParams &P, cudaStream_t st) {
+  if (P.n == 0) return ABG_OK;
+  ab2dev::KernelParams Q = P;
+  Q.work_counter = P.work_counter + 12;
+  Q.layout_kind = ab2dev::kLayoutSeed;
+  const uint64_t wpb = ab2dev::kWarpsPerBlock;
+  const uint64_t n_work = (uint64_t)P.n * m->spi;
+  void *args[] = {&Q};
+  ABG_CUDA(cudaLaunchKernel(m->kernel_h, dim3((unsigned)std::min<uint64_t>((uint64_t)m->grid_h, (n_work + wpb - 1) / wpb)),
+                            dim3(ab2dev::kThreadsPerBlock), args, m->smem_s, st));
+  return ABG_OK;
+}
+
+// bins of everything hashed since reset_bins: write cursors, scatter (+ payloads), prefilter -> survivor lists
+int launch_bins(const abg_mapper *m, cudaStream_t st, const cudaEvent_t *ev_b = nullptr) {
+  ab2dev::FilterParams F = filter_params(m);
+  const size_t sm = (size_t)m->n_bins * 4;
+  ab2dev::count_kernel<<<m->grid_sc, ab2dev::kScatterThreads, sm, st>>>(F);
+  ab2dev::bin_prefix_kernel<<<1, 1024, 0, st>>>(F, (uint32_t)m->grid_sc);
+  ab2dev::scatter_kernel<<<m->grid_sc, ab2dev::kScatterThreads, sm, st>>>(F);
+  if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[1], st));
+  ab2dev::filter_kernel<<<m->grid_f, 256, 0, st>>>(F);
+  if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[2], st));
+  ABG_CUDA(cudaGetLastError());
+  return ABG_OK;
+}
+
 // One sub-batch on stream st.  Two-phase mode: seeding (one warp per read strand), then alignment/mating (one
 // warp per pair) from the stored candidate sets, then the single-kernel path for the few pairs whose sets
 // outgrew the stored form.  P.work_counter points at this chunk's {map, seed, align} counters + redo count.
-int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const cudaEvent_t *ev_ph = nullptr) {
+int launch(const abg_mapper *m, ab2dev::KernelParams &P, cudaStream_t st, const cudaEvent_t *ev_ph = nullptr,
+           bool bins_done = false) {
   if (P.n == 0) return ABG_OK;
   const uint64_t wpb = ab2dev::kWarpsPerBlock;
   int rc;
+  if (m->use_bins && !bins_done) {  // the sub-batch is the whole batch: hash, bin and filter it here
+    if ((rc = reset_bins(m, P.n, st))) return rc;
+    if ((rc = launch_hash(m, P, st))) return rc;
+    if (ev_ph) ABG_CUDA(cudaEventRecord(m->ev_b[0], st));
+    if ((rc = launch_bins(m, st, ev_ph ? m->ev_b : nullptr))) return rc;
+  }
   if (!m->split) {
     const int grid = (int)std::min<uint64_t>((uint64_t)m->grid, ((uint64_t)P.n + wpb - 1) / wpb);
     P.layout_kind = ab2dev::kLayoutFull;
@@ -876,6 +984,81 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       m->grid_e = n_sm * std::max(per_e, 1);
       m->grid_d = n_sm * std::max(per_d, 1);
     }
+    {
+      // binned seeding (default whenever the index carries seed-context records; ABISMAL_B200_BINS=0: one warp per
+      // strand gathers its own records, the round-1 seeding)
+      const char *e = std::getenv("ABISMAL_B200_BINS");
+      const bool have_ctx = ix->ctx != nullptr && (ix->dev.n_ctx3 == 0 || (ix->ctx_t != nullptr && ix->ctx_a != nullptr));
+      m->use_bins = !(e && std::atoi(e) == 0) && !m->overlap && have_ctx && m->ml / 32u + 5u <= 32u;  // a plane of the read fits one word per lane
+    }
+    if (m->use_bins) {
+      const bool rp = (p->mode & ABG_MODE_RANDOM_PBAT) != 0;
+      m->spi = m->paired ? (rp ? 8u : 4u) : (rp ? 4u : 2u);
+      m->pw = m->ml / 32u + 5u;
+      const uint64_t n_strands = (uint64_t)max_batch * m->spi;
+      const char *ef = std::getenv("ABISMAL_B200_TUPLE_FACTOR");
+      const double factor = (ef && std::atof(ef) > 0.0) ? std::atof(ef) : 1.25;
+      const uint64_t warps = (uint64_t)n_sm * 8 * ab2dev::kWarpsPerBlock;
+      uint64_t cap = (uint64_t)((double)n_strands * (double)(m->ml - 8u) * factor) + warps * ab2dev::kTupleBlock;
+      if (const char *ec = std::getenv("ABISMAL_B200_TUPLE_CAP"))  // testing aid: absolute capacity
+        if (std::atol(ec) > 0) cap = (uint64_t)std::atol(ec);
+      cap = std::min<uint64_t>(cap, 0xfff00000ull) / ab2dev::kTupleBlock * ab2dev::kTupleBlock;
+      cap = std::max<uint64_t>(cap, ab2dev::kTupleBlock);
+      m->tup_cap = (uint32_t)cap;
+      const uint64_t total_rec = (uint64_t)ab2dev::kCtxArrays * (ix->dev.n_ctx + 2 * ix->dev.n_ctx3);
+      const char *es = std::getenv("ABISMAL_B200_BIN_SHIFT");
+      uint32_t shift = (es && std::atoi(es) >= 10 && std::atoi(es) <= 30) ? (uint32_t)std::atoi(es) : 19u;  // 16 MB of records
+      while ((total_rec >> shift) + 1 > ab2dev::kMaxBins) ++shift;
+      m->bin_shift = shift;
+      m->n_bins = (uint32_t)(total_rec >> shift) + 1u;
+      m->surv_cap = ab2dev::kSurvSlots;
+      if (const char *ec = std::getenv("ABISMAL_B200_SURV_CAP"))  // testing aid: fewer listed survivors per strand
+        if (std::atol(ec) > 0) m->surv_cap = std::min<uint32_t>(ab2dev::kSurvSlots, (uint32_t)std::atol(ec));
+      m->kernel_h = (const void *)ab2dev::hash_kernel<4>;
+      if (cudaFuncSetAttribute(m->kernel_h, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        (void)cudaGetLastError();
+      ABG_M(raise_smem_cap(ix->device, m->kernel_h, m->smem_s));
+      int per_h = 0, per_f = 0;
+      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_h, m->kernel_h, ab2dev::kThreadsPerBlock, m->smem_s));
+      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, (const void *)ab2dev::filter_kernel, 256, 0));
+      // any allocation that fails switches the binned path off (the direct path needs none of this memory)
+      bool ok = per_h >= 1 && per_f >= 1;
+      auto grab = [&](void **ptr, size_t bytes) {
+        if (ok && cudaMalloc(ptr, bytes) != cudaSuccess) {
+          (void)cudaGetLastError();
+          ok = false;
+        }
+      };
+      grab((void **)&m->d_tup, cap * sizeof(ab2dev::SeedTuple));
+      grab((void **)&m->d_tup_b, cap * sizeof(ab2dev::SeedTuple));
+      grab((void **)&m->d_pay_b, cap * 32);
+      grab((void **)&m->d_planes, n_strands * 2 * m->pw * 4);
+      grab((void **)&m->d_strand_flag, n_strands);
+      grab((void **)&m->d_bin_hist, (size_t)m->n_bins * n_sm * 4);
+      grab((void **)&m->d_surv_count, n_strands * 4);
+      grab((void **)&m->d_surv, n_strands * m->surv_cap * sizeof(uint2));
+      grab((void **)&m->d_bin_work, 4 * sizeof(unsigned int));
+      if (!ok) {
+        for (void *q : {(void *)m->d_tup, (void *)m->d_tup_b, (void *)m->d_pay_b, (void *)m->d_planes, (void *)m->d_strand_flag,
+                        (void *)m->d_bin_hist, (void *)m->d_surv_count, (void *)m->d_surv, (void *)m->d_bin_work})
+          cudaFree(q);
+        m->d_tup = m->d_tup_b = nullptr;
+        m->d_pay_b = nullptr;
+        m->d_planes = m->d_bin_hist = m->d_surv_count = nullptr;
+        m->d_strand_flag = nullptr;
+        m->d_surv = nullptr;
+        m->d_bin_work = nullptr;
+        m->use_bins = false;
+      }
+      else {
+        m->grid_h = n_sm * per_h;
+        m->grid_sc = n_sm;  // one 1024-thread CTA per SM: its write frontier (one line per bin) stays in L2
+        m->grid_f = n_sm * per_f;
+        for (int k = 0; k < 3; ++k) ABG_M(cudaEventCreate(&m->ev_b[k]));
+        ABG_M(cudaEventCreateWithFlags(&m->ev_bins, cudaEventDisableTiming));
+        grid_max = std::max(grid_max, m->grid_h);
+      }
+    }
     grid_max = std::max(grid_max, std::max(std::max(m->grid_s + m->grid_a_aux, m->grid_a), m->grid_e));
     const bool rpbat = (p->mode & ABG_MODE_RANDOM_PBAT) != 0;
     m->n_pass = m->paired ? (rpbat ? 8u : 4u) : 1u;
@@ -884,7 +1067,10 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     ABG_M(cudaMalloc(&m->d_redo_flag, (size_t)max_batch * sizeof(unsigned int)));
     ABG_M(cudaMalloc(&m->d_redo_list, (size_t)max_batch * sizeof(uint32_t)));
     if (m->paired) {
-      const uint64_t cap = std::min<uint64_t>((uint64_t)max_batch * kOvfPerItem + (1u << 20), 0x7fffffffull);
+      // ABISMAL_B200_OVF_PER_ITEM: arena entries per pair (repeat-rich genomes want more: a set grows to 32 768 entries)
+      const char *eo = std::getenv("ABISMAL_B200_OVF_PER_ITEM");
+      const uint64_t per_item = (eo && std::atol(eo) > 0) ? (uint64_t)std::atol(eo) : kOvfPerItem;
+      const uint64_t cap = std::min<uint64_t>((uint64_t)max_batch * per_item + (1u << 20), 0x7fffffffull);
       m->ovf_cap = (uint32_t)cap;
       ABG_M(cudaMalloc(&m->d_set_ovf, cap * sizeof(uint64_t)));
       ABG_M(cudaMalloc(&m->d_task_ovf, cap * sizeof(uint32_t)));
@@ -899,8 +1085,11 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       m->tb_slack = warps * ab2dev::kTbGrabTasks * ab2dev::tb_sm_words(m->ml);
       const uint32_t *cap = m->paired ? kTaskCapPe : kTaskCapSe;
       uint64_t off = 0;
+      // ABISMAL_B200_TASK_SCALE: multiplier on the task-list and traceback capacities per read / pair
+      const char *et = std::getenv("ABISMAL_B200_TASK_SCALE");
+      const uint32_t tscale = (et && std::atol(et) > 0) ? (uint32_t)std::atol(et) : 1u;
       for (int c = 0; c < 3; ++c) {
-        m->task_cap_item[c] = cap[c] * (rpbat ? 2u : 1u);
+        m->task_cap_item[c] = cap[c] * (rpbat ? 2u : 1u) * tscale;
         m->task_class_off[c] = off;
         off += (uint64_t)max_batch * m->task_cap_item[c] + (uint64_t)m->n_chunks_max * m->task_slack;
       }
@@ -984,6 +1173,18 @@ void abg_mapper_destroy(abg_mapper *m) {
     if (m->ev_aux[k]) cudaEventDestroy(m->ev_aux[k]);
   }
   cudaFree(m->d_counters);
+  cudaFree(m->d_tup);
+  cudaFree(m->d_tup_b);
+  cudaFree(m->d_pay_b);
+  cudaFree(m->d_planes);
+  cudaFree(m->d_strand_flag);
+  cudaFree(m->d_bin_hist);
+  cudaFree(m->d_surv_count);
+  cudaFree(m->d_surv);
+  cudaFree(m->d_bin_work);
+  for (cudaEvent_t e : m->ev_b)
+    if (e) cudaEventDestroy(e);
+  if (m->ev_bins) cudaEventDestroy(m->ev_bins);
   cudaFree(m->d_sets);
   cudaFree(m->d_redo_flag);
   cudaFree(m->d_redo_list);
@@ -1087,6 +1288,18 @@ void read_times(abg_mapper *m) {
       m->phase_ms[1] = b;
       m->phase_ms[2] = c;
       m->task_ms[0] = m->task_ms[1] = 0.f;
+      m->bin_ms[0] = m->bin_ms[1] = m->bin_ms[2] = 0.f;
+      if (m->use_bins) {
+        float h = 0.f, sc = 0.f, f = 0.f;
+        if (cudaEventElapsedTime(&h, m->ev0, m->ev_b[0]) == cudaSuccess && cudaEventElapsedTime(&sc, m->ev_b[0], m->ev_b[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&f, m->ev_b[1], m->ev_b[2]) == cudaSuccess) {
+          m->bin_ms[0] = h;
+          m->bin_ms[1] = sc;
+          m->bin_ms[2] = f;
+        }
+        else
+          (void)cudaGetLastError();
+      }
       if (m->use_tasks) {
         float e = 0.f, d = 0.f;
         if (cudaEventElapsedTime(&e, m->ev_ph[0], m->ev_t[0]) == cudaSuccess && cudaEventElapsedTime(&d, m->ev_t[0], m->ev_t[1]) == cudaSuccess) {
@@ -1180,6 +1393,11 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
   ABG_CUDA(cudaMemsetAsync(m->d_work, 0, kWorkWords * sizeof(unsigned int), m->s_h2d));
   if (m->d_counters) ABG_CUDA(cudaMemsetAsync(m->d_counters, 0, 6 * sizeof(unsigned long long), m->s_h2d));
   const size_t slot_sets = (size_t)m->grid_scratch * ab2dev::kWarpsPerBlock;
+  // Binned seeding works on the whole batch (the more strands share a bin, the fewer records come from DRAM):
+  // the sub-batches are hashed as they arrive (stream s_run[0]), binned and filtered together, and only then
+  // flow through the per-sub-batch kernels, whose results are copied back as they finish.
+  const bool bins = m->use_bins && m->split;
+  if (bins && n_chunks != 0 && (rc = reset_bins(m, n, m->s_h2d)) != ABG_OK) return rc;
   for (uint32_t j = 0; j < n_chunks; ++j) {
     const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
     for (int e = 0; e < n_ends; ++e) {
@@ -1196,6 +1414,20 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
                                m->s_h2d));
     }
     ABG_CUDA(cudaEventRecord(m->ev_in[j], m->s_h2d));
+    if (bins) {
+      ABG_CUDA(cudaStreamWaitEvent(m->s_run[0], m->ev_in[j], 0));
+      ab2dev::KernelParams P;
+      fill_params(m, P, c0, c1 - c0, j);
+      if ((rc = launch_hash(m, P, m->s_run[0])) != ABG_OK) return rc;
+    }
+  }
+  if (bins && n_chunks != 0) {
+    if ((rc = launch_bins(m, m->s_run[0])) != ABG_OK) return rc;
+    ABG_CUDA(cudaEventRecord(m->ev_bins, m->s_run[0]));
+    ABG_CUDA(cudaStreamWaitEvent(m->s_run[1], m->ev_bins, 0));
+  }
+  for (uint32_t j = 0; j < n_chunks; ++j) {
+    const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
     cudaStream_t sr = m->s_run[j & 1];
     ABG_CUDA(cudaStreamWaitEvent(sr, m->ev_in[j], 0));
     ab2dev::KernelParams P;
@@ -1206,7 +1438,7 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
       if (P.mem_scr) P.mem_scr += slot_sets * ab2dev::kPeLarge;
       P.tb += slot_sets * 2 * m->tb_words * 32;
     }
-    if ((rc = launch(m, P, sr)) != ABG_OK) return rc;
+    if ((rc = launch(m, P, sr, nullptr, bins)) != ABG_OK) return rc;
     ABG_CUDA(cudaEventRecord(m->ev_k[j], sr));
     ABG_CUDA(cudaStreamWaitEvent(m->s_d2h, m->ev_k[j], 0));
     if ((rc = copy_results_async(m, d, c0, c1 - c0, m->s_d2h)) != ABG_OK) return rc;
@@ -1241,10 +1473,65 @@ void abg_mapper_last_kernel_times(const abg_mapper *m, float out[5]) {
   out[3] = m->phase_ms[1] - m->task_ms[0] - m->task_ms[1];
   out[4] = m->phase_ms[2];
 }
+void abg_mapper_last_seed_times(const abg_mapper *m, float out[4]) {
+  for (int k = 0; k < 4; ++k) out[k] = 0.f;
+  if (!m) return;
+  out[0] = m->bin_ms[0];
+  out[1] = m->bin_ms[1];
+  out[2] = m->bin_ms[2];
+  out[3] = m->phase_ms[0] - m->bin_ms[0] - m->bin_ms[1] - m->bin_ms[2];
+}
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m) {
-  return (m && m->cur_n) ? (m->split ? (m->overlap ? 4u : (m->use_tasks ? 5u : 3u)) : 1u) : 0u;
+  return (m && m->cur_n) ? (m->split ? (m->overlap ? 4u : (m->use_tasks ? 5u : 3u)) + (m->use_bins ? 4u : 0u) : 1u) : 0u;
+}
+int abg_mapper_binned(const abg_mapper *m) { return (m && m->use_bins) ? 1 : 0; }
+int abg_mapper_bin_stats(abg_mapper *m, uint64_t out[6]) {
+  if (!m || !out) return fail(ABG_ERR_INVALID, "abg_mapper_bin_stats: null argument");
+  for (int k = 0; k < 6; ++k) out[k] = 0;
+  if (!m->use_bins) return ABG_OK;
+  ABG_CUDA(cudaSetDevice(m->idx->device));
+  ABG_CUDA(cudaDeviceSynchronize());
+  unsigned int w[4];
+  ABG_CUDA(cudaMemcpy(w, m->d_bin_work, sizeof w, cudaMemcpyDeviceToHost));
+  const size_t ns = (size_t)m->cur_n * m->spi;
+  std::vector<uint8_t> flag(ns);
+  std::vector<uint32_t> cnt(ns);
+  if (ns) {
+    ABG_CUDA(cudaMemcpy(flag.data(), m->d_strand_flag, ns, cudaMemcpyDeviceToHost));
+    ABG_CUDA(cudaMemcpy(cnt.data(), m->d_surv_count, ns * 4, cudaMemcpyDeviceToHost));
+  }
+  uint64_t direct = 0, surv = 0;
+  for (size_t k = 0; k < ns; ++k) {
+    if (flag[k] == 2) continue;
+    if (flag[k] == 1 || cnt[k] > m->surv_cap) ++direct;
+    else surv += cnt[k];
+  }
+  out[0] = ns;          // strands of the last batch
+  out[1] = direct;      // of them mapped by process_seeds itself
+  out[2] = w[1];        // tuples binned
+  out[3] = surv;        // prefilter survivors of the listed strands
+  out[4] = m->n_bins;
+  out[5] = m->tup_cap;
+  return ABG_OK;
 }
 uint32_t abg_mapper_chunk(const abg_mapper *m) { return m ? m->chunk : 0u; }
+
+int abg_mapper_last_run_stats(abg_mapper *m, uint32_t out[8]) {
+  if (!m || !out) return fail(ABG_ERR_INVALID, "abg_mapper_last_run_stats: null argument");
+  ABG_CUDA(cudaSetDevice(m->idx->device));
+  unsigned int w[2 + kChunkWords];
+  ABG_CUDA(cudaStreamSynchronize(m->stream));
+  ABG_CUDA(cudaMemcpy(w, m->d_work, sizeof w, cudaMemcpyDeviceToHost));
+  out[0] = w[2 + 3];
+  out[1] = w[1];
+  out[2] = m->ovf_cap;
+  out[3] = w[2 + 5];
+  out[4] = w[2 + 6];
+  out[5] = w[2 + 7];
+  out[6] = w[2 + 8];
+  out[7] = w[0];
+  return ABG_OK;
+}
 
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out) {
   if (!m || !out) return fail(ABG_ERR_INVALID, "abg_mapper_get_counters: null argument");

@@ -112,8 +112,37 @@ struct TaskResult {   // AlnOut of the task
 };
 constexpr uint32_t kNoTask = 0xffffffffu;
 
+// Binned seeding (seed_bins.cuh): the (strand, seed offset) probes of a whole batch as 16-byte tuples, binned by
+// the address range of their seed-context records so that a slice of the records is L2-resident while every
+// probe that touches it is filtered.
+struct SeedTuple {
+  uint32_t rec_lo;   // record number a * n_entries + first entry of the range, within the tuple's table (low 32 bits)
+  uint32_t cnt_hi;   // bits 0..7: high bits of the record number; bits 8..31: candidates in the range
+  uint32_t sid;      // strand: (read pair, pass) of the batch
+  uint32_t meta;     // seed offset [0,10) | compared bases of the record [10,18) | bound [18,27) | three-letter table 27
+                     // | examined by the specific phase 28 | by the sensitive phase 29 | g_to_a 30
+};
+struct BinParams {
+  SeedTuple *tup;             // emission order (hash_kernel); nullptr = binned seeding off
+  unsigned int *tup_count;    // slots handed out (in blocks; unused slots hold empty tuples)
+  uint32_t tup_cap;
+  uint32_t pw;                // words per read plane
+  uint32_t *planes;           // [strand][2][pw]: 2-bit codes of the strand's read (A0 C1 G2 T3) as two bit planes
+  uint8_t *strand_flag;       // [strand]: 0 = survivors listed, 1 = take the direct path (process_seeds), 2 = empty read
+  uint32_t *bin_hist;         // (scatter kernels) tuples per (bin, scatter CTA)
+  uint32_t bin_shift, n_bins; // bin = global record number >> bin_shift
+  uint64_t rec_base[3];       // global record number of the first record of ctx, ctx_t, ctx_a
+  uint32_t *surv_count;       // [strand] prefilter survivors found (may exceed surv_cap: then the strand takes the direct path)
+  uint2 *surv;                // [strand][surv_cap]: {entry number in its index table, offset | table << 10 | spec << 11 | sens << 12}
+  uint32_t surv_cap;
+  uint32_t spi;               // strands per read / pair
+  uint32_t sid_base;          // strand number of the first strand of this launch (sub-batches of one batch)
+  uint32_t pad;
+};
+
 struct KernelParams {
   IndexDev ix;
+  BinParams bp;
   // batch
   uint32_t n;
   const char *seq[2];
@@ -233,7 +262,7 @@ struct WarpScalars {
   unsigned long long cnt[6];
 };
 
-constexpr int kParamBytes = 640;
+constexpr int kParamBytes = 768;
 constexpr int kTab3Bytes = 2 * 256 * 4;
 static_assert(sizeof(KernelParams) <= kParamBytes, "KernelParams must fit its shared-memory slot");
 
@@ -2423,6 +2452,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) align_kernel(const __g
   flush_counters(W);
 }
 
+// seed_bins.cuh: process_seeds for a strand whose prefilter survivors the binned kernels have listed
+__device__ void process_binned(int set_id, int end, uint32_t strand_code, uint32_t sid);
+
 // Phase 1 of the two-phase launch: seeding only.  Paired: one work item per (pair, call, side) -- the passes
 // of a pair are independent (every map_fragments call starts from reset pe_candidates) -- so a warp hashes,
 // probes and compares ONE read strand and stores the resulting set.  Single-end: the passes of a read feed
@@ -2462,7 +2494,21 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
       }
       load_end(W, 0, P.seq[0] + o0, len);
       reset_set(W, 0, 0, len);
-      if (rpbat) {
+      if (P.bp.tup != nullptr) {  // binned seeding: the strands in the order of strand_plan (seed_bins.cuh)
+        const uint32_t s0 = P.bp.sid_base + item * P.bp.spi;
+        if (rpbat) {
+          process_binned(0, 0, T, s0);
+          process_binned(0, 0, A, s0 + 1);
+          process_binned(0, 0, A | RC, s0 + 2);
+          process_binned(0, 0, T | RC, s0 + 3);
+        }
+        else {
+          const uint32_t cv = a_rich ? A : T;
+          process_binned(0, 0, cv, s0);
+          process_binned(0, 0, cv | RC, s0 + 1);
+        }
+      }
+      else if (rpbat) {
         process_seeds(0, 0, T);
         process_seeds(0, 0, A);
         process_seeds(0, 0, A | RC);
@@ -2488,7 +2534,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
       reset_set(W, 2, 1, len);
       if (len != 0) {
         load_end(W, end, P.seq[end] + o, len);
-        process_seeds(2, end, flags);
+        if (P.bp.tup != nullptr) process_binned(2, end, flags, P.bp.sid_base + w);
+        else process_seeds(2, end, flags);
       }
       if (!store_set(W, 2, stored_set(P, item, pass), (int)P.set_slots, true)) {
         // grew beyond the stored form and the overflow arena is full (or absent): the whole pair is redone

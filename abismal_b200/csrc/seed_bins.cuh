@@ -1,0 +1,515 @@
+// seed_bins.cuh -- binned seeding: cross-read locality for the seed-context prefilter.
+//
+// process_seeds (abismal.cpp:1269-1375) examines, per read strand, ~1000 index entries at ~126 seed offsets;
+// with one warp per strand every examined entry is a random 32-byte sector of the 20 GB record array, and a
+// batch of 2^20 pairs fetches every record ~6.6 times from DRAM.  check_hits / full_compare (:1105-1150) is a
+// PURE function of (strand, offset, entry); only the updates of the candidate set are order dependent, and no
+// update can ever be accepted above the set's initial cutoff (0.4 x read length: the heaps start with that
+// sentinel and cutoffs only tighten).  So the batch is seeded in four kernels:
+//
+//   hash_kernel     one warp per strand: encode, hash, probe the counters (L2 resident), narrow oversized buckets
+//                   (find_candidates) -- everything of process_seeds up to the candidate ranges -- and emit one
+//                   16-byte TUPLE per (offset, table) with a non-empty range, plus the strand's 2-bit read planes;
+//   scatter_kernel  tuples -> bins by the address of their first record (one bin = 2^bin_shift records, ~32 MB),
+//                   each with a 32-byte payload: the 128 read bases its records are compared with;
+//   filter_kernel   tuples in bin order, one lane per candidate: record (L2 hit after the bin's first touch)
+//                   against payload, lower bound of the distance, survivors (~1 %) appended to their strand's list;
+//   seed_kernel     (mapper_kernels.cuh, process_binned below) one warp per strand: survivors in canonical order
+//                   (offset, two-letter before three-letter, bucket order), the deep compare of each, then the
+//                   specific and the sensitive phase replayed against the candidate set exactly as process_seeds
+//                   orders them.  Strands outside the fast path (reads with N, longer than kBinMaxLen, survivor
+//                   or tuple overflow) run process_seeds itself.
+#pragma once
+
+#include "mapper_kernels.cuh"
+
+namespace ab2dev {
+
+constexpr uint32_t kBinMaxLen = 1023;    // seed offset field of a tuple: 10 bits
+constexpr uint32_t kMaxBins = 8192;      // bin cursors of one scatter CTA live in shared memory
+constexpr uint32_t kScatterThreads = 1024;
+constexpr uint32_t kTupleBlock = 256;    // tuple slots a warp reserves at a time
+constexpr uint32_t kSurvSlots = 64;      // survivors per strand the replay handles (two per lane)
+constexpr uint32_t kMaxTupleCount = (1u << 24) - 1u;
+
+__device__ __forceinline__ uint32_t tuple_cnt(const SeedTuple &t) { return t.cnt_hi >> 8; }
+__device__ __forceinline__ uint64_t tuple_rec(const SeedTuple &t) { return (uint64_t)t.rec_lo | ((uint64_t)(t.cnt_hi & 255u) << 32); }
+__device__ __forceinline__ uint32_t tuple_table(uint32_t meta) { return ((meta >> 27) & 1u) ? (1u + ((meta >> 30) & 1u)) : 0u; }
+
+// ---- hash_kernel ---------------------------------------------------------------------------------------------
+struct TupleAlloc {  // warp-uniform cursor into the warp's current block of tuple slots
+  uint32_t cur, end;
+  bool full;
+};
+
+// Writes the tuples of the lanes that have one (`has`), compacted, into the warp's block(s).
+__device__ __forceinline__ void emit_tuples(const BinParams &B, TupleAlloc &al, bool has, const SeedTuple &t, int lane) {
+  const unsigned m = __ballot_sync(FULL, has);
+  if (m == 0u) return;
+  const uint32_t n = (uint32_t)__popc(m);
+  const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
+  const uint32_t avail = al.end - al.cur;
+  if (has && rank < avail) B.tup[al.cur + rank] = t;
+  if (n <= avail) {
+    al.cur += n;
+    return;
+  }
+  // a fresh block for the rest
+  uint32_t base = 0;
+  if (lane == 0) {  // (tup_cap is a multiple of kTupleBlock; once the buffer is full the cursor stops moving)
+    base = *reinterpret_cast<volatile unsigned int *>(B.tup_count);
+    if (base < B.tup_cap) base = atomicAdd(B.tup_count, kTupleBlock);
+  }
+  base = __shfl_sync(FULL, base, 0);
+  if (base >= B.tup_cap) {  // out of tuple memory: the strand takes the direct path
+    al.cur = al.end = 0;
+    al.full = true;
+    return;
+  }
+  if (has && rank >= avail) B.tup[base + (rank - avail)] = t;
+  al.cur = base + (n - avail);
+  al.end = base + kTupleBlock;
+}
+
+// Everything of process_seeds up to the candidate ranges, for pass `strand_code` of `end`: tuples + read planes.
+// Returns the strand's flag.
+__device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t strand_code, uint32_t sid) {
+  const Warp W;
+  const KernelParams &P = params();
+  const IndexDev &ix = P.ix;
+  const BinParams &B = P.bp;
+  const int lane = W.lane;
+  build_qcode(end, strand_code);
+  build_packed(end, strand_code);
+  al.full = false;
+  const uint32_t readlen = W.scal()->len[end];
+  const uint8_t *qcode = W.qcode(end);
+  // 2-bit planes of the encoded read (conversion undone: code 5 is A, code 10 is T); N anywhere -> direct path
+  {
+    uint32_t my_lo = 0, my_hi = 0;
+    bool has_n = false;
+    for (uint32_t w = 0; w < B.pw; ++w) {
+      const uint32_t i = 32u * w + (uint32_t)lane;
+      const uint32_t code = i < readlen ? qcode[i] : 0u;
+      const unsigned lo = __ballot_sync(FULL, code == 2u || (code & 8u) != 0u);
+      const unsigned hi = __ballot_sync(FULL, code == 4u || (code & 8u) != 0u);
+      has_n = has_n || __ballot_sync(FULL, i < readlen && code == 0u) != 0u;
+      if ((uint32_t)lane == w) {
+        my_lo = lo;
+        my_hi = hi;
+      }
+    }
+    uint32_t *dst = B.planes + (size_t)sid * 2u * B.pw;
+    if ((uint32_t)lane < B.pw) {
+      dst[lane] = my_lo;
+      dst[B.pw + lane] = my_hi;
+    }
+    if (has_n || readlen > kBinMaxLen) return 1u;
+  }
+  const uint32_t *p2 = W.plane(0), *p3a = W.plane(1), *p3b = W.plane(2);
+  const uint32_t *T3 = tab3();
+  const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
+  const uint32_t *counter3 = g_to_a ? ix.counter_a : ix.counter_t;
+  const uint32_t *index3 = g_to_a ? ix.index_a : ix.index_t;
+  const uint32_t *bits3 = g_to_a ? ix.bits_a : ix.bits_t;
+  const uint32_t maxc = P.max_candidates;
+  const uint32_t specific_len = min(readlen - P.window_size, readlen >> 1);
+  const uint32_t specific_lim = max(P.window_size, readlen >> 1);
+  const uint32_t lim_two = readlen - 25u + 1u;
+  const uint32_t n_off = max(specific_lim, lim_two);
+  const uint32_t bound = (uint32_t)invalid_hit_diffs(readlen);
+  const uint32_t meta_strand = (bound << 18) | (g_to_a ? (1u << 30) : 0u);
+  bool bad = false;
+  for (uint32_t base_off = 0; base_off < n_off; base_off += 32) {
+    const uint32_t i = base_off + (uint32_t)lane;
+    const bool active = i < n_off;
+    const bool in_spec = i < specific_lim, in_sens = i < lim_two;
+    SeedTuple t2, t3;
+    bool has2 = false, has3 = false;
+    if (active) {
+      const uint32_t k = __brev(plane_window(p2, i)) >> 7;
+      const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
+      const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
+      uint32_t s2, e2, s3, e3;
+      probe_two(ix, k, s2, e2);
+      probe(counter3, bits3, k3, s3, e3);
+      const uint32_t d_two = e2 - s2, d_three = e3 - s3;
+      // the sensitive phase's bucket rule (abismal.cpp:1351-1370), on the raw bucket sizes
+      const bool el2 = d_two != 0u && d_two <= maxc && (d_three == 0u || d_two <= 10u * d_three);
+      const bool el3 = d_three != 0u && d_three <= maxc;
+      const uint32_t a = min((uint32_t)(kCtxArrays - 1), i >> 5);
+      const uint32_t q0 = i - 32u * a;
+      const uint32_t meta_off = i | (min(128u, readlen - q0) << 10) | meta_strand;
+      {  // two-letter table
+        bool spec = false;
+        const bool sens = el2 && in_sens;
+        uint32_t lo = s2, hi = e2;
+        if (in_spec) {
+          if (d_two > maxc || d_two == 0u) {  // the specific phase narrows the bucket (abismal.cpp:1316-1323)
+            const SeedRange r = find_candidates(maxc, qcode + i, readlen - i, s2, e2);
+            lo = r.low;
+            hi = r.high;
+            spec = (hi - lo) != 0u && ((hi - lo) <= maxc || r.p >= specific_len);
+          }
+          else spec = true;
+        }
+        if (spec || sens) {
+          const uint32_t cnt = hi - lo;
+          if (cnt > kMaxTupleCount) bad = true;
+          const uint64_t rec = (uint64_t)a * ix.n_ctx + lo;
+          t2.rec_lo = (uint32_t)rec;
+          t2.cnt_hi = (uint32_t)(rec >> 32) | (cnt << 8);
+          t2.sid = sid;
+          t2.meta = meta_off | (spec ? (1u << 28) : 0u) | (sens ? (1u << 29) : 0u);
+          has2 = true;
+        }
+      }
+      {  // three-letter table
+        bool spec = false;
+        const bool sens = el3 && in_sens;
+        uint32_t lo = s3, hi = e3;
+        if (in_spec) {
+          if (d_three > maxc || d_three == 0u) {
+            const SeedRange r = find_candidates_three(index3, g_to_a, maxc, qcode + i, readlen - i, s3, e3);
+            lo = r.low;
+            hi = r.high;
+            spec = (hi - lo) != 0u && ((hi - lo) <= maxc || r.p >= specific_len);
+          }
+          else spec = true;
+        }
+        if (spec || sens) {
+          const uint32_t cnt = hi - lo;
+          if (cnt > kMaxTupleCount) bad = true;
+          const uint64_t rec = (uint64_t)a * ix.n_ctx3 + lo;
+          t3.rec_lo = (uint32_t)rec;
+          t3.cnt_hi = (uint32_t)(rec >> 32) | (cnt << 8);
+          t3.sid = sid;
+          t3.meta = meta_off | (1u << 27) | (spec ? (1u << 28) : 0u) | (sens ? (1u << 29) : 0u);
+          has3 = true;
+        }
+      }
+    }
+    __syncwarp();
+    emit_tuples(B, al, has2, t2, lane);
+    emit_tuples(B, al, has3, t3, lane);
+  }
+  if (__any_sync(FULL, bad) || al.full) return 1u;
+  return 0u;
+}
+
+// (end, flags) of strand `pass` of an item: the order process_seeds is called in by map_single_ended[_rand]
+// (abismal.cpp:1511-1704) and map_paired_ended[_rand] (:1887-2185)
+__device__ __forceinline__ void strand_plan(const KernelParams &P, int pass, int &end, uint32_t &flags) {
+  const bool paired = P.mode & ABG_MODE_PAIRED;
+  const bool a_rich = P.mode & ABG_MODE_A_RICH;
+  const bool rpbat = P.mode & ABG_MODE_RANDOM_PBAT;
+  const uint32_t T = 0, A = ABG_FLAG_A_RICH, RC = ABG_FLAG_RC;
+  if (!paired) {
+    end = 0;
+    if (rpbat) flags = pass == 0 ? T : (pass == 1 ? A : (pass == 2 ? (A | RC) : (T | RC)));
+    else flags = (a_rich ? A : T) | (pass == 1 ? RC : 0u);
+    return;
+  }
+  const CallPlan cp = call_plan(pass >> 1, rpbat, a_rich);
+  end = (pass & 1) ? cp.e2 : cp.e1;
+  flags = (pass & 1) ? cp.f2 : cp.f1;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreadsPerBlock, MINB) hash_kernel(const __grid_constant__ KernelParams Pin) {
+  block_prologue(Pin);
+  const KernelParams &P = params();
+  const BinParams &B = P.bp;
+  const Warp W;
+  const int lane = W.lane;
+  WarpScalars *S = W.scal();
+  TupleAlloc al;
+  al.cur = al.end = 0u;
+  al.full = false;
+  const unsigned int n_work = P.n * B.spi;
+  for (;;) {
+    unsigned int w = 0;
+    if (lane == 0) w = atomicAdd(P.work_counter, 1u);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= n_work) break;
+    if (lane == 0) {
+      S->qkey[0] = S->qkey[1] = ~0u;
+      S->packed_key = ~0u;
+    }
+    __syncwarp();
+    const unsigned int item = w / B.spi;
+    int end;
+    uint32_t flags;
+    strand_plan(P, (int)(w % B.spi), end, flags);
+    const uint32_t o = P.off[end][item], len = P.off[end][item + 1] - o;
+    if (lane == 0) S->len[end] = len;
+    __syncwarp();
+    uint32_t flag = 2u;
+    if (len != 0) {
+      load_end(W, end, P.seq[end] + o, len);
+      flag = emit_strand(al, end, flags, B.sid_base + w);
+    }
+    if (lane == 0) B.strand_flag[B.sid_base + w] = (uint8_t)flag;
+  }
+  // the unused rest of the warp's last block: empty tuples
+  for (uint32_t k = al.cur + (uint32_t)lane; k < al.end; k += 32) B.tup[k] = SeedTuple{0u, 0u, 0u, 0u};
+}
+
+// ---- scatter_kernel / filter_kernel ----------------------------------------------------------------------------
+struct FilterParams {
+  const SeedTuple *tup;
+  const unsigned int *tup_count;
+  uint32_t tup_cap;
+  const uint32_t *planes;
+  uint32_t pw;
+  uint32_t bin_shift, n_bins;
+  uint64_t rec_base[3];
+  uint32_t *bin_hist;      // in: tuples per bin; bin_prefix_kernel turns it into the bins' write cursors
+  uint32_t *n_binned;      // out of bin_prefix_kernel: tuples in all bins
+  SeedTuple *tup_b;        // binned tuples
+  uint4 *pay_b;            // their payloads: 2 x uint4 per tuple = {lo, hi} planes of four 32-base chunks
+  const uint4 *ctx[3];     // record arrays of the three tables
+  uint64_t n_tab[3];       // entries per table (records of array a start at a * n_tab)
+  uint32_t *surv_count;
+  uint2 *surv;
+  uint32_t surv_cap;
+  unsigned int *work;      // filter_kernel's work cursor
+};
+
+// Binning without global atomics: CTA c of count_kernel and of scatter_kernel owns the same contiguous range of
+// the tuple array.  count_kernel leaves the CTA's tuples per bin in bin_hist[bin * n_cta + c]; one exclusive
+// prefix sum over that (bin-major) matrix gives every (bin, CTA) its own write range, so the scatter CTAs hand
+// out positions from shared-memory cursors.  (One global atomicAdd per tuple was measured at 45 ms for 2^29
+// tuples, tools/micro/gather_bench4.cu.)
+__device__ __forceinline__ void cta_range(const FilterParams &F, uint64_t &i0, uint64_t &i1) {
+  const uint64_t n = min(*F.tup_count, F.tup_cap);
+  uint64_t per = (n + gridDim.x - 1) / gridDim.x;
+  per = (per + kScatterThreads - 1) / kScatterThreads * kScatterThreads;
+  i0 = min(n, per * blockIdx.x);
+  i1 = min(n, i0 + per);
+}
+__device__ __forceinline__ SeedTuple load_tuple(const SeedTuple *p, uint4 &raw) {
+  raw = __ldg(reinterpret_cast<const uint4 *>(p));
+  SeedTuple t;
+  t.rec_lo = raw.x; t.cnt_hi = raw.y; t.sid = raw.z; t.meta = raw.w;
+  return t;
+}
+
+__global__ void __launch_bounds__(kScatterThreads) count_kernel(FilterParams F) {
+  extern __shared__ uint32_t s_bins[];
+  for (uint32_t b = threadIdx.x; b < F.n_bins; b += blockDim.x) s_bins[b] = 0u;
+  __syncthreads();
+  uint64_t i0, i1;
+  cta_range(F, i0, i1);
+  for (uint64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    uint4 raw;
+    const SeedTuple t = load_tuple(F.tup + i, raw);
+    if (tuple_cnt(t) == 0u) continue;
+    atomicAdd(s_bins + (uint32_t)((F.rec_base[tuple_table(t.meta)] + tuple_rec(t)) >> F.bin_shift), 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < F.n_bins; b += blockDim.x) F.bin_hist[(size_t)b * gridDim.x + blockIdx.x] = s_bins[b];
+}
+
+// exclusive prefix sum of the n_bins x n_cta matrix in place (one block)
+__global__ void bin_prefix_kernel(FilterParams F, uint32_t n_cta) {
+  __shared__ uint32_t part[1024];
+  const uint32_t n = F.n_bins * n_cta;
+  const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+  const uint32_t b0 = min(n, threadIdx.x * per), b1 = min(n, b0 + per);
+  uint32_t sum = 0;
+  for (uint32_t b = b0; b < b1; ++b) sum += F.bin_hist[b];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (uint32_t k = 0; k < blockDim.x; ++k) {
+      const uint32_t v = part[k];
+      part[k] = acc;
+      acc += v;
+    }
+    *F.n_binned = acc;
+  }
+  __syncthreads();
+  uint32_t acc = part[threadIdx.x];
+  for (uint32_t b = b0; b < b1; ++b) {
+    const uint32_t v = F.bin_hist[b];
+    F.bin_hist[b] = acc;
+    acc += v;
+  }
+}
+
+__global__ void __launch_bounds__(kScatterThreads) scatter_kernel(FilterParams F) {
+  extern __shared__ uint32_t s_bins[];
+  for (uint32_t b = threadIdx.x; b < F.n_bins; b += blockDim.x) s_bins[b] = F.bin_hist[(size_t)b * gridDim.x + blockIdx.x];
+  __syncthreads();
+  uint64_t i0, i1;
+  cta_range(F, i0, i1);
+  for (uint64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    uint4 raw;
+    const SeedTuple t = load_tuple(F.tup + i, raw);
+    if (tuple_cnt(t) == 0u) continue;
+    const uint64_t g = F.rec_base[tuple_table(t.meta)] + tuple_rec(t);
+    const uint32_t at = atomicAdd(s_bins + (uint32_t)(g >> F.bin_shift), 1u);
+    reinterpret_cast<uint4 *>(F.tup_b)[at] = raw;
+    // the 128 read bases from q0 = offset - 32 a (a = min(offset / 32, 3)), as four {lo, hi} plane words
+    const uint32_t off = t.meta & 1023u;
+    const uint32_t q0 = off - 32u * min((uint32_t)(kCtxArrays - 1), off >> 5);
+    const uint32_t w0 = q0 >> 5, sh = q0 & 31u;
+    const uint32_t *pl = F.planes + (size_t)t.sid * 2u * F.pw + w0, *ph = pl + F.pw;
+    uint32_t l[5], h[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      l[c] = __ldg(pl + c);
+      h[c] = __ldg(ph + c);
+    }
+    uint4 a, b;
+    a.x = __funnelshift_r(l[0], l[1], sh); a.y = __funnelshift_r(h[0], h[1], sh);
+    a.z = __funnelshift_r(l[1], l[2], sh); a.w = __funnelshift_r(h[1], h[2], sh);
+    b.x = __funnelshift_r(l[2], l[3], sh); b.y = __funnelshift_r(h[2], h[3], sh);
+    b.z = __funnelshift_r(l[3], l[4], sh); b.w = __funnelshift_r(h[3], h[4], sh);
+    F.pay_b[2 * (size_t)at] = a;
+    F.pay_b[2 * (size_t)at + 1] = b;
+  }
+}
+
+// mismatch bits of 32 bases: genome planes (glo, ghi) against read planes (rlo, rhi); a converted read base also
+// matches its unconverted partner (g_to_a: read A matches genome G; else: read T matches genome C)
+__device__ __forceinline__ uint32_t mismatch_bits(uint32_t glo, uint32_t ghi, uint32_t rlo, uint32_t rhi, bool g_to_a) {
+  const uint32_t diff = (glo ^ rlo) | (ghi ^ rhi);
+  const uint32_t extra = g_to_a ? (~rlo & ~rhi & ghi & ~glo) : (rlo & rhi & ~ghi & glo);
+  return diff & ~extra;
+}
+
+__global__ void __launch_bounds__(256, 4) filter_kernel(FilterParams F) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = *F.n_binned;
+  for (;;) {
+    uint32_t w0 = 0;
+    if (lane == 0) w0 = atomicAdd(F.work, 32u);
+    w0 = __shfl_sync(FULL, w0, 0);
+    if (w0 >= n) break;
+    SeedTuple t = SeedTuple{0u, 0u, 0u, 0u};
+    if (w0 + (uint32_t)lane < n) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(F.tup_b) + w0 + lane);
+      t.rec_lo = raw.x; t.cnt_hi = raw.y; t.sid = raw.z; t.meta = raw.w;
+    }
+    const uint32_t tot = tuple_cnt(t);
+    const uint32_t incl = warp_incl_scan_add(tot, lane);
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+      const uint32_t cidx = c0 + (uint32_t)lane;
+      const bool valid = cidx < total;
+      int o = 0;  // owner lane = number of lanes whose inclusive sum is <= cidx
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t vv = __shfl_sync(FULL, incl, (o + s - 1) & 31);
+        if (vv <= cidx) o += s;
+      }
+      o &= 31;
+      const uint32_t o_incl = __shfl_sync(FULL, incl, o), o_tot = __shfl_sync(FULL, tot, o);
+      const uint32_t o_rec_lo = __shfl_sync(FULL, t.rec_lo, o), o_hi = __shfl_sync(FULL, t.cnt_hi, o) & 255u;
+      const uint32_t o_meta = __shfl_sync(FULL, t.meta, o), o_sid = __shfl_sync(FULL, t.sid, o);
+      if (!valid) continue;
+      const uint32_t r = cidx - (o_incl - o_tot);
+      const uint32_t tab = tuple_table(o_meta);
+      const uint64_t rec = ((uint64_t)o_rec_lo | ((uint64_t)o_hi << 32)) + r;
+      uint32_t w[8];
+      load_ctx(F.ctx[tab] + 2 * rec, w);
+      const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
+      const bool sentinel = (w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) == ~0u;
+      const bool g_to_a = (o_meta >> 30) & 1u;
+      const int nb = (int)((o_meta >> 10) & 255u);  // compared bases of the record: 1..128
+      const uint32_t m0 = mismatch_bits(w[0], w[1], pa.x, pa.y, g_to_a), m1 = mismatch_bits(w[2], w[3], pa.z, pa.w, g_to_a);
+      const uint32_t m2 = mismatch_bits(w[4], w[5], pb.x, pb.y, g_to_a), m3 = mismatch_bits(w[6], w[7], pb.z, pb.w, g_to_a);
+      int lb = __popc(nb >= 32 ? m0 : (m0 & ((1u << nb) - 1u)));
+      if (nb > 32) lb += __popc(nb >= 64 ? m1 : (m1 & ((1u << (nb - 32)) - 1u)));
+      if (nb > 64) lb += __popc(nb >= 96 ? m2 : (m2 & ((1u << (nb - 64)) - 1u)));
+      if (nb > 96) lb += __popc(nb >= 128 ? m3 : (m3 & ((1u << (nb - 96)) - 1u)));
+      const int bound = (int)((o_meta >> 18) & 511u);
+      if (lb <= bound || sentinel) {
+        const uint32_t off = o_meta & 1023u;
+        const uint32_t a = min((uint32_t)(kCtxArrays - 1), off >> 5);
+        const uint32_t entry = (uint32_t)(rec - (uint64_t)a * F.n_tab[tab]);
+        const uint32_t at = atomicAdd(F.surv_count + o_sid, 1u);
+        if (at < F.surv_cap)
+          F.surv[(size_t)o_sid * F.surv_cap + at] = make_uint2(entry, off | ((o_meta >> 27) & 7u) << 10);
+      }
+    }
+  }
+}
+
+// ---- seed_kernel side: the survivors of one strand against its candidate set ---------------------------------
+// Equivalent of process_seeds(set_id, end, strand_code) for strand `sid` when its survivors were listed.
+__device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand_code, uint32_t sid) {
+  const Warp W;
+  const KernelParams &P = params();
+  const BinParams &B = P.bp;
+  const int lane = W.lane;
+  const uint32_t n_raw = __ldcg(B.surv_count + sid);
+  if (__ldcg(B.strand_flag + sid) != 0u || n_raw > min(B.surv_cap, kSurvSlots)) {
+    process_seeds(set_id, end, strand_code);
+    return;
+  }
+  build_qcode(end, strand_code);
+  build_packed(end, strand_code);
+  const int n = (int)n_raw;
+  const uint32_t readlen = W.scal()->len[end];
+  const int n_words = (int)((readlen + 15) / 16);
+  const int bound = invalid_hit_diffs(readlen);
+  const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
+  const uint32_t *index3 = g_to_a ? P.ix.index_a : P.ix.index_t;
+  // keys: offset | table | entry | spec | sens -- unique per candidate, so the flag bits never decide the order
+  uint64_t *keys = reinterpret_cast<uint64_t *>(W.log_pos());   // [64]
+  uint64_t *sorted = keys + kSurvSlots;                          // [64]
+  __syncwarp();
+  for (int k = lane; k < n; k += 32) {
+    const uint2 e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
+    const uint64_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
+    keys[k] = (off << 36) | (is3 << 35) | ((uint64_t)e.x << 3) | fl;
+  }
+  __syncwarp();
+  for (int k = lane; k < n; k += 32) {
+    const uint64_t mine = keys[k];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += keys[j] < mine;
+    sorted[rank] = mine;
+  }
+  __syncwarp();
+  uint32_t *res_pos = reinterpret_cast<uint32_t *>(keys), *res_meta = res_pos + kSurvSlots;  // over the unsorted keys
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int k = k0 + lane;
+    const bool valid = k < n;
+    const uint64_t key = valid ? sorted[k] : 0ull;
+    const uint32_t entry = (uint32_t)(key >> 3), is3 = (uint32_t)(key >> 35) & 1u, off = (uint32_t)(key >> 36);
+    const Deep1 r = compare_deep_one(index3, n_words, bound, valid, entry, off | (is3 << 31));
+    __syncwarp();
+    if (valid) {
+      res_pos[k] = r.pos;
+      res_meta[k] = (uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)min(r.pm, 0x3fff) << 16) | ((uint32_t)(key & 3u) << 30);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {  // one lane mutates the set (see replay_hits)
+    CandSet res;
+    res.load(W, set_id);
+    res.set_specific();
+    for (int k = 0; k < n && !res.sure_ambig; ++k) {
+      const uint32_t m = res_meta[k];
+      if (((m >> 30) & 1u) == 0u) continue;  // bit 30: examined by the specific phase (tuple bit 28)
+      if ((int)((m >> 16) & 0x3fffu) <= res.cutoff) res.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res_pos[k]);
+    }
+    if (res.should_do_sensitive()) {
+      res.set_sensitive();
+      for (int k = 0; k < n && !res.sure_ambig; ++k) {
+        const uint32_t m = res_meta[k];
+        if (((m >> 31) & 1u) == 0u) continue;  // bit 31: examined by the sensitive phase (tuple bit 29)
+        if ((int)((m >> 16) & 0x3fffu) <= res.cutoff) res.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res_pos[k]);
+      }
+    }
+    res.store_one_lane(W, set_id);
+  }
+  __syncwarp();
+}
+
+}  // namespace ab2dev

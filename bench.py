@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--parity-pairs", type=int, default=4000, help="pairs per rank checked against the CPU oracle")
     ap.add_argument("--seed", type=int, default=20251017)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--as-rank", type=int, default=None,
+                    help="single process: time the reads rank R of a multi-GPU run would get (reproduces one rank of an N-GPU run)")
     ap.add_argument("--no-cli", action="store_true", help="skip the FASTQ->SAM leg and the SAM comparison with the reference")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -299,9 +301,10 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
             state["ixf"], state["paths"] = workload.get_index(genome_bases, args.seed, device=local_rank, need_files=True, log=log)
         paths = state["paths"]
         sim_procs = int(os.environ.get("ABISMAL_B200_SIM_PROCS", "0")) or max(1, min(16, n_cpu // max(world, 1)))
-        prefix = os.path.join(paths["dir"], "%s_n%d_r%d" % (args.mode, n_units, rank))
+        data_rank = rank if args.as_rank is None else args.as_rank
+        prefix = os.path.join(paths["dir"], "%s_n%d_r%d" % (args.mode, n_units, data_rank))
         state["prefix"] = prefix
-        fq1, fq2 = workload.simulate_reads(REF_BIN, paths["fasta"], prefix, n_units, seed=args.seed % 1000 + rank,
+        fq1, fq2 = workload.simulate_reads(REF_BIN, paths["fasta"], prefix, n_units, seed=args.seed % 1000 + data_rank,
                                            paired=paired, mode_flag=sim_flag, n_procs=sim_procs, log=log)
         state["fqs"] = [fq1, fq2] if paired else [fq1]
     sync.run("read simulation", prep_reads)
@@ -389,13 +392,14 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
     barrier()
 
     def timed_device():
-        kernel_ms, phase_ms = [], [0.0] * 5
+        kernel_ms, phase_ms, seed_ms = [], [0.0] * 5, [0.0] * 4
         for _ in range(args.steps):
             m.run()
             m.sync()
             kernel_ms.append(m.last_kernel_ms)
             phase_ms = [x + y for x, y in zip(phase_ms, m.last_kernel_times)]
-        state.update(dev_ms=sum(kernel_ms), phase_ms=phase_ms)
+            seed_ms = [x + y for x, y in zip(seed_ms, m.last_seed_times)]
+        state.update(dev_ms=sum(kernel_ms), phase_ms=phase_ms, seed_ms=seed_ms, bin_stats=m.bin_stats() if m.binned else None)
     sync.run("device-resident leg", timed_device)
     barrier()
     dev_ms, phase_ms = state["dev_ms"], state["phase_ms"]
@@ -481,9 +485,13 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
                 "parity": {"%s_checked" % unit: total_checked, "ranks_checked": world, "mismatching_records": total_bad,
                            "against": "CPU oracle (oracle/abismal_oracle.cpp), first %d %s of every rank's timed batch" % (n_o, unit)},
             }
-            names = m.KERNELS
-            out["kernels"] = {nm: {"ms_per_launch": t / args.steps, "share_of_step": t / dev_ms}
-                              for nm, t in zip(names, phase_ms)}
+            # the seeding is four kernels when binned (hash -> scatter -> filter -> seed_kernel on the survivors),
+            # one otherwise; then enum_kernel, dp_kernel, align_kernel and the redo kernel
+            times = list(zip(m.SEED_KERNELS, state["seed_ms"])) if m.binned else [("seed_kernel", phase_ms[0])]
+            times += list(zip(m.KERNELS[1:], phase_ms[1:]))
+            out["kernels"] = {nm: {"ms_per_launch": t / args.steps, "share_of_step": t / dev_ms} for nm, t in times}
+            if state["bin_stats"]:
+                out["binned_seeding"] = state["bin_stats"]
             # ---- roofline + CPU baseline + front end (rank 0, N = 1) -------------------
             if world == 1 and not args.no_cpu_baseline:
                 peak, peak_src = hbm_peak()
@@ -497,8 +505,9 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
                     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                         tj = json.load(f)
                     tj = tj.get(args.mode, tj if args.mode == "pbat" else None)
-                    if tj is None or not tj.get("kernel", "").startswith("seed_kernel"):
-                        raise KeyError("traffic.json holds no seed_kernel capture for this mode")
+                    want_kernel = "seeding" if m.binned else "seed_kernel"
+                    if tj is None or not tj.get("kernel", "").startswith(want_kernel):
+                        raise KeyError("traffic.json holds no capture of the seeding kernels for this mode")
                     # ncu --set full capture of the same kernel on a smaller batch of the same reads, scaled to
                     # this launch's batch (the kernel's work is linear in the number of pairs)
                     per = float(tj.get("units_per_pair", 1.0))
@@ -521,7 +530,10 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
                                    "algorithmic_bytes_per_%s" % unit[:-1]: seed_bytes,
                                    "algorithmic_bytes_per_%s_whole_path" % unit[:-1]: seed_bytes + dp_bytes,
                                    "whole_step_frac": (seed_bytes + dp_bytes) * b[0].n / (dev_ms / args.steps / 1e3) / 1e9 / peak,
-                                   "kernel": "seed_kernel", "ms_per_launch": ms_per_launch, "kernels": out["kernels"],
+                                   "kernel": ("seeding = hash_kernel + scatter_kernel + filter_kernel + seed_kernel (one launch each "
+                                              "per batch; the algorithmic bytes of process_seeds are spread over them)")
+                                             if m.binned else "seed_kernel",
+                                   "ms_per_launch": ms_per_launch, "kernels": out["kernels"],
                                    "counters_from": "CPU oracle on the first %d %s of the batch" % (n_o, unit),
                                    "random_gather": gather}
                 n_s = min(args.cpu_sample_pairs, b[0].n)

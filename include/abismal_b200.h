@@ -187,8 +187,22 @@ void abg_mapper_last_phase_ms(const abg_mapper *m, float out[3]);
 /* All five kernels of a run: out[0] seed_kernel, out[1] enum_kernel, out[2] dp_kernel, out[3] align_kernel,
  * out[4] map_reads_kernel over the redo list (out[1] = out[2] = 0 without the task-parallel alignment). */
 void abg_mapper_last_kernel_times(const abg_mapper *m, float out[5]);
+/* Binned seeding (the default when the index carries seed-context records): out[0] hash_kernel, out[1]
+ * scatter_kernel (with the bins' prefix sum), out[2] filter_kernel, out[3] seed_kernel of the last abg_mapper_run;
+ * their sum is out[0] of abg_mapper_last_kernel_times.  Without binning out[3] is the whole seeding. */
+void abg_mapper_last_seed_times(const abg_mapper *m, float out[4]);
+/* 1 when the mapper seeds through the binned kernels, 0 when every strand gathers its own records. */
+int abg_mapper_binned(const abg_mapper *m);
+/* Diagnostics of the last batch (binned seeding): out[0] strands, out[1] strands that took the direct path
+ * (reads with N, survivor or tuple overflow), out[2] tuples binned, out[3] prefilter survivors, out[4] bins,
+ * out[5] tuple capacity. */
+int abg_mapper_bin_stats(abg_mapper *m, uint64_t out[6]);
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m);
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out);
+/* Diagnostics of the most recent abg_mapper_run (after abg_mapper_sync): out[0] pairs left to the redo kernel,
+ * out[1] / out[2] entries used / available in the arena of stored candidate sets beyond 32 entries,
+ * out[3..5] alignment tasks emitted per band class, out[6] traceback units handed out, out[7] kernel error flag. */
+int abg_mapper_last_run_stats(abg_mapper *m, uint32_t out[8]);
 
 #ifdef __cplusplus
 }

@@ -78,8 +78,50 @@ def test_records_equal_oracle(workspace, rep_index, gpu, tag, mode, kw, files):
     helpers.assert_results_equal(got, want, bool(mode & 1))
     mapped = want.pe_r1["pos"] != 0 if mode & 1 else want.se1["pos"] != 0
     assert mapped.sum() > 30  # the case is not vacuous
+    # the benchmarked seeding ran: hash -> scatter -> filter -> replay of the listed survivors, for most strands
+    assert m.binned
+    st = m.bin_stats()
+    assert st["tuples"] > 0 and st["survivors"] > 0 and st["strands_direct"] < 0.5 * st["strands"], st
     m.close()
     o.close()
+
+
+@pytest.mark.parametrize("tag,mode,kw,files", [c for c in RECORD_CASES if c[0] in ("se", "se_rpbat", "pe", "pe_rpbat_ambig", "pe_c10")],
+                         ids=["se", "se_rpbat", "pe", "pe_rpbat_ambig", "pe_c10"])
+def test_records_equal_oracle_with_direct_seeding(workspace, rep_index, gpu, monkeypatch, tag, mode, kw, files):
+    """ABISMAL_B200_BINS=0: every strand gathers its own seed-context records (process_seeds in one warp), the
+    path strands outside the binned kernels' fast path take (reads with N, survivor or tuple overflow)."""
+    from abismal_b200 import Mapper
+    ixf, ix, kind = rep_index
+    monkeypatch.setenv("ABISMAL_B200_BINS", "0")
+    b = [_fq(workspace, f, kind=kind) for f in files]
+    m = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max([x.max_len for x in b] + [64]), **kw)
+    monkeypatch.delenv("ABISMAL_B200_BINS")
+    assert not m.binned
+    o = helpers.OracleMapper(ixf, mode=mode, **kw)
+    helpers.assert_results_equal(m.map_batch(*b), o.map_batch(*b), bool(mode & 1))
+    o.close()
+    m.close()
+
+
+def test_binned_seeding_overflow_paths(workspace, rep_index, gpu, monkeypatch):
+    """Tuple memory too small for the batch, survivor lists too short: the strands that do not fit take the direct
+    path, same records."""
+    from abismal_b200 import Mapper
+    ixf, ix, kind = rep_index
+    b1, b2 = _fq(workspace, "rep_pe_1.fq", kind=kind), _fq(workspace, "rep_pe_2.fq", kind=kind)
+    o = helpers.OracleMapper(ixf, mode=1)
+    want = o.map_batch(b1, b2)
+    o.close()
+    for var, val in (("ABISMAL_B200_TUPLE_CAP", "16384"), ("ABISMAL_B200_SURV_CAP", "3")):
+        monkeypatch.setenv(var, val)
+        m = Mapper(ix, mode=1, max_batch=b1.n, max_read_len=160)
+        monkeypatch.delenv(var)
+        got = m.map_batch(b1, b2)
+        st = m.bin_stats()
+        assert m.binned and 0 < st["strands_direct"] < st["strands"], (var, st)
+        helpers.assert_results_equal(got, want, True)
+        m.close()
 
 
 @pytest.mark.parametrize("tag,mode,kw,files", [c for c in RECORD_CASES if c[0] in ("se", "pe", "pe_rpbat_ambig")],
@@ -96,7 +138,7 @@ def test_records_equal_oracle_with_alignments_in_the_warp(workspace, rep_index, 
     monkeypatch.delenv("ABISMAL_B200_TASKS")
     mt = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max([x.max_len for x in b] + [64]), **kw)
     got, got_t = m.map_batch(*b), mt.map_batch(*b)
-    assert m.launches_per_run == 3 and mt.launches_per_run == 5
+    assert m.launches_per_run == 3 + 4 * m.binned and mt.launches_per_run == 5 + 4 * mt.binned
     helpers.assert_results_equal(got, got_t, bool(mode & 1))
     o = helpers.OracleMapper(ixf, mode=mode, **kw)
     helpers.assert_results_equal(got, o.map_batch(*b), bool(mode & 1))

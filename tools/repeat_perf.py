@@ -106,17 +106,21 @@ def main():
     ixf = IndexFile(idx)
     out["index_entries"] = [int(ixf.index_size), int(ixf.index_size_three)]
     ix = Index(ixf, 0)
-    for tasks in ("1", "0"):
+    for tasks, ovf, tscale in (("1", "32", "1"), ("1", "4096", "128"), ("0", "32", "1")):
         os.environ["ABISMAL_B200_TASKS"] = tasks
+        os.environ["ABISMAL_B200_OVF_PER_ITEM"] = ovf
+        os.environ["ABISMAL_B200_TASK_SCALE"] = tscale
         m = Mapper(ix, mode=1, max_batch=b1.n, max_read_len=160)
         m.upload(b1, b2)
         for _ in range(2):
             m.run()
             m.sync()
         res = m.download(b1.n)
+        tasks = "%s,ovf=%s,scale=%s" % (tasks, ovf, tscale)
         out["tasks=" + tasks] = {"ms": m.last_kernel_ms, "reads_per_s": 2.0 * b1.n / (m.last_kernel_ms / 1e3),
                                  "kernels_ms": dict(zip(m.KERNELS, m.last_kernel_times)),
-                                 "pairs_mapped_frac": float((res.pe_r1["pos"] != 0).mean())}
+                                 "pairs_mapped_frac": float((res.pe_r1["pos"] != 0).mean()),
+                                 "run_stats": m.last_run_stats()}
         print("[rep] tasks=%s %s" % (tasks, json.dumps(out["tasks=" + tasks])), flush=True)
         m.close()
     ix.close()
