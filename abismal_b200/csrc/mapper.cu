@@ -111,7 +111,8 @@ constexpr uint32_t kMaxChunks = 256;  // sub-batches one abg_map_batch call is p
 // task slots handed out per class [3] + traceback units, dp_kernel's cursors [3]
 constexpr uint32_t kChunkWords = 14;  // ... [12] hash_kernel's work counter (binned seeding), [13] spare
 constexpr uint32_t kWorkWords = 2 + kChunkWords * kMaxChunks;  // [0] error flag, [1] cursor of the set overflow arena
-constexpr uint32_t kOvfPerItem = 32;  // overflow arena entries per pair of max_batch (sets beyond set_slots entries)
+constexpr uint32_t kOvfPerItem = 256;  // overflow arena entries per pair of max_batch (sets beyond set_slots entries):
+// 3 GB per 2^20 pairs; a repeat-rich 100 Mbp test genome needs ~100 per pair (tools/repeat_perf.py)
 // task-parallel alignment: slots per read / pair in the three task lists (bands <= 16 / <= 32 / <= 61 columns) and
 // traceback allocations per read / pair (in tasks of the first class); beyond these the alignment runs in the warp
 constexpr uint32_t kTaskCapPe[3] = {5, 2, 1}, kTaskCapSe[3] = {3, 1, 1};
@@ -190,7 +191,8 @@ struct abg_mapper {
   uint32_t *d_cigar_inline[2] = {nullptr, nullptr};  // [max_batch][inline_ops]
   // scratch
   uint64_t *d_pe_overflow = nullptr;
-  int16_t *d_mem_scr = nullptr;
+  int16_t *d_mem_scr = nullptr, *d_mem_scr2 = nullptr;
+  uint32_t heavy_min = 64;
   uint64_t *d_tb = nullptr;
   uint32_t tb_words = 0;
   unsigned int *d_work = nullptr;   // [0] error flag, [1] overflow arena cursor, [2 + kChunkWords j ..] sub-batch j (see kChunkWords)
@@ -307,6 +309,8 @@ void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint
   P.ml = m->ml;
   P.pe_overflow = m->d_pe_overflow;
   P.mem_scr = m->d_mem_scr;
+  P.mem_scr2 = m->d_mem_scr2;
+  P.heavy_min = m->heavy_min;
   P.tb = m->d_tb;
   P.tb_words = m->tb_words;
   P.work_counter = work;
@@ -1130,6 +1134,9 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     ABG_M(cudaMallocHost(&m->h_pe_r2, (size_t)max_batch * sizeof(abg_hit)));
     ABG_M(cudaMalloc(&m->d_pe_overflow, slots * 2 * ab2dev::kPeLarge * sizeof(uint64_t)));
     ABG_M(cudaMalloc(&m->d_mem_scr, slots * ab2dev::kPeLarge * sizeof(int16_t)));
+    ABG_M(cudaMalloc(&m->d_mem_scr2, slots * ab2dev::kPeLarge * sizeof(int16_t)));
+    if (const char *eh = std::getenv("ABISMAL_B200_HEAVY_MIN"))  // set size from which best_pair goes by rows (0: always)
+      m->heavy_min = (uint32_t)std::max(0l, std::atol(eh));
   }
   m->tb_words = ab2dev::tb_sm_words(m->ml);
   ABG_M(cudaMalloc(&m->d_tb, slots * 2 * m->tb_words * 32 * sizeof(uint64_t)));
@@ -1164,6 +1171,7 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFreeHost(m->h_pe_r2);
   cudaFree(m->d_pe_overflow);
   cudaFree(m->d_mem_scr);
+  cudaFree(m->d_mem_scr2);
   cudaFree(m->d_tb);
   cudaFree(m->d_work);
   cudaFree(m->d_ready);
@@ -1436,6 +1444,7 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
     if (j & 1) {
       if (P.pe_overflow) P.pe_overflow += slot_sets * 2 * ab2dev::kPeLarge;
       if (P.mem_scr) P.mem_scr += slot_sets * ab2dev::kPeLarge;
+      if (P.mem_scr2) P.mem_scr2 += slot_sets * ab2dev::kPeLarge;
       P.tb += slot_sets * 2 * m->tb_words * 32;
     }
     if ((rc = launch(m, P, sr, nullptr, bins)) != ABG_OK) return rc;

@@ -42,6 +42,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <limits.h>
 
 #include "abismal_b200.h"
 
@@ -159,7 +160,9 @@ struct KernelParams {
   // per-warp-slot scratch
   uint32_t ml;            // padded max read length (multiple of 32)
   uint64_t *pe_overflow;  // [slots][2][kPeLarge]
-  int16_t *mem_scr;       // [slots][kPeLarge]
+  int16_t *mem_scr;       // [slots][kPeLarge]: best_pair's memo / alignment scores of set 2's partners
+  int16_t *mem_scr2;      // [slots][kPeLarge]: alignment scores of set 3 (row-parallel best_pair)
+  uint32_t heavy_min;     // sets with at least this many entries take the row-parallel best_pair
   uint64_t *tb;           // [slots][2][tb_words][32]
   uint32_t tb_words;      // 64-bit traceback words per lane per alignment
   unsigned int *work_counter;
@@ -257,7 +260,8 @@ struct WarpScalars {
   uint32_t len[2];
   uint32_t qkey[2];     // which (flags) is encoded in qcode[e]; ~0u = none
   uint32_t packed_key;  // which (end, flags) is in packed/planes; ~0u = none
-  uint32_t pad[3];
+  uint32_t loaded[2];   // binned seeding: base[e] holds the read's bases (the replay loads them only when needed)
+  uint32_t pad;
   TbKey tbk[2];
   unsigned long long cnt[6];
 };
@@ -797,6 +801,7 @@ __device__ __forceinline__ void load_ctx(const uint4 *p, uint32_t (&w)[8]) {
 #endif
 }
 
+constexpr int kDeferredExact = -2;  // pm of a candidate whose window needs exact_compare, left to the caller
 // Deep part of a compare chunk: index entries, 2-bit genome windows (staged, with early exit at the bound) and
 // the exact 4-bit compare for windows that hold N / IUPAC codes, for the candidates still `valid`.
 template <int KC, int NC0>
@@ -805,7 +810,7 @@ __device__ __forceinline__ void compare_deep(const IndexDev &ix, const uint32_t 
                                              const uint32_t *mT, int n_words, int bound, const bool (&valid)[KC],
                                              const uint32_t (&slot)[KC], const uint32_t (&sub)[KC], int (&d)[KC],
                                              int (&pm)[KC], uint32_t (&the_pos)[KC], uint32_t &n_entry,
-                                             uint32_t &n_word) {
+                                             uint32_t &n_word, bool defer_exact = false) {
   const int n_bases = 16 * n_words;
   const int n_chunks = (n_bases + 31) >> 5;
   // ---- index gathers of the candidates the records did not reject (all of them without records) ----
@@ -890,6 +895,10 @@ __device__ __forceinline__ void compare_deep(const IndexDev &ix, const uint32_t 
 #pragma unroll
   for (int k = 0; k < KC; ++k)
     if (exc[k]) {
+      if (defer_exact) {  // the caller has no packed read yet: it runs exact_compare itself (kDeferredExact)
+        pm[k] = kDeferredExact;
+        continue;
+      }
       int mx = 0;
       d[k] = exact_compare(the_pos[k], n_words, bound, &mx);
       pm[k] = mx;
@@ -903,7 +912,7 @@ struct Deep1 {
   uint32_t pos, n_entry, n_word;
 };
 __device__ __noinline__ Deep1 compare_deep_one(const uint32_t *__restrict__ index3, int n_words, int bound, bool valid_in,
-                                               uint32_t slot_in, uint32_t sub_in) {
+                                               uint32_t slot_in, uint32_t sub_in, bool defer_exact = false) {
   const Warp W;
   const bool valid[1] = {valid_in};
   const uint32_t slot[1] = {slot_in}, sub[1] = {sub_in};
@@ -913,7 +922,7 @@ __device__ __noinline__ Deep1 compare_deep_one(const uint32_t *__restrict__ inde
   r.n_entry = 0;
   r.n_word = 0;
   compare_deep<1, 4>(params().ix, index3, W.masks(0), W.masks(1), W.masks(2), W.masks(3), n_words, bound, valid, slot, sub,
-                     d, pm, the_pos, r.n_entry, r.n_word);
+                     d, pm, the_pos, r.n_entry, r.n_word, defer_exact);
   r.d = d[0];
   r.pm = pm[0];
   r.pos = the_pos[0];
@@ -1824,6 +1833,261 @@ struct PeBest {
   __device__ int diffs() const { return (int)(int16_t)(r1.diffs() + r2.diffs()); }
 };
 
+// ---- best_pair on large candidate sets (repeats): the sweep by rows ----------------------------------------
+// best_pair (abismal.cpp:1722-1831) walks the position-sorted sets with two pointers: row j2 meets the entries
+// j1 in [lo(j2), hi(j2)) of the other set (lo, hi non-decreasing in j2), in the order (j2, j1), and folds every
+// pair into pe_element::update.  That fold depends on the order only through
+//   * the winner: the FIRST pair, in that order, whose key (pair score, then fewer diffs) beats the state the
+//     call started with and is not beaten later -- i.e. the first pair holding the best key;
+//   * the ambiguity flag: set when another pair (or the starting state) holds the same key;
+//   * `scr1`: on a memo hit the reference records the score of the set-1 alignment it ran most recently, not
+//     the partner's.  An alignment runs when its entry is met for the first time (j1 at
+//     or beyond every earlier row's hi) or when its memoised score is 0.
+// so 32 rows are evaluated at a time, one per lane, from precomputed scores, and combined by a warp reduction.
+// The early exit on sure_ambig only skips pairs that cannot change the state.
+constexpr int kScoreNone = -32768;
+
+struct PairPick {
+  int scr1, scr2;
+  uint32_t pos1, pos2, t1, t2;
+};
+
+// alignment scores of the entries of set `id` into scr[]: 2 * len for exact matches, the task's result, or -- for
+// needed entries without a task (list full) -- the banded DP in this warp
+template <class F>
+__device__ __forceinline__ void score_set(const Warp &W, int id, int end, uint32_t flags, int max_diffs, int readlen,
+                                          const uint32_t *tof, uint32_t ovf, int16_t *scr, F needed) {
+  const KernelParams &P = params();
+  const HeapRef v = heap_of(W, id);
+  const int n = W.cs(id)->sz;
+  AlnOut ao;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + W.lane;
+    Hit h(0);
+    int sc = kScoreNone;
+    bool want = false;
+    if (j < n) {
+      h = v.get(j);
+      if (!h.empty()) {
+        if (h.diffs() == 0) sc = (int)(int16_t)(2 * readlen);
+        else {
+          const uint32_t t = task_id_of(tof, j, ovf);
+          if (t != kNoTask) {
+            const uint2 rr = __ldcg(reinterpret_cast<const uint2 *>(P.task_res + t));
+            if ((int)(int16_t)(rr.y >> 16) == band_width(h.diffs(), max_diffs)) sc = (int)(int16_t)(rr.x & 0xffffu);
+          }
+          if (sc == kScoreNone) want = needed(h);
+        }
+      }
+    }
+    unsigned m = __ballot_sync(FULL, want);
+    while (m != 0u) {
+      const int k = __ffs(m) - 1;
+      m &= m - 1u;
+      const Hit hk(__shfl_sync(FULL, h.w, k));
+      const int a = (int)(int16_t)align(false, false, end, end, flags, hk.diffs(), max_diffs, readlen, hk.pos(), ao, kNoTask);
+      if (W.lane == k) sc = a;
+    }
+    if (j < n) scr[j] = (int16_t)sc;
+  }
+  __syncwarp();
+}
+
+__device__ __noinline__ PairPick best_pair_rows(bool swap_ends, int e1, uint32_t flags1, uint32_t flags2, PeBest *best_io,
+                                                const uint32_t *tof1, const uint32_t *tof2) {
+  const Warp W;
+  const KernelParams &P = params();
+  const int lane = W.lane;
+  const int e2 = 1 - e1;
+  PeBest best = *best_io;
+  const HeapRef v1 = heap_of(W, 2), v2 = heap_of(W, 3);
+  const int n1 = W.cs(2)->sz, n2 = W.cs(3)->sz;
+  int16_t *scr1 = P.mem_scr + W.slot() * (size_t)kPeLarge, *scr2 = P.mem_scr2 + W.slot() * (size_t)kPeLarge;
+  const uint32_t readlen1 = W.scal()->len[e1], readlen2 = W.scal()->len[e2];
+  const int max_diffs1 = frac_of(P.valid_frac, readlen1), max_diffs2 = frac_of(P.valid_frac, readlen2);
+  const uint32_t min_dist = P.min_dist, max_dist = P.max_dist;
+  const uint32_t ovf1 = W.cs(2)->ovf, ovf2 = W.cs(3)->ovf;
+  PairPick pick = PairPick{0, 0, 0u, 0u, kNoTask, kNoTask};
+  int s1 = 0, s2 = 0;  // leading empties (position 0 sorts first)
+  for (int j0 = 0; j0 < n1; j0 += 32) s1 += __popc(__ballot_sync(FULL, j0 + lane < n1 && v1.get(j0 + lane).empty()));
+  for (int j0 = 0; j0 < n2; j0 += 32) s2 += __popc(__ballot_sync(FULL, j0 + lane < n2 && v2.get(j0 + lane).empty()));
+  // first j1 in [s1, n1) with pos1 + add >= lim / pos1 + add > lim (32-bit arithmetic as in best_pair)
+  auto first_ge = [&](int lo, uint32_t add, uint32_t lim) {
+    int hi = n1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (v1.get(mid).pos() + add >= lim) hi = mid;
+      else lo = mid + 1;
+    }
+    return lo;
+  };
+  auto first_gt = [&](int lo, uint32_t add, uint32_t lim) {
+    int hi = n1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (v1.get(mid).pos() + add > lim) hi = mid;
+      else lo = mid + 1;
+    }
+    return lo;
+  };
+  // scores of the entries that have a partner (the others are never asked about)
+  score_set(W, 3, e2, flags2, max_diffs2, (int)readlen2, tof2, ovf2, scr2, [&](Hit h) {
+    const uint32_t lim = h.pos() + readlen2;
+    const int lo = first_ge(s1, max_dist, lim);
+    return lo < n1 && v1.get(lo).pos() + min_dist <= lim;
+  });
+  score_set(W, 2, e1, flags1, max_diffs1, (int)readlen1, tof1, ovf1, scr1, [&](Hit h) {
+    const uint32_t p1 = h.pos();
+    int lo = s2, hi = n2;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (v2.get(mid).pos() + readlen2 >= p1 + min_dist) hi = mid;
+      else lo = mid + 1;
+    }
+    return lo < n2 && p1 + max_dist >= v2.get(lo).pos() + readlen2;
+  });
+  __threadfence_block();
+  int carry_hi = 0;        // hi of the last non-empty row so far: entries below it have been met
+  int carry_exec = 0;      // score of the set-1 alignment run most recently (`scr1` of the reference)
+  for (int r0 = s2; r0 < n2 && !best.sure_ambig(); r0 += 32) {
+    const int j2 = r0 + lane;
+    const bool row = j2 < n2;
+    Hit h2(0);
+    int lo = 0, hi = 0, sc2 = 0;
+    if (row) {
+      h2 = v2.get(j2);
+      const uint32_t lim = h2.pos() + readlen2;
+      lo = first_ge(s1, max_dist, lim);
+      hi = first_gt(lo, min_dist, lim);
+      sc2 = (int)*(volatile int16_t *)(scr2 + j2);
+    }
+    const bool nonempty = row && lo < hi;
+    // hi of the nearest non-empty row below this lane (hi is non-decreasing over the rows)
+    int prev_hi = nonempty ? hi : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(FULL, prev_hi, d);
+      if (lane >= d) prev_hi = max(prev_hi, o);
+    }
+    const int chunk_hi = __shfl_sync(FULL, prev_hi, 31);
+    prev_hi = __shfl_up_sync(FULL, prev_hi, 1);
+    prev_hi = max(carry_hi, lane == 0 ? 0 : prev_hi);
+    // the row: best key, the first j1 holding it, how many hold it, zero scores in front of it, last run alignment
+    long long kbest = LLONG_MIN;
+    int jbest = -1, nbest = 0, last_zero = -1;
+    bool zero_before = false;
+    if (nonempty) {
+      for (int j1 = lo; j1 < hi; ++j1) {
+        const Hit h1 = v1.get(j1);
+        const int m1 = (int)*(volatile int16_t *)(scr1 + j1);
+        const int pair_scr = (int)(int16_t)(sc2 + m1);
+        const long long key = (long long)pair_scr * (1ll << 20) - (long long)(h1.diffs() + h2.diffs());
+        if (key > kbest) {
+          kbest = key;
+          jbest = j1;
+          nbest = 1;
+          zero_before = last_zero >= 0;
+        }
+        else if (key == kbest) ++nbest;
+        if (m1 == 0) last_zero = j1;
+      }
+    }
+    // A pair score equal to max_aln_score can end the reference's sweep in the middle of the chunk (sure_ambig):
+    // such chunks (rare: both ends match exactly) are folded pair by pair, in order, from the same scores.
+    int smax = nonempty ? (int)((kbest + (1ll << 19)) >> 20) : INT_MIN;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) smax = max(smax, __shfl_xor_sync(FULL, smax, d));
+    if (max(smax, best.aln_score) >= best.max_aln_score) {
+      int seen_hi = carry_hi, cur_scr1 = carry_exec;
+      bool stop = false;
+      for (int l = 0; l < 32 && !stop; ++l) {
+        const int lo_l = __shfl_sync(FULL, lo, l), hi_l = __shfl_sync(FULL, hi, l);
+        if (!(__shfl_sync(FULL, (int)nonempty, l) != 0)) continue;
+        const Hit g2(__shfl_sync(FULL, h2.w, l));
+        const int gsc2 = __shfl_sync(FULL, sc2, l);
+        for (int j1 = lo_l; j1 < hi_l; ++j1) {
+          if (best.sure_ambig()) {
+            stop = true;
+            break;
+          }
+          const Hit g1 = v1.get(j1);
+          const int m1 = (int)*(volatile int16_t *)(scr1 + j1);
+          if (j1 >= seen_hi || m1 == 0) cur_scr1 = m1;  // this alignment runs now
+          const int pair_scr = (int)(int16_t)(gsc2 + m1);
+          if (swap_ends ? best.update(pair_scr, g2, g1) : best.update(pair_scr, g1, g2)) {
+            pick.scr1 = cur_scr1;
+            pick.scr2 = gsc2;
+            pick.pos1 = g1.pos();
+            pick.pos2 = g2.pos();
+            pick.t1 = task_id_of(tof1, j1, ovf1);
+            pick.t2 = task_id_of(tof2, r0 + l, ovf2);
+          }
+        }
+        seen_hi = max(seen_hi, hi_l);
+      }
+      carry_exec = cur_scr1;
+      carry_hi = max(carry_hi, chunk_hi);
+      if (stop) break;
+      continue;
+    }
+    bool exec_any = false;
+    int exec_scr = 0;
+    if (nonempty) {
+      if (hi > prev_hi) {  // the row's last entry is met for the first time
+        exec_any = true;
+        exec_scr = (int)*(volatile int16_t *)(scr1 + hi - 1);
+      }
+      else if (last_zero >= 0) exec_any = true;  // exec_scr = 0
+    }
+    // ---- the chunk's first pair with the best key, and how many pairs hold that key
+    long long kmax = kbest;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) kmax = max(kmax, __shfl_xor_sync(FULL, kmax, d));
+    const unsigned holders = __ballot_sync(FULL, nonempty && kbest == kmax);
+    if (holders != 0u) {
+      const int wl = __ffs(holders) - 1;
+      int count = (nonempty && kbest == kmax) ? nbest : 0;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) count += __shfl_xor_sync(FULL, count, d);
+      const int rd = best.r1.diffs() + best.r2.diffs();
+      const long long kcur = (long long)best.aln_score * (1ll << 20) - (long long)rd;
+      if (kmax > kcur) {
+        // replacement by pair (row wl, its jbest); later holders of the key make it ambiguous
+        const int wj1 = __shfl_sync(FULL, jbest, wl);
+        const int wj2 = r0 + wl;
+        const Hit w1 = v1.get(wj1), w2 = v2.get(wj2);
+        const int wm1 = (int)*(volatile int16_t *)(scr1 + wj1), wsc2 = __shfl_sync(FULL, sc2, wl);
+        best.aln_score = (int)(int16_t)(wsc2 + wm1);
+        best.r1 = swap_ends ? w2 : w1;
+        best.r2 = swap_ends ? w1 : w2;
+        if (count >= 2) best.r1.set_ambig();
+        // scr1 at that moment
+        const int w_prev_hi = __shfl_sync(FULL, prev_hi, wl);
+        const bool w_zero_before = __shfl_sync(FULL, (int)zero_before, wl) != 0;
+        int stale;
+        if (wj1 >= w_prev_hi || wm1 == 0) stale = wm1;
+        else if (w_zero_before) stale = 0;
+        else {
+          const unsigned below = __ballot_sync(FULL, exec_any) & ((1u << wl) - 1u);
+          stale = below != 0u ? __shfl_sync(FULL, exec_scr, 31 - __clz(below)) : carry_exec;
+        }
+        pick.scr1 = stale;
+        pick.scr2 = wsc2;
+        pick.pos1 = w1.pos();
+        pick.pos2 = w2.pos();
+        pick.t1 = task_id_of(tof1, wj1, ovf1);
+        pick.t2 = task_id_of(tof2, wj2, ovf2);
+      }
+      else if (kmax == kcur) best.r1.set_ambig();
+    }
+    const unsigned execs = __ballot_sync(FULL, exec_any);
+    if (execs != 0u) carry_exec = __shfl_sync(FULL, exec_scr, 31 - __clz(execs));
+    carry_hi = max(carry_hi, chunk_hi);
+  }
+  *best_io = best;
+  return pick;
+}
+
 // best_pair<swap_ends> (abismal.cpp:1722-1831) over pe sets 2 (end e1, un-reversed) and 3 (end e2, reversed).
 // The traceback slot of an end is its end number.
 // tof1 / tof2: task ids of the entries of sets 2 / 3 (enum_kernel), or nullptr
@@ -1849,6 +2113,19 @@ __device__ __noinline__ void best_pair(bool swap_ends, int e1, uint32_t flags1, 
   const uint32_t ovf1 = W.cs(2)->ovf, ovf2 = W.cs(3)->ovf;
   AlnOut ao;
 
+  const bool by_rows = tof1 != nullptr && tof2 != nullptr && (uint32_t)max(j1_end, j2_end) >= P.heavy_min;
+  if (by_rows) {
+    const PairPick pk = best_pair_rows(swap_ends, e1, flags1, flags2, &best, tof1, tof2);
+    if (pk.pos1 != 0u) {
+      best_scr1 = pk.scr1;
+      best_scr2 = pk.scr2;
+      best_pos1 = pk.pos1;
+      best_pos2 = pk.pos2;
+      best_t1 = pk.t1;
+      best_t2 = pk.t2;
+    }
+    j2 = j2_end;  // the sweep below has nothing left to do
+  }
   for (; j1 != j1_end && v1.get(j1).empty(); ++j1) {
   }
   for (; j2 != j2_end && v2.get(j2).empty(); ++j2) {
@@ -1917,15 +2194,21 @@ __device__ __noinline__ void best_single(int pe_id, int se_id) {
   const HeapRef pv = heap_of(W, pe_id);
   const int n = W.cs(pe_id)->sz;
   __syncwarp();
-  if (W.lane == 0) {  // one lane mutates the set (see replay_hits)
-    CandSet res;
-    res.load(W, se_id);
-    for (int i = 0; i != n && !res.sure_ambig; ++i) {
-      const Hit h = pv.get(i);
-      res.update(false, h.diffs(), h.flags(), h.pos());
+  // one lane mutates the set (see replay_hits); the entries reach it 32 at a time through the warp (large sets
+  // live in HBM: one coalesced load per 32 entries instead of one dependent load per entry)
+  CandSet res;
+  res.load(W, se_id);
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const Hit h = i0 + W.lane < n ? pv.get(i0 + W.lane) : Hit(0);
+    const int m = min(32, n - i0);
+    for (int k = 0; k < m; ++k) {
+      const Hit hk(__shfl_sync(FULL, h.w, k));
+      if (W.lane == 0 && !res.sure_ambig) res.update(false, hk.diffs(), hk.flags(), hk.pos());
     }
-    res.store_one_lane(W, se_id);
+    if (__shfl_sync(FULL, (int)res.sure_ambig, 0) != 0) break;
   }
+  __syncwarp();
+  if (W.lane == 0) res.store_one_lane(W, se_id);
   __syncwarp();
 }
 
@@ -2453,7 +2736,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) align_kernel(const __g
 }
 
 // seed_bins.cuh: process_seeds for a strand whose prefilter survivors the binned kernels have listed
-__device__ void process_binned(int set_id, int end, uint32_t strand_code, uint32_t sid);
+__device__ void process_binned(int set_id, int end, uint32_t strand_code, uint32_t sid, const char *seq);
 
 // Phase 1 of the two-phase launch: seeding only.  Paired: one work item per (pair, call, side) -- the passes
 // of a pair are independent (every map_fragments call starts from reset pe_candidates) -- so a warp hashes,
@@ -2492,20 +2775,23 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
         publish_set(P, item, lane);
         continue;
       }
-      load_end(W, 0, P.seq[0] + o0, len);
+      const bool binned = P.bp.tup != nullptr;
+      if (!binned) load_end(W, 0, P.seq[0] + o0, len);
+      else if (lane == 0) S->loaded[0] = 0u;
       reset_set(W, 0, 0, len);
-      if (P.bp.tup != nullptr) {  // binned seeding: the strands in the order of strand_plan (seed_bins.cuh)
+      if (binned) {  // binned seeding: the strands in the order of strand_plan (seed_bins.cuh)
         const uint32_t s0 = P.bp.sid_base + item * P.bp.spi;
+        const char *sq = P.seq[0] + o0;
         if (rpbat) {
-          process_binned(0, 0, T, s0);
-          process_binned(0, 0, A, s0 + 1);
-          process_binned(0, 0, A | RC, s0 + 2);
-          process_binned(0, 0, T | RC, s0 + 3);
+          process_binned(0, 0, T, s0, sq);
+          process_binned(0, 0, A, s0 + 1, sq);
+          process_binned(0, 0, A | RC, s0 + 2, sq);
+          process_binned(0, 0, T | RC, s0 + 3, sq);
         }
         else {
           const uint32_t cv = a_rich ? A : T;
-          process_binned(0, 0, cv, s0);
-          process_binned(0, 0, cv | RC, s0 + 1);
+          process_binned(0, 0, cv, s0, sq);
+          process_binned(0, 0, cv | RC, s0 + 1, sq);
         }
       }
       else if (rpbat) {
@@ -2533,9 +2819,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) seed_kernel(const __gr
       __syncwarp();
       reset_set(W, 2, 1, len);
       if (len != 0) {
-        load_end(W, end, P.seq[end] + o, len);
-        if (P.bp.tup != nullptr) process_binned(2, end, flags, P.bp.sid_base + w);
-        else process_seeds(2, end, flags);
+        if (P.bp.tup != nullptr) {
+          if (lane == 0) S->loaded[end] = 0u;
+          process_binned(2, end, flags, P.bp.sid_base + w, P.seq[end] + o);
+        }
+        else {
+          load_end(W, end, P.seq[end] + o, len);
+          process_seeds(2, end, flags);
+        }
       }
       if (!store_set(W, 2, stored_set(P, item, pass), (int)P.set_slots, true)) {
         // grew beyond the stored form and the overflow arena is full (or absent): the whole pair is redone

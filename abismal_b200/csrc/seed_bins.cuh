@@ -29,7 +29,7 @@ constexpr uint32_t kBinMaxLen = 1023;    // seed offset field of a tuple: 10 bit
 constexpr uint32_t kMaxBins = 8192;      // bin cursors of one scatter CTA live in shared memory
 constexpr uint32_t kScatterThreads = 1024;
 constexpr uint32_t kTupleBlock = 256;    // tuple slots a warp reserves at a time
-constexpr uint32_t kSurvSlots = 64;      // survivors per strand the replay handles (two per lane)
+constexpr uint32_t kSurvSlots = 128;     // survivors per strand the replay handles (four per lane)
 constexpr uint32_t kMaxTupleCount = (1u << 24) - 1u;
 
 __device__ __forceinline__ uint32_t tuple_cnt(const SeedTuple &t) { return t.cnt_hi >> 8; }
@@ -80,25 +80,40 @@ __device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t s
   const BinParams &B = P.bp;
   const int lane = W.lane;
   build_qcode(end, strand_code);
-  build_packed(end, strand_code);
   al.full = false;
   const uint32_t readlen = W.scal()->len[end];
   const uint8_t *qcode = W.qcode(end);
-  // 2-bit planes of the encoded read (conversion undone: code 5 is A, code 10 is T); N anywhere -> direct path
+  const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
+  // One pass over the encoded read: the three hash planes (as build_packed leaves them; packed words and match
+  // masks are not needed here) and the 2-bit planes of the bases (conversion undone: code 5 is A, code 10 is T)
+  // for the scatter and seed kernels.  N anywhere -> direct path.
   {
+    uint32_t *p2w = W.plane(0), *p3aw = W.plane(1), *p3bw = W.plane(2);
+    const uint32_t hw = W.L.plane_words;
     uint32_t my_lo = 0, my_hi = 0;
     bool has_n = false;
-    for (uint32_t w = 0; w < B.pw; ++w) {
+    for (uint32_t w = 0; w < max(B.pw, hw); ++w) {
       const uint32_t i = 32u * w + (uint32_t)lane;
       const uint32_t code = i < readlen ? qcode[i] : 0u;
+      const uint32_t t = three_num(g_to_a, code);
+      const unsigned m2 = __ballot_sync(FULL, get_bit(code));
+      const unsigned ma = __ballot_sync(FULL, t & 1u);
+      const unsigned mb = __ballot_sync(FULL, t & 2u);
       const unsigned lo = __ballot_sync(FULL, code == 2u || (code & 8u) != 0u);
       const unsigned hi = __ballot_sync(FULL, code == 4u || (code & 8u) != 0u);
       has_n = has_n || __ballot_sync(FULL, i < readlen && code == 0u) != 0u;
+      if (lane == 0 && w < hw) {
+        p2w[w] = m2;
+        p3aw[w] = ma;
+        p3bw[w] = mb;
+      }
       if ((uint32_t)lane == w) {
         my_lo = lo;
         my_hi = hi;
       }
     }
+    if (lane == 0) W.scal()->packed_key = ~0u;  // the planes no longer belong to what build_packed last built
+    __syncwarp();
     uint32_t *dst = B.planes + (size_t)sid * 2u * B.pw;
     if ((uint32_t)lane < B.pw) {
       dst[lane] = my_lo;
@@ -108,7 +123,6 @@ __device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t s
   }
   const uint32_t *p2 = W.plane(0), *p3a = W.plane(1), *p3b = W.plane(2);
   const uint32_t *T3 = tab3();
-  const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
   const uint32_t *counter3 = g_to_a ? ix.counter_a : ix.counter_t;
   const uint32_t *index3 = g_to_a ? ix.index_a : ix.index_t;
   const uint32_t *bits3 = g_to_a ? ix.bits_a : ix.bits_t;
@@ -440,53 +454,106 @@ __global__ void __launch_bounds__(256, 4) filter_kernel(FilterParams F) {
 }
 
 // ---- seed_kernel side: the survivors of one strand against its candidate set ---------------------------------
-// Equivalent of process_seeds(set_id, end, strand_code) for strand `sid` when its survivors were listed.
-__device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand_code, uint32_t sid) {
+// The read's bases, encoded for the pass, when something needs them after all (the direct path, exact_compare)
+__device__ __forceinline__ void ensure_encoded(const Warp &W, int end, uint32_t strand_code, const char *seq) {
+  WarpScalars *S = W.scal();
+  __syncwarp();
+  if (S->loaded[end] == 0u) {
+    load_end(W, end, seq, S->len[end]);
+    if (W.lane == 0) S->loaded[end] = 1u;
+    __syncwarp();
+  }
+  build_qcode(end, strand_code);
+  build_packed(end, strand_code);
+}
+
+// Equivalent of process_seeds(set_id, end, strand_code) for strand `sid` when its survivors were listed.  The
+// match masks of the deep compare come from the 2-bit planes hash_kernel stored (no N in the read here), so the
+// read is not loaded and encoded a second time.
+__device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand_code, uint32_t sid, const char *seq) {
   const Warp W;
   const KernelParams &P = params();
   const BinParams &B = P.bp;
   const int lane = W.lane;
+  WarpScalars *S = W.scal();
   const uint32_t n_raw = __ldcg(B.surv_count + sid);
   if (__ldcg(B.strand_flag + sid) != 0u || n_raw > min(B.surv_cap, kSurvSlots)) {
+    ensure_encoded(W, end, strand_code, seq);
     process_seeds(set_id, end, strand_code);
     return;
   }
-  build_qcode(end, strand_code);
-  build_packed(end, strand_code);
   const int n = (int)n_raw;
-  const uint32_t readlen = W.scal()->len[end];
+  const uint32_t readlen = S->len[end];
   const int n_words = (int)((readlen + 15) / 16);
   const int bound = invalid_hit_diffs(readlen);
   const bool g_to_a = ((strand_code & ABG_FLAG_A_RICH) != 0) != ((strand_code & ABG_FLAG_RC) != 0);
   const uint32_t *index3 = g_to_a ? P.ix.index_a : P.ix.index_t;
-  // keys: offset | table | entry | spec | sens -- unique per candidate, so the flag bits never decide the order
-  uint64_t *keys = reinterpret_cast<uint64_t *>(W.log_pos());   // [64]
-  uint64_t *sorted = keys + kSurvSlots;                          // [64]
-  __syncwarp();
-  for (int k = lane; k < n; k += 32) {
-    const uint2 e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
-    const uint64_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
-    keys[k] = (off << 36) | (is3 << 35) | ((uint64_t)e.x << 3) | fl;
+  // ---- match masks (what build_packed derives from the encoded read): bit j of masks(X)[c] <=> read base 32c+j
+  // matches genome base X; a converted base also matches its partner; the 0xF tail of the last packed word
+  // matches everything, positions past it nothing
+  uint32_t lo = 0, hi = 0;
+  if ((uint32_t)lane < B.pw) {
+    const uint32_t *pl = B.planes + (size_t)sid * 2u * B.pw;
+    lo = __ldcg(pl + lane);
+    hi = __ldcg(pl + B.pw + lane);
   }
   __syncwarp();
-  for (int k = lane; k < n; k += 32) {
-    const uint64_t mine = keys[k];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += keys[j] < mine;
-    sorted[rank] = mine;
+  if ((uint32_t)lane < W.L.mask_words) {
+    const int r = (int)readlen - 32 * lane, t = 16 * n_words - 32 * lane;
+    const uint32_t real = r >= 32 ? ~0u : (r <= 0 ? 0u : ((1u << r) - 1u));
+    const uint32_t tail = (t >= 32 ? ~0u : (t <= 0 ? 0u : ((1u << t) - 1u))) & ~real;
+    const uint32_t isA = ~lo & ~hi & real, isC = lo & ~hi & real, isG = ~lo & hi & real, isT = lo & hi & real;
+    W.masks(0)[lane] = isA | tail;
+    W.masks(1)[lane] = isC | (g_to_a ? 0u : isT) | tail;
+    W.masks(2)[lane] = isG | (g_to_a ? isA : 0u) | tail;
+    W.masks(3)[lane] = isT | tail;
+  }
+  if (lane == 0) S->packed_key = ~0u;  // the masks no longer belong to what build_packed last built
+  // ---- canonical order (offset, two-letter before three-letter, entry): every lane ranks its own keys; the
+  // deep compare needs no particular order (it is pure), the results land at their rank
+  uint64_t *keys = reinterpret_cast<uint64_t *>(W.log_pos());  // [kSurvSlots] (the survivor log's region)
+  uint64_t mine[kSurvSlots / 32];
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < (int)kSurvSlots / 32; ++q) {
+    const int k = 32 * q + lane;
+    mine[q] = ~0ull;
+    if (k < n) {
+      const uint2 e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
+      const uint64_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
+      mine[q] = (off << 36) | (is3 << 35) | ((uint64_t)e.x << 3) | fl;  // unique per candidate: fl never decides
+      keys[k] = mine[q];
+    }
   }
   __syncwarp();
-  uint32_t *res_pos = reinterpret_cast<uint32_t *>(keys), *res_meta = res_pos + kSurvSlots;  // over the unsorted keys
-  for (int k0 = 0; k0 < n; k0 += 32) {
-    const int k = k0 + lane;
-    const bool valid = k < n;
-    const uint64_t key = valid ? sorted[k] : 0ull;
-    const uint32_t entry = (uint32_t)(key >> 3), is3 = (uint32_t)(key >> 35) & 1u, off = (uint32_t)(key >> 36);
-    const Deep1 r = compare_deep_one(index3, n_words, bound, valid, entry, off | (is3 << 31));
-    __syncwarp();
+  int rank[kSurvSlots / 32];
+#pragma unroll
+  for (int q = 0; q < (int)kSurvSlots / 32; ++q) {
+    rank[q] = 0;
+    if (32 * q + lane < n)
+      for (int j = 0; j < n; ++j) rank[q] += keys[j] < mine[q];
+  }
+  __syncwarp();
+  uint32_t *res_pos = reinterpret_cast<uint32_t *>(keys), *res_meta = res_pos + kSurvSlots;  // over the keys
+#pragma unroll
+  for (int q = 0; q < (int)kSurvSlots / 32; ++q) {
+    if (32 * q >= n) break;
+    const bool valid = 32 * q + lane < n;
+    const uint64_t key = valid ? mine[q] : 0ull;
+    const uint32_t entry = (uint32_t)(key >> 3), is3 = (uint32_t)(key >> 35) & 1u, off = (uint32_t)(key >> 36) & 1023u;
+    Deep1 r = compare_deep_one(index3, n_words, bound, valid, entry, off | (is3 << 31), true);
+    const bool deferred = valid && r.pm == kDeferredExact;
+    if (__any_sync(FULL, deferred)) {  // a window with N / IUPAC codes: the exact compare needs the packed read
+      ensure_encoded(W, end, strand_code, seq);
+      if (deferred) {
+        int mx = 0;
+        r.d = exact_compare(r.pos, n_words, bound, &mx);
+        r.pm = mx;
+      }
+    }
     if (valid) {
-      res_pos[k] = r.pos;
-      res_meta[k] = (uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)min(r.pm, 0x3fff) << 16) | ((uint32_t)(key & 3u) << 30);
+      res_pos[rank[q]] = r.pos;
+      res_meta[rank[q]] = (uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)max(0, min(r.pm, 0x3fff)) << 16) | ((uint32_t)(key & 3u) << 30);
     }
   }
   __syncwarp();

@@ -104,6 +104,26 @@ def test_records_equal_oracle_with_direct_seeding(workspace, rep_index, gpu, mon
     m.close()
 
 
+PE_CASES = [c for c in RECORD_CASES if c[1] & 1]
+
+
+@pytest.mark.parametrize("tag,mode,kw,files", PE_CASES, ids=[c[0] for c in PE_CASES])
+def test_records_equal_oracle_best_pair_by_rows(workspace, rep_index, gpu, monkeypatch, tag, mode, kw, files):
+    """ABISMAL_B200_HEAVY_MIN=0: every pair takes the row-parallel best_pair that large candidate sets (repeats)
+    take by default -- scores from the task results, 32 rows per step, the in-order fold for chunks that can reach
+    sure_ambig -- and gives the records of the two-pointer sweep."""
+    from abismal_b200 import Mapper
+    ixf, ix, kind = rep_index
+    monkeypatch.setenv("ABISMAL_B200_HEAVY_MIN", "0")
+    b = [_fq(workspace, f, kind=kind) for f in files]
+    m = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max([x.max_len for x in b] + [64]), **kw)
+    monkeypatch.delenv("ABISMAL_B200_HEAVY_MIN")
+    o = helpers.OracleMapper(ixf, mode=mode, **kw)
+    helpers.assert_results_equal(m.map_batch(*b), o.map_batch(*b), True)
+    o.close()
+    m.close()
+
+
 def test_binned_seeding_overflow_paths(workspace, rep_index, gpu, monkeypatch):
     """Tuple memory too small for the batch, survivor lists too short: the strands that do not fit take the direct
     path, same records."""

@@ -106,7 +106,7 @@ def main():
     ixf = IndexFile(idx)
     out["index_entries"] = [int(ixf.index_size), int(ixf.index_size_three)]
     ix = Index(ixf, 0)
-    for tasks, ovf, tscale in (("1", "32", "1"), ("1", "4096", "128"), ("0", "32", "1")):
+    for tasks, ovf, tscale in (("1", "256", "4"), ("1", "4096", "128")):
         os.environ["ABISMAL_B200_TASKS"] = tasks
         os.environ["ABISMAL_B200_OVF_PER_ITEM"] = ovf
         os.environ["ABISMAL_B200_TASK_SCALE"] = tscale
