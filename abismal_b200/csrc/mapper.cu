@@ -115,7 +115,7 @@ constexpr uint32_t kOvfPerItem = 256;  // overflow arena entries per pair of max
 // 3 GB per 2^20 pairs; a repeat-rich 100 Mbp test genome needs ~100 per pair (tools/repeat_perf.py)
 // task-parallel alignment: slots per read / pair in the three task lists (bands <= 16 / <= 32 / <= 61 columns) and
 // traceback allocations per read / pair (in tasks of the first class); beyond these the alignment runs in the warp
-constexpr uint32_t kTaskCapPe[3] = {5, 2, 1}, kTaskCapSe[3] = {3, 1, 1};
+constexpr uint32_t kTaskCapPe[3] = {40, 32, 8}, kTaskCapSe[3] = {24, 8, 8};  // 2 GB per 2^20 pairs
 constexpr uint32_t kTbTasksPe = 4, kTbTasksSe = 2;
 
 struct abg_mapper {

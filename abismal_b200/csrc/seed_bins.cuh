@@ -377,77 +377,94 @@ __global__ void __launch_bounds__(kScatterThreads) scatter_kernel(FilterParams F
       l[c] = __ldg(pl + c);
       h[c] = __ldg(ph + c);
     }
-    uint4 a, b;
-    a.x = __funnelshift_r(l[0], l[1], sh); a.y = __funnelshift_r(h[0], h[1], sh);
-    a.z = __funnelshift_r(l[1], l[2], sh); a.w = __funnelshift_r(h[1], h[2], sh);
-    b.x = __funnelshift_r(l[2], l[3], sh); b.y = __funnelshift_r(h[2], h[3], sh);
-    b.z = __funnelshift_r(l[3], l[4], sh); b.w = __funnelshift_r(h[3], h[4], sh);
-    F.pay_b[2 * (size_t)at] = a;
-    F.pay_b[2 * (size_t)at + 1] = b;
+    // g_to_a strands are stored complemented (A<->T, C<->G in the 2-bit code): "read A also matches genome G"
+    // becomes "read T also matches genome C", the rule of the other strands, once the record is complemented too
+    const uint32_t x = ((t.meta >> 30) & 1u) ? ~0u : 0u;
+    const uint32_t p0 = __funnelshift_r(l[0], l[1], sh) ^ x, p1 = __funnelshift_r(h[0], h[1], sh) ^ x;
+    const uint32_t p2 = __funnelshift_r(l[1], l[2], sh) ^ x, p3 = __funnelshift_r(h[1], h[2], sh) ^ x;
+    const uint32_t p4 = __funnelshift_r(l[2], l[3], sh) ^ x, p5 = __funnelshift_r(h[2], h[3], sh) ^ x;
+    const uint32_t p6 = __funnelshift_r(l[3], l[4], sh) ^ x, p7 = __funnelshift_r(h[3], h[4], sh) ^ x;
+    // one 32-byte store = one sector operation (the scatter is bound by the rate of scattered sector writes)
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(F.pay_b + 2 * (size_t)at), "r"(p0), "r"(p1), "r"(p2),
+                 "r"(p3), "r"(p4), "r"(p5), "r"(p6), "r"(p7)
+                 : "memory");
   }
 }
 
-// mismatch bits of 32 bases: genome planes (glo, ghi) against read planes (rlo, rhi); a converted read base also
-// matches its unconverted partner (g_to_a: read A matches genome G; else: read T matches genome C)
-__device__ __forceinline__ uint32_t mismatch_bits(uint32_t glo, uint32_t ghi, uint32_t rlo, uint32_t rhi, bool g_to_a) {
+// mismatch bits of 32 bases: genome planes (glo, ghi) against read planes (rlo, rhi), both complemented for
+// g_to_a strands, so that the one conversion rule left is "read T (11) also matches genome C (01)"
+__device__ __forceinline__ uint32_t mismatch_bits(uint32_t glo, uint32_t ghi, uint32_t rlo, uint32_t rhi) {
   const uint32_t diff = (glo ^ rlo) | (ghi ^ rhi);
-  const uint32_t extra = g_to_a ? (~rlo & ~rhi & ghi & ~glo) : (rlo & rhi & ~ghi & glo);
-  return diff & ~extra;
+  return diff & ~(rlo & rhi & glo & ~ghi);
+}
+__device__ __forceinline__ uint32_t low_mask(int k) {  // k low bits set, k in [0, 32]
+  uint32_t r;
+  asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(k));  // shifts of 32 and more give 0
+  return r - 1u;
 }
 
-__global__ void __launch_bounds__(256, 4) filter_kernel(FilterParams F) {
-  const int lane = threadIdx.x & 31;
+#ifndef ABG_FILTER_MINB
+#define ABG_FILTER_MINB 6
+#endif
+constexpr uint32_t kFilterGrab = 8;  // groups of 32 tuples a warp takes per work-counter atomic
+
+__global__ void __launch_bounds__(256, ABG_FILTER_MINB) filter_kernel(FilterParams F) {
+  __shared__ uint4 s_hdr[8][32];
+  __shared__ uint32_t s_excl[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = *F.n_binned;
   for (;;) {
-    uint32_t w0 = 0;
-    if (lane == 0) w0 = atomicAdd(F.work, 32u);
-    w0 = __shfl_sync(FULL, w0, 0);
-    if (w0 >= n) break;
-    SeedTuple t = SeedTuple{0u, 0u, 0u, 0u};
-    if (w0 + (uint32_t)lane < n) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(F.tup_b) + w0 + lane);
-      t.rec_lo = raw.x; t.cnt_hi = raw.y; t.sid = raw.z; t.meta = raw.w;
-    }
-    const uint32_t tot = tuple_cnt(t);
-    const uint32_t incl = warp_incl_scan_add(tot, lane);
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    for (uint32_t c0 = 0; c0 < total; c0 += 32) {
-      const uint32_t cidx = c0 + (uint32_t)lane;
-      const bool valid = cidx < total;
-      int o = 0;  // owner lane = number of lanes whose inclusive sum is <= cidx
-#pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) {
-        const uint32_t vv = __shfl_sync(FULL, incl, (o + s - 1) & 31);
-        if (vv <= cidx) o += s;
-      }
-      o &= 31;
-      const uint32_t o_incl = __shfl_sync(FULL, incl, o), o_tot = __shfl_sync(FULL, tot, o);
-      const uint32_t o_rec_lo = __shfl_sync(FULL, t.rec_lo, o), o_hi = __shfl_sync(FULL, t.cnt_hi, o) & 255u;
-      const uint32_t o_meta = __shfl_sync(FULL, t.meta, o), o_sid = __shfl_sync(FULL, t.sid, o);
-      if (!valid) continue;
-      const uint32_t r = cidx - (o_incl - o_tot);
-      const uint32_t tab = tuple_table(o_meta);
-      const uint64_t rec = ((uint64_t)o_rec_lo | ((uint64_t)o_hi << 32)) + r;
-      uint32_t w[8];
-      load_ctx(F.ctx[tab] + 2 * rec, w);
-      const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
-      const bool sentinel = (w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) == ~0u;
-      const bool g_to_a = (o_meta >> 30) & 1u;
-      const int nb = (int)((o_meta >> 10) & 255u);  // compared bases of the record: 1..128
-      const uint32_t m0 = mismatch_bits(w[0], w[1], pa.x, pa.y, g_to_a), m1 = mismatch_bits(w[2], w[3], pa.z, pa.w, g_to_a);
-      const uint32_t m2 = mismatch_bits(w[4], w[5], pb.x, pb.y, g_to_a), m3 = mismatch_bits(w[6], w[7], pb.z, pb.w, g_to_a);
-      int lb = __popc(nb >= 32 ? m0 : (m0 & ((1u << nb) - 1u)));
-      if (nb > 32) lb += __popc(nb >= 64 ? m1 : (m1 & ((1u << (nb - 32)) - 1u)));
-      if (nb > 64) lb += __popc(nb >= 96 ? m2 : (m2 & ((1u << (nb - 64)) - 1u)));
-      if (nb > 96) lb += __popc(nb >= 128 ? m3 : (m3 & ((1u << (nb - 96)) - 1u)));
-      const int bound = (int)((o_meta >> 18) & 511u);
-      if (lb <= bound || sentinel) {
-        const uint32_t off = o_meta & 1023u;
-        const uint32_t a = min((uint32_t)(kCtxArrays - 1), off >> 5);
-        const uint32_t entry = (uint32_t)(rec - (uint64_t)a * F.n_tab[tab]);
-        const uint32_t at = atomicAdd(F.surv_count + o_sid, 1u);
-        if (at < F.surv_cap)
-          F.surv[(size_t)o_sid * F.surv_cap + at] = make_uint2(entry, off | ((o_meta >> 27) & 7u) << 10);
+    uint32_t g0 = 0;
+    if (lane == 0) g0 = atomicAdd(F.work, 32u * kFilterGrab);
+    g0 = __shfl_sync(FULL, g0, 0);
+    if (g0 >= n) break;
+    const uint32_t g1 = min(n, g0 + 32u * kFilterGrab);
+    for (uint32_t w0 = g0; w0 < g1; w0 += 32) {
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (w0 + (uint32_t)lane < n) raw = __ldcs(reinterpret_cast<const uint4 *>(F.tup_b) + w0 + lane);
+      const uint32_t tot = raw.y >> 8;
+      const uint32_t incl = warp_incl_scan_add(tot, lane);
+      const uint32_t total = __shfl_sync(FULL, incl, 31);
+      const uint32_t excl = incl - tot;
+      __syncwarp();
+      s_hdr[wid][lane] = raw;
+      s_excl[wid][lane] = excl;
+      __syncwarp();
+      for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+        // owner tuple of candidate c0 + lane: tuples that end at or before c0, plus the tuples that start inside
+        // (c0, c0 + lane] (every binned tuple has at least one candidate)
+        const uint32_t st = excl - c0;
+        const uint32_t heads = __reduce_or_sync(FULL, (tot != 0u && st - 1u < 31u) ? (1u << st) : 0u);
+        const uint32_t first = (uint32_t)__popc(__ballot_sync(FULL, incl <= c0));
+        const uint32_t cidx = c0 + (uint32_t)lane;
+        if (cidx >= total) continue;
+        const uint32_t o = (first + (uint32_t)__popc(heads & ((2u << lane) - 1u) & ~1u)) & 31u;
+        const uint4 h = s_hdr[wid][o];
+        const uint32_t r = cidx - s_excl[wid][o];
+        const uint32_t meta = h.w;
+        const uint32_t tab = tuple_table(meta);
+        const uint64_t rec = ((uint64_t)h.x | ((uint64_t)(h.y & 255u) << 32)) + r;
+        uint32_t w[8];
+        load_ctx(F.ctx[tab] + 2 * rec, w);
+        const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
+        const bool sentinel = (w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) == ~0u;
+        const uint32_t x = ((meta >> 30) & 1u) ? ~0u : 0u;
+        const uint32_t m0 = mismatch_bits(w[0] ^ x, w[1] ^ x, pa.x, pa.y), m1 = mismatch_bits(w[2] ^ x, w[3] ^ x, pa.z, pa.w);
+        const uint32_t m2 = mismatch_bits(w[4] ^ x, w[5] ^ x, pb.x, pb.y), m3 = mismatch_bits(w[6] ^ x, w[7] ^ x, pb.z, pb.w);
+        const int nb = (int)((meta >> 10) & 255u);  // compared bases of the record: 1..128
+        int lb;
+        if (nb >= 64)
+          lb = __popc(m0) + __popc(m1) + __popc(m2 & low_mask(min(nb - 64, 32))) + __popc(m3 & low_mask(max(nb - 96, 0)));
+        else
+          lb = __popc(m0 & low_mask(min(nb, 32))) + __popc(m1 & low_mask(max(nb - 32, 0)));
+        const int bound = (int)((meta >> 18) & 511u);
+        if (lb <= bound || sentinel) {
+          const uint32_t off = meta & 1023u;
+          const uint32_t a = min((uint32_t)(kCtxArrays - 1), off >> 5);
+          const uint32_t entry = (uint32_t)(rec - (uint64_t)a * F.n_tab[tab]);
+          const uint32_t at = atomicAdd(F.surv_count + h.z, 1u);
+          if (at < F.surv_cap) F.surv[(size_t)h.z * F.surv_cap + at] = make_uint2(entry, off | ((meta >> 27) & 7u) << 10);
+        }
       }
     }
   }
@@ -509,37 +526,29 @@ __device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand
     W.masks(3)[lane] = isT | tail;
   }
   if (lane == 0) S->packed_key = ~0u;  // the masks no longer belong to what build_packed last built
-  // ---- canonical order (offset, two-letter before three-letter, entry): every lane ranks its own keys; the
-  // deep compare needs no particular order (it is pure), the results land at their rank
+  // ---- canonical order (offset, two-letter before three-letter, entry): rank of every key; perm[rank] = slot
   uint64_t *keys = reinterpret_cast<uint64_t *>(W.log_pos());  // [kSurvSlots] (the survivor log's region)
-  uint64_t mine[kSurvSlots / 32];
+  uint8_t *perm = reinterpret_cast<uint8_t *>(W.stage());       // [kSurvSlots] (the staging region of replay_hits)
   __syncwarp();
-#pragma unroll
-  for (int q = 0; q < (int)kSurvSlots / 32; ++q) {
-    const int k = 32 * q + lane;
-    mine[q] = ~0ull;
-    if (k < n) {
-      const uint2 e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
-      const uint64_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
-      mine[q] = (off << 36) | (is3 << 35) | ((uint64_t)e.x << 3) | fl;  // unique per candidate: fl never decides
-      keys[k] = mine[q];
-    }
+  for (int k = lane; k < n; k += 32) {
+    const uint2 e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
+    const uint64_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
+    keys[k] = (off << 36) | (is3 << 35) | ((uint64_t)e.x << 3) | fl;  // unique per candidate: fl never decides
   }
   __syncwarp();
-  int rank[kSurvSlots / 32];
-#pragma unroll
-  for (int q = 0; q < (int)kSurvSlots / 32; ++q) {
-    rank[q] = 0;
-    if (32 * q + lane < n)
-      for (int j = 0; j < n; ++j) rank[q] += keys[j] < mine[q];
+  for (int k = lane; k < n; k += 32) {
+    const uint64_t mine = keys[k];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += keys[j] < mine;
+    perm[rank] = (uint8_t)k;
   }
   __syncwarp();
-  uint32_t *res_pos = reinterpret_cast<uint32_t *>(keys), *res_meta = res_pos + kSurvSlots;  // over the keys
-#pragma unroll
-  for (int q = 0; q < (int)kSurvSlots / 32; ++q) {
-    if (32 * q >= n) break;
-    const bool valid = 32 * q + lane < n;
-    const uint64_t key = valid ? mine[q] : 0ull;
+  // ---- deep compare of every survivor (pure: any order); the result takes the place of its key
+  uint32_t *res = reinterpret_cast<uint32_t *>(keys);  // slot k: {pos, d | pm << 16 | spec << 30 | sens << 31}
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int k = k0 + lane;
+    const bool valid = k < n;
+    const uint64_t key = valid ? keys[k] : 0ull;
     const uint32_t entry = (uint32_t)(key >> 3), is3 = (uint32_t)(key >> 35) & 1u, off = (uint32_t)(key >> 36) & 1023u;
     Deep1 r = compare_deep_one(index3, n_words, bound, valid, entry, off | (is3 << 31), true);
     const bool deferred = valid && r.pm == kDeferredExact;
@@ -551,30 +560,33 @@ __device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand
         r.pm = mx;
       }
     }
+    __syncwarp();
     if (valid) {
-      res_pos[rank[q]] = r.pos;
-      res_meta[rank[q]] = (uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)max(0, min(r.pm, 0x3fff)) << 16) | ((uint32_t)(key & 3u) << 30);
+      res[2 * k] = r.pos;
+      res[2 * k + 1] = (uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)max(0, min(r.pm, 0x3fff)) << 16) | ((uint32_t)(key & 3u) << 30);
     }
   }
   __syncwarp();
   if (lane == 0) {  // one lane mutates the set (see replay_hits)
-    CandSet res;
-    res.load(W, set_id);
-    res.set_specific();
-    for (int k = 0; k < n && !res.sure_ambig; ++k) {
-      const uint32_t m = res_meta[k];
+    CandSet cs;
+    cs.load(W, set_id);
+    cs.set_specific();
+    for (int q = 0; q < n && !cs.sure_ambig; ++q) {
+      const int k = perm[q];
+      const uint32_t m = res[2 * k + 1];
       if (((m >> 30) & 1u) == 0u) continue;  // bit 30: examined by the specific phase (tuple bit 28)
-      if ((int)((m >> 16) & 0x3fffu) <= res.cutoff) res.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res_pos[k]);
+      if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res[2 * k]);
     }
-    if (res.should_do_sensitive()) {
-      res.set_sensitive();
-      for (int k = 0; k < n && !res.sure_ambig; ++k) {
-        const uint32_t m = res_meta[k];
+    if (cs.should_do_sensitive()) {
+      cs.set_sensitive();
+      for (int q = 0; q < n && !cs.sure_ambig; ++q) {
+        const int k = perm[q];
+        const uint32_t m = res[2 * k + 1];
         if (((m >> 31) & 1u) == 0u) continue;  // bit 31: examined by the sensitive phase (tuple bit 29)
-        if ((int)((m >> 16) & 0x3fffu) <= res.cutoff) res.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res_pos[k]);
+        if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res[2 * k]);
       }
     }
-    res.store_one_lane(W, set_id);
+    cs.store_one_lane(W, set_id);
   }
   __syncwarp();
 }
