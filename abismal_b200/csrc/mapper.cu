@@ -117,6 +117,7 @@ constexpr uint32_t kOvfPerItem = 256;  // overflow arena entries per pair of max
 // traceback allocations per read / pair (in tasks of the first class); beyond these the alignment runs in the warp
 constexpr uint32_t kTaskCapPe[3] = {40, 32, 8}, kTaskCapSe[3] = {24, 8, 8};  // 2 GB per 2^20 pairs
 constexpr uint32_t kTbTasksPe = 4, kTbTasksSe = 2;
+constexpr int kScatterCtasPerSm = 2;  // count_kernel / scatter_kernel: CTAs per SM (the scatter is bound by memory latency)
 
 struct abg_mapper {
   abg_index *idx = nullptr;
@@ -169,6 +170,8 @@ struct abg_mapper {
   uint32_t spi = 1, bin_shift = 0, n_bins = 0, tup_cap = 0, pw = 0, surv_cap = 0;
   const void *kernel_h = nullptr;
   int grid_h = 0, grid_sc = 0, grid_f = 0;
+  bool filter_pipe = false;  // filter_kernel<true>: two record gathers per lane in flight
+  uint32_t filter_grab = 64;  // tuples per work-cursor atomic: the live window of the record array stays near one bin
   ab2dev::SeedTuple *d_tup = nullptr, *d_tup_b = nullptr;
   uint4 *d_pay_b = nullptr;
   uint32_t *d_planes = nullptr, *d_bin_hist = nullptr, *d_surv_count = nullptr;
@@ -367,6 +370,7 @@ ab2dev::FilterParams filter_params(const abg_mapper *m) {
   F.surv = m->d_surv;
   F.surv_cap = m->surv_cap;
   F.work = m->d_bin_work + 2;
+  F.grab = m->filter_grab;
   return F;
 }
 
@@ -399,7 +403,8 @@ int launch_bins(const abg_mapper *m, cudaStream_t st, const cudaEvent_t *ev_b = 
   ab2dev::bin_prefix_kernel<<<1, 1024, 0, st>>>(F, (uint32_t)m->grid_sc);
   ab2dev::scatter_kernel<<<m->grid_sc, ab2dev::kScatterThreads, sm, st>>>(F);
   if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[1], st));
-  ab2dev::filter_kernel<<<m->grid_f, 256, 0, st>>>(F);
+  if (m->filter_pipe) ab2dev::filter_kernel<true><<<m->grid_f, 256, 0, st>>>(F);
+  else ab2dev::filter_kernel<false><<<m->grid_f, 256, 0, st>>>(F);
   if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[2], st));
   ABG_CUDA(cudaGetLastError());
   return ABG_OK;
@@ -1015,6 +1020,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       while ((total_rec >> shift) + 1 > ab2dev::kMaxBins) ++shift;
       m->bin_shift = shift;
       m->n_bins = (uint32_t)(total_rec >> shift) + 1u;
+      if (const char *eg = std::getenv("ABISMAL_B200_FILTER_GRAB"))  // tuning: 32 .. 4096 tuples
+        if (std::atoi(eg) >= 32 && std::atoi(eg) <= 4096) m->filter_grab = (uint32_t)std::atoi(eg) / 32u * 32u;
       m->surv_cap = ab2dev::kSurvSlots;
       if (const char *ec = std::getenv("ABISMAL_B200_SURV_CAP"))  // testing aid: fewer listed survivors per strand
         if (std::atol(ec) > 0) m->surv_cap = std::min<uint32_t>(ab2dev::kSurvSlots, (uint32_t)std::atol(ec));
@@ -1024,7 +1031,9 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       ABG_M(raise_smem_cap(ix->device, m->kernel_h, m->smem_s));
       int per_h = 0, per_f = 0;
       ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_h, m->kernel_h, ab2dev::kThreadsPerBlock, m->smem_s));
-      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, (const void *)ab2dev::filter_kernel, 256, 0));
+      if (const char *ep = std::getenv("ABISMAL_B200_FILTER_PIPE")) m->filter_pipe = std::atoi(ep) != 0;
+      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, m->filter_pipe ? (const void *)ab2dev::filter_kernel<true>
+                                                                                   : (const void *)ab2dev::filter_kernel<false>, 256, 0));
       // any allocation that fails switches the binned path off (the direct path needs none of this memory)
       bool ok = per_h >= 1 && per_f >= 1;
       auto grab = [&](void **ptr, size_t bytes) {
@@ -1038,7 +1047,7 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       grab((void **)&m->d_pay_b, cap * 32);
       grab((void **)&m->d_planes, n_strands * 2 * m->pw * 4);
       grab((void **)&m->d_strand_flag, n_strands);
-      grab((void **)&m->d_bin_hist, (size_t)m->n_bins * n_sm * 4);
+      grab((void **)&m->d_bin_hist, (size_t)m->n_bins * n_sm * kScatterCtasPerSm * 4);
       grab((void **)&m->d_surv_count, n_strands * 4);
       grab((void **)&m->d_surv, n_strands * m->surv_cap * sizeof(uint2));
       grab((void **)&m->d_bin_work, 4 * sizeof(unsigned int));
@@ -1056,7 +1065,7 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       }
       else {
         m->grid_h = n_sm * per_h;
-        m->grid_sc = n_sm;  // one 1024-thread CTA per SM: its write frontier (one line per bin) stays in L2
+        m->grid_sc = n_sm * kScatterCtasPerSm;  // 1024-thread CTAs; every CTA has its own write range in every bin
         m->grid_f = n_sm * per_f;
         for (int k = 0; k < 3; ++k) ABG_M(cudaEventCreate(&m->ev_b[k]));
         ABG_M(cudaEventCreateWithFlags(&m->ev_bins, cudaEventDisableTiming));

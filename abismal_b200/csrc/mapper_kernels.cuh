@@ -128,7 +128,7 @@ struct BinParams {
   unsigned int *tup_count;    // slots handed out (in blocks; unused slots hold empty tuples)
   uint32_t tup_cap;
   uint32_t pw;                // words per read plane
-  uint32_t *planes;           // [strand][2][pw]: 2-bit codes of the strand's read (A0 C1 G2 T3) as two bit planes
+  uint32_t *planes;           // [strand][pw][2]: 2-bit codes of the strand's read (A0 C1 G2 T3), {lo, hi} plane words of 32 bases
   uint8_t *strand_flag;       // [strand]: 0 = survivors listed, 1 = take the direct path (process_seeds), 2 = empty read
   uint32_t *bin_hist;         // (scatter kernels) tuples per (bin, scatter CTA)
   uint32_t bin_shift, n_bins; // bin = global record number >> bin_shift

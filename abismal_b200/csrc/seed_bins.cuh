@@ -73,7 +73,12 @@ __device__ __forceinline__ void emit_tuples(const BinParams &B, TupleAlloc &al, 
 
 // Everything of process_seeds up to the candidate ranges, for pass `strand_code` of `end`: tuples + read planes.
 // Returns the strand's flag.
-__device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t strand_code, uint32_t sid) {
+// (The tuple cursor travels by value: by reference it would live in local memory of the caller.)
+struct EmitResult {
+  TupleAlloc al;
+  uint32_t flag;
+};
+__device__ __noinline__ EmitResult emit_strand(TupleAlloc al, int end, uint32_t strand_code, uint32_t sid) {
   const Warp W;
   const KernelParams &P = params();
   const IndexDev &ix = P.ix;
@@ -114,12 +119,10 @@ __device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t s
     }
     if (lane == 0) W.scal()->packed_key = ~0u;  // the planes no longer belong to what build_packed last built
     __syncwarp();
-    uint32_t *dst = B.planes + (size_t)sid * 2u * B.pw;
-    if ((uint32_t)lane < B.pw) {
-      dst[lane] = my_lo;
-      dst[B.pw + lane] = my_hi;
-    }
-    if (has_n || readlen > kBinMaxLen) return 1u;
+    // {lo, hi} of 32 bases side by side: the scatter kernel's five-word windows are five 8-byte loads
+    uint2 *dst = reinterpret_cast<uint2 *>(B.planes) + (size_t)sid * B.pw;
+    if ((uint32_t)lane < B.pw) dst[lane] = make_uint2(my_lo, my_hi);
+    if (has_n || readlen > kBinMaxLen) return EmitResult{al, 1u};
   }
   const uint32_t *p2 = W.plane(0), *p3a = W.plane(1), *p3b = W.plane(2);
   const uint32_t *T3 = tab3();
@@ -134,9 +137,23 @@ __device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t s
   const uint32_t bound = (uint32_t)invalid_hit_diffs(readlen);
   const uint32_t meta_strand = (bound << 18) | (g_to_a ? (1u << 30) : 0u);
   bool bad = false;
+  // the probes of the next 32 offsets are requested into L1 while this round's are consumed (the compact counter
+  // blocks and the bitmaps live in L2: the round trip is the kernel's longest stall)
+  auto prefetch_probes = [&](uint32_t i) {
+    if (i >= n_off) return;
+    const uint32_t k = __brev(plane_window(p2, i)) >> 7;
+    if (ix.cc != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.cc + 2 * (size_t)(k / kCcKeys)));
+    if (bits3 != nullptr) {
+      const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
+      const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(bits3 + (k3 >> 5)));
+    }
+  };
+  prefetch_probes((uint32_t)lane);
   for (uint32_t base_off = 0; base_off < n_off; base_off += 32) {
     const uint32_t i = base_off + (uint32_t)lane;
     const bool active = i < n_off;
+    prefetch_probes(i + 32u);
     const bool in_spec = i < specific_lim, in_sens = i < lim_two;
     SeedTuple t2, t3;
     bool has2 = false, has3 = false;
@@ -159,13 +176,13 @@ __device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t s
         const bool sens = el2 && in_sens;
         uint32_t lo = s2, hi = e2;
         if (in_spec) {
-          if (d_two > maxc || d_two == 0u) {  // the specific phase narrows the bucket (abismal.cpp:1316-1323)
+          if (d_two > maxc) {  // the specific phase narrows the bucket (abismal.cpp:1316-1323)
             const SeedRange r = find_candidates(maxc, qcode + i, readlen - i, s2, e2);
             lo = r.low;
             hi = r.high;
             spec = (hi - lo) != 0u && ((hi - lo) <= maxc || r.p >= specific_len);
           }
-          else spec = true;
+          else spec = d_two != 0u;  // (an empty bucket comes back from find_candidates as it went in)
         }
         if (spec || sens) {
           const uint32_t cnt = hi - lo;
@@ -183,13 +200,13 @@ __device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t s
         const bool sens = el3 && in_sens;
         uint32_t lo = s3, hi = e3;
         if (in_spec) {
-          if (d_three > maxc || d_three == 0u) {
+          if (d_three > maxc) {
             const SeedRange r = find_candidates_three(index3, g_to_a, maxc, qcode + i, readlen - i, s3, e3);
             lo = r.low;
             hi = r.high;
             spec = (hi - lo) != 0u && ((hi - lo) <= maxc || r.p >= specific_len);
           }
-          else spec = true;
+          else spec = d_three != 0u;
         }
         if (spec || sens) {
           const uint32_t cnt = hi - lo;
@@ -207,8 +224,7 @@ __device__ __noinline__ uint32_t emit_strand(TupleAlloc &al, int end, uint32_t s
     emit_tuples(B, al, has2, t2, lane);
     emit_tuples(B, al, has3, t3, lane);
   }
-  if (__any_sync(FULL, bad) || al.full) return 1u;
-  return 0u;
+  return EmitResult{al, (__any_sync(FULL, bad) || al.full) ? 1u : 0u};
 }
 
 // (end, flags) of strand `pass` of an item: the order process_seeds is called in by map_single_ended[_rand]
@@ -261,7 +277,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) hash_kernel(const __gr
     uint32_t flag = 2u;
     if (len != 0) {
       load_end(W, end, P.seq[end] + o, len);
-      flag = emit_strand(al, end, flags, B.sid_base + w);
+      const EmitResult er = emit_strand(al, end, flags, B.sid_base + w);
+      al = er.al;
+      flag = er.flag;
     }
     if (lane == 0) B.strand_flag[B.sid_base + w] = (uint8_t)flag;
   }
@@ -288,6 +306,7 @@ struct FilterParams {
   uint2 *surv;
   uint32_t surv_cap;
   unsigned int *work;      // filter_kernel's work cursor
+  uint32_t grab;           // tuples a filter warp takes per work-cursor atomic (a multiple of 32)
 };
 
 // Binning without global atomics: CTA c of count_kernel and of scatter_kernel owns the same contiguous range of
@@ -353,39 +372,43 @@ __global__ void bin_prefix_kernel(FilterParams F, uint32_t n_cta) {
   }
 }
 
-__global__ void __launch_bounds__(kScatterThreads) scatter_kernel(FilterParams F) {
+__global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(FilterParams F) {
   extern __shared__ uint32_t s_bins[];
   for (uint32_t b = threadIdx.x; b < F.n_bins; b += blockDim.x) s_bins[b] = F.bin_hist[(size_t)b * gridDim.x + blockIdx.x];
   __syncthreads();
   uint64_t i0, i1;
   cta_range(F, i0, i1);
-  for (uint64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    uint4 raw;
-    const SeedTuple t = load_tuple(F.tup + i, raw);
-    if (tuple_cnt(t) == 0u) continue;
-    const uint64_t g = F.rec_base[tuple_table(t.meta)] + tuple_rec(t);
-    const uint32_t at = atomicAdd(s_bins + (uint32_t)(g >> F.bin_shift), 1u);
-    reinterpret_cast<uint4 *>(F.tup_b)[at] = raw;
+  // the kernel is bound by memory latency (tuple -> planes of its strand -> two scattered stores): the next tuple
+  // is in flight while this one is handled, and two CTAs of 1024 threads share an SM
+  const uint4 *src = reinterpret_cast<const uint4 *>(F.tup);
+  uint64_t i = i0 + threadIdx.x;
+  uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+  if (i < i1) nxt = __ldcs(src + i);
+  for (; i < i1; i += blockDim.x) {
+    const uint4 raw = nxt;
+    if (i + blockDim.x < i1) nxt = __ldcs(src + i + blockDim.x);
+    if ((raw.y >> 8) == 0u) continue;
+    const uint32_t meta = raw.w;
+    const uint64_t g = F.rec_base[tuple_table(meta)] + ((uint64_t)raw.x | ((uint64_t)(raw.y & 255u) << 32));
     // the 128 read bases from q0 = offset - 32 a (a = min(offset / 32, 3)), as four {lo, hi} plane words
-    const uint32_t off = t.meta & 1023u;
+    const uint32_t off = meta & 1023u;
     const uint32_t q0 = off - 32u * min((uint32_t)(kCtxArrays - 1), off >> 5);
-    const uint32_t w0 = q0 >> 5, sh = q0 & 31u;
-    const uint32_t *pl = F.planes + (size_t)t.sid * 2u * F.pw + w0, *ph = pl + F.pw;
-    uint32_t l[5], h[5];
+    const uint32_t sh = q0 & 31u;
+    const uint2 *pl = reinterpret_cast<const uint2 *>(F.planes) + (size_t)raw.z * F.pw + (q0 >> 5);
+    uint2 v[5];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-      l[c] = __ldg(pl + c);
-      h[c] = __ldg(ph + c);
-    }
+    for (int c = 0; c < 5; ++c) v[c] = __ldg(pl + c);
+    const uint32_t at = atomicAdd(s_bins + (uint32_t)(g >> F.bin_shift), 1u);
+    __stcs(reinterpret_cast<uint4 *>(F.tup_b) + at, raw);
     // g_to_a strands are stored complemented (A<->T, C<->G in the 2-bit code): "read A also matches genome G"
     // becomes "read T also matches genome C", the rule of the other strands, once the record is complemented too
-    const uint32_t x = ((t.meta >> 30) & 1u) ? ~0u : 0u;
-    const uint32_t p0 = __funnelshift_r(l[0], l[1], sh) ^ x, p1 = __funnelshift_r(h[0], h[1], sh) ^ x;
-    const uint32_t p2 = __funnelshift_r(l[1], l[2], sh) ^ x, p3 = __funnelshift_r(h[1], h[2], sh) ^ x;
-    const uint32_t p4 = __funnelshift_r(l[2], l[3], sh) ^ x, p5 = __funnelshift_r(h[2], h[3], sh) ^ x;
-    const uint32_t p6 = __funnelshift_r(l[3], l[4], sh) ^ x, p7 = __funnelshift_r(h[3], h[4], sh) ^ x;
+    const uint32_t x = ((meta >> 30) & 1u) ? ~0u : 0u;
+    const uint32_t p0 = __funnelshift_r(v[0].x, v[1].x, sh) ^ x, p1 = __funnelshift_r(v[0].y, v[1].y, sh) ^ x;
+    const uint32_t p2 = __funnelshift_r(v[1].x, v[2].x, sh) ^ x, p3 = __funnelshift_r(v[1].y, v[2].y, sh) ^ x;
+    const uint32_t p4 = __funnelshift_r(v[2].x, v[3].x, sh) ^ x, p5 = __funnelshift_r(v[2].y, v[3].y, sh) ^ x;
+    const uint32_t p6 = __funnelshift_r(v[3].x, v[4].x, sh) ^ x, p7 = __funnelshift_r(v[3].y, v[4].y, sh) ^ x;
     // one 32-byte store = one sector operation (the scatter is bound by the rate of scattered sector writes)
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(F.pay_b + 2 * (size_t)at), "r"(p0), "r"(p1), "r"(p2),
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(F.pay_b + 2 * (size_t)at), "r"(p0), "r"(p1), "r"(p2),
                  "r"(p3), "r"(p4), "r"(p5), "r"(p6), "r"(p7)
                  : "memory");
   }
@@ -403,22 +426,45 @@ __device__ __forceinline__ uint32_t low_mask(int k) {  // k low bits set, k in [
   return r - 1u;
 }
 
-#ifndef ABG_FILTER_MINB
-#define ABG_FILTER_MINB 6
-#endif
-constexpr uint32_t kFilterGrab = 8;  // groups of 32 tuples a warp takes per work-counter atomic
+// One candidate per lane: record against payload -> lower bound of the distance -> survivor entry.
+__device__ __forceinline__ void filter_candidate(const FilterParams &F, const uint4 h, uint64_t rec, const uint32_t (&w)[8],
+                                                 const uint4 pa, const uint4 pb) {
+  const uint32_t meta = h.w;
+  const bool sentinel = (w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) == ~0u;
+  const uint32_t x = ((meta >> 30) & 1u) ? ~0u : 0u;
+  const uint32_t m0 = mismatch_bits(w[0] ^ x, w[1] ^ x, pa.x, pa.y), m1 = mismatch_bits(w[2] ^ x, w[3] ^ x, pa.z, pa.w);
+  const uint32_t m2 = mismatch_bits(w[4] ^ x, w[5] ^ x, pb.x, pb.y), m3 = mismatch_bits(w[6] ^ x, w[7] ^ x, pb.z, pb.w);
+  const int nb = (int)((meta >> 10) & 255u);  // compared bases of the record: 1..128
+  int lb;
+  if (nb >= 64)
+    lb = __popc(m0) + __popc(m1) + __popc(m2 & low_mask(min(nb - 64, 32))) + __popc(m3 & low_mask(max(nb - 96, 0)));
+  else
+    lb = __popc(m0 & low_mask(min(nb, 32))) + __popc(m1 & low_mask(max(nb - 32, 0)));
+  const int bound = (int)((meta >> 18) & 511u);
+  if (lb <= bound || sentinel) {
+    const uint32_t tab = tuple_table(meta);
+    const uint32_t off = meta & 1023u;
+    const uint32_t a = min((uint32_t)(kCtxArrays - 1), off >> 5);
+    const uint32_t entry = (uint32_t)(rec - (uint64_t)a * F.n_tab[tab]);
+    const uint32_t at = atomicAdd(F.surv_count + h.z, 1u);
+    if (at < F.surv_cap) F.surv[(size_t)h.z * F.surv_cap + at] = make_uint2(entry, off | ((meta >> 27) & 7u) << 10);
+  }
+}
 
-__global__ void __launch_bounds__(256, ABG_FILTER_MINB) filter_kernel(FilterParams F) {
+// PIPE: the record of the next 32 candidates is in flight while this round's is compared (the kernel waits on
+// the record gathers; a second gather per lane in flight costs 11 registers).
+template <bool PIPE>
+__global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams F) {
   __shared__ uint4 s_hdr[8][32];
   __shared__ uint32_t s_excl[8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = *F.n_binned;
   for (;;) {
     uint32_t g0 = 0;
-    if (lane == 0) g0 = atomicAdd(F.work, 32u * kFilterGrab);
+    if (lane == 0) g0 = atomicAdd(F.work, F.grab);
     g0 = __shfl_sync(FULL, g0, 0);
     if (g0 >= n) break;
-    const uint32_t g1 = min(n, g0 + 32u * kFilterGrab);
+    const uint32_t g1 = min(n, g0 + F.grab);
     for (uint32_t w0 = g0; w0 < g1; w0 += 32) {
       uint4 raw = make_uint4(0u, 0u, 0u, 0u);
       if (w0 + (uint32_t)lane < n) raw = __ldcs(reinterpret_cast<const uint4 *>(F.tup_b) + w0 + lane);
@@ -430,40 +476,53 @@ __global__ void __launch_bounds__(256, ABG_FILTER_MINB) filter_kernel(FilterPara
       s_hdr[wid][lane] = raw;
       s_excl[wid][lane] = excl;
       __syncwarp();
-      for (uint32_t c0 = 0; c0 < total; c0 += 32) {
-        // owner tuple of candidate c0 + lane: tuples that end at or before c0, plus the tuples that start inside
-        // (c0, c0 + lane] (every binned tuple has at least one candidate)
+      // owner tuple of candidate c0 + lane: tuples that end at or before c0, plus the tuples that start inside
+      // (c0, c0 + lane] (every binned tuple has at least one candidate); -> the candidate's record, or false
+      auto locate = [&](uint32_t c0, uint32_t &o, uint64_t &rec) -> bool {
         const uint32_t st = excl - c0;
         const uint32_t heads = __reduce_or_sync(FULL, (tot != 0u && st - 1u < 31u) ? (1u << st) : 0u);
         const uint32_t first = (uint32_t)__popc(__ballot_sync(FULL, incl <= c0));
         const uint32_t cidx = c0 + (uint32_t)lane;
-        if (cidx >= total) continue;
-        const uint32_t o = (first + (uint32_t)__popc(heads & ((2u << lane) - 1u) & ~1u)) & 31u;
+        o = (first + (uint32_t)__popc(heads & ((2u << lane) - 1u) & ~1u)) & 31u;
+        if (cidx >= total) return false;
         const uint4 h = s_hdr[wid][o];
-        const uint32_t r = cidx - s_excl[wid][o];
-        const uint32_t meta = h.w;
-        const uint32_t tab = tuple_table(meta);
-        const uint64_t rec = ((uint64_t)h.x | ((uint64_t)(h.y & 255u) << 32)) + r;
-        uint32_t w[8];
-        load_ctx(F.ctx[tab] + 2 * rec, w);
-        const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
-        const bool sentinel = (w[0] & w[1] & w[2] & w[3] & w[4] & w[5] & w[6] & w[7]) == ~0u;
-        const uint32_t x = ((meta >> 30) & 1u) ? ~0u : 0u;
-        const uint32_t m0 = mismatch_bits(w[0] ^ x, w[1] ^ x, pa.x, pa.y), m1 = mismatch_bits(w[2] ^ x, w[3] ^ x, pa.z, pa.w);
-        const uint32_t m2 = mismatch_bits(w[4] ^ x, w[5] ^ x, pb.x, pb.y), m3 = mismatch_bits(w[6] ^ x, w[7] ^ x, pb.z, pb.w);
-        const int nb = (int)((meta >> 10) & 255u);  // compared bases of the record: 1..128
-        int lb;
-        if (nb >= 64)
-          lb = __popc(m0) + __popc(m1) + __popc(m2 & low_mask(min(nb - 64, 32))) + __popc(m3 & low_mask(max(nb - 96, 0)));
-        else
-          lb = __popc(m0 & low_mask(min(nb, 32))) + __popc(m1 & low_mask(max(nb - 32, 0)));
-        const int bound = (int)((meta >> 18) & 511u);
-        if (lb <= bound || sentinel) {
-          const uint32_t off = meta & 1023u;
-          const uint32_t a = min((uint32_t)(kCtxArrays - 1), off >> 5);
-          const uint32_t entry = (uint32_t)(rec - (uint64_t)a * F.n_tab[tab]);
-          const uint32_t at = atomicAdd(F.surv_count + h.z, 1u);
-          if (at < F.surv_cap) F.surv[(size_t)h.z * F.surv_cap + at] = make_uint2(entry, off | ((meta >> 27) & 7u) << 10);
+        rec = ((uint64_t)h.x | ((uint64_t)(h.y & 255u) << 32)) + (cidx - s_excl[wid][o]);
+        return true;
+      };
+      if (!PIPE) {
+        for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+          uint32_t o;
+          uint64_t rec = 0;
+          if (!locate(c0, o, rec)) continue;
+          const uint4 h = s_hdr[wid][o];
+          uint32_t w[8];
+          load_ctx(F.ctx[tuple_table(h.w)] + 2 * rec, w);
+          const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
+          filter_candidate(F, h, rec, w, pa, pb);
+        }
+      }
+      else {
+        uint32_t o = 0, w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        uint64_t rec = 0;
+        bool ok = total != 0u && locate(0u, o, rec);
+        if (ok) load_ctx(F.ctx[tuple_table(s_hdr[wid][o].w)] + 2 * rec, w);
+        for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+          uint32_t o_n = 0, w_n[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          uint64_t rec_n = 0;
+          bool ok_n = false;
+          if (c0 + 32u < total) {  // (warp-uniform)
+            ok_n = locate(c0 + 32u, o_n, rec_n);
+            if (ok_n) load_ctx(F.ctx[tuple_table(s_hdr[wid][o_n].w)] + 2 * rec_n, w_n);
+          }
+          if (ok) {
+            const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
+            filter_candidate(F, s_hdr[wid][o], rec, w, pa, pb);
+          }
+          ok = ok_n;
+          o = o_n;
+          rec = rec_n;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) w[q] = w_n[q];
         }
       }
     }
@@ -510,9 +569,9 @@ __device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand
   // matches everything, positions past it nothing
   uint32_t lo = 0, hi = 0;
   if ((uint32_t)lane < B.pw) {
-    const uint32_t *pl = B.planes + (size_t)sid * 2u * B.pw;
-    lo = __ldcg(pl + lane);
-    hi = __ldcg(pl + B.pw + lane);
+    const uint2 v = __ldcg(reinterpret_cast<const uint2 *>(B.planes) + (size_t)sid * B.pw + lane);
+    lo = v.x;
+    hi = v.y;
   }
   __syncwarp();
   if ((uint32_t)lane < W.L.mask_words) {
@@ -526,31 +585,27 @@ __device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand
     W.masks(3)[lane] = isT | tail;
   }
   if (lane == 0) S->packed_key = ~0u;  // the masks no longer belong to what build_packed last built
-  // ---- canonical order (offset, two-letter before three-letter, entry): rank of every key; perm[rank] = slot
-  uint64_t *keys = reinterpret_cast<uint64_t *>(W.log_pos());  // [kSurvSlots] (the survivor log's region)
-  uint8_t *perm = reinterpret_cast<uint8_t *>(W.stage());       // [kSurvSlots] (the staging region of replay_hits)
+  // ---- deep compare of every survivor (pure: any order).  Only the few that a phase could still accept go on:
+  // the specific phase starts from cutoff = good_cutoff, the sensitive phase from the heap's top, and within a
+  // phase cutoffs only tighten (CandSet::update), so pm above both can never be accepted -- on a random genome
+  // that is everything but the read's true locus (seen once per indexed offset).
+  const CandState *st0 = W.cs(set_id);
+  const int c_spec = st0->good_cutoff;
+  // (within the specific phase the heap's top can rise to good_cutoff when it starts below it: a full SE heap
+  // pops its top for a worse hit that is still <= cutoff)
+  const int c_sens = max(heap_of(W, set_id).get(0).diffs(), c_spec);
+  uint64_t *acc_key = reinterpret_cast<uint64_t *>(W.log_pos());  // [32] canonical-order keys of the kept ones
+  uint64_t *acc_res = acc_key + 32;                                // [32] {pos, d | pm << 16 | spec << 30 | sens << 31}
+  uint64_t *sorted = acc_res + 32;                                 // [32] acc_res in canonical order
+  int n_acc = 0;
   __syncwarp();
-  for (int k = lane; k < n; k += 32) {
-    const uint2 e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
-    const uint64_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
-    keys[k] = (off << 36) | (is3 << 35) | ((uint64_t)e.x << 3) | fl;  // unique per candidate: fl never decides
-  }
-  __syncwarp();
-  for (int k = lane; k < n; k += 32) {
-    const uint64_t mine = keys[k];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += keys[j] < mine;
-    perm[rank] = (uint8_t)k;
-  }
-  __syncwarp();
-  // ---- deep compare of every survivor (pure: any order); the result takes the place of its key
-  uint32_t *res = reinterpret_cast<uint32_t *>(keys);  // slot k: {pos, d | pm << 16 | spec << 30 | sens << 31}
   for (int k0 = 0; k0 < n; k0 += 32) {
     const int k = k0 + lane;
     const bool valid = k < n;
-    const uint64_t key = valid ? keys[k] : 0ull;
-    const uint32_t entry = (uint32_t)(key >> 3), is3 = (uint32_t)(key >> 35) & 1u, off = (uint32_t)(key >> 36) & 1023u;
-    Deep1 r = compare_deep_one(index3, n_words, bound, valid, entry, off | (is3 << 31), true);
+    uint2 e = make_uint2(0u, 0u);
+    if (valid) e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
+    const uint32_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
+    Deep1 r = compare_deep_one(index3, n_words, bound, valid, e.x, off | (is3 << 31), true);
     const bool deferred = valid && r.pm == kDeferredExact;
     if (__any_sync(FULL, deferred)) {  // a window with N / IUPAC codes: the exact compare needs the packed read
       ensure_encoded(W, end, strand_code, seq);
@@ -560,30 +615,46 @@ __device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand
         r.pm = mx;
       }
     }
-    __syncwarp();
-    if (valid) {
-      res[2 * k] = r.pos;
-      res[2 * k + 1] = (uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)max(0, min(r.pm, 0x3fff)) << 16) | ((uint32_t)(key & 3u) << 30);
+    const bool keep = valid && (((fl & 1u) != 0u && r.pm <= c_spec) || ((fl & 2u) != 0u && r.pm <= c_sens));
+    const unsigned km = __ballot_sync(FULL, keep);
+    const int at = n_acc + __popc(km & ((1u << lane) - 1u));
+    if (keep && at < 32) {
+      // unique per candidate (fl never decides): offset, two-letter before three-letter, bucket order
+      acc_key[at] = ((uint64_t)off << 36) | ((uint64_t)is3 << 35) | ((uint64_t)e.x << 3) | fl;
+      acc_res[at] = (uint64_t)r.pos | ((uint64_t)((uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)max(0, min(r.pm, 0x3fff)) << 16) | (fl << 30)) << 32);
     }
+    n_acc += __popc(km);
+  }
+  if (n_acc > 32) {  // many acceptable candidates (repeats): the strand is seeded directly
+    ensure_encoded(W, end, strand_code, seq);
+    process_seeds(set_id, end, strand_code);
+    return;
   }
   __syncwarp();
-  if (lane == 0) {  // one lane mutates the set (see replay_hits)
+  if (lane < n_acc) {
+    const uint64_t mine = acc_key[lane];
+    int rank = 0;
+    for (int j = 0; j < n_acc; ++j) rank += acc_key[j] < mine;
+    sorted[rank] = acc_res[lane];
+  }
+  __syncwarp();
+  if (lane == 0) {  // one lane mutates the set (see replay_hits); the phases move the cutoff even without updates
     CandSet cs;
     cs.load(W, set_id);
     cs.set_specific();
-    for (int q = 0; q < n && !cs.sure_ambig; ++q) {
-      const int k = perm[q];
-      const uint32_t m = res[2 * k + 1];
+    for (int q = 0; q < n_acc && !cs.sure_ambig; ++q) {
+      const uint64_t v = sorted[q];
+      const uint32_t m = (uint32_t)(v >> 32);
       if (((m >> 30) & 1u) == 0u) continue;  // bit 30: examined by the specific phase (tuple bit 28)
-      if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res[2 * k]);
+      if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, (uint32_t)v);
     }
     if (cs.should_do_sensitive()) {
       cs.set_sensitive();
-      for (int q = 0; q < n && !cs.sure_ambig; ++q) {
-        const int k = perm[q];
-        const uint32_t m = res[2 * k + 1];
+      for (int q = 0; q < n_acc && !cs.sure_ambig; ++q) {
+        const uint64_t v = sorted[q];
+        const uint32_t m = (uint32_t)(v >> 32);
         if (((m >> 31) & 1u) == 0u) continue;  // bit 31: examined by the sensitive phase (tuple bit 29)
-        if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res[2 * k]);
+        if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, (uint32_t)v);
       }
     }
     cs.store_one_lane(W, set_id);
