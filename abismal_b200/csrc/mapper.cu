@@ -117,7 +117,7 @@ constexpr uint32_t kOvfPerItem = 256;  // overflow arena entries per pair of max
 // traceback allocations per read / pair (in tasks of the first class); beyond these the alignment runs in the warp
 constexpr uint32_t kTaskCapPe[3] = {40, 32, 8}, kTaskCapSe[3] = {24, 8, 8};  // 2 GB per 2^20 pairs
 constexpr uint32_t kTbTasksPe = 4, kTbTasksSe = 2;
-constexpr int kScatterCtasPerSm = 2;  // count_kernel / scatter_kernel: CTAs per SM (the scatter is bound by memory latency)
+constexpr int kScatterCtasPerSmMax = 2;  // count_kernel / scatter_kernel: at most this many CTAs per SM
 
 struct abg_mapper {
   abg_index *idx = nullptr;
@@ -171,9 +171,8 @@ struct abg_mapper {
   const void *kernel_h = nullptr;
   int grid_h = 0, grid_sc = 0, grid_f = 0;
   bool filter_pipe = false;  // filter_kernel<true>: two record gathers per lane in flight
-  uint32_t filter_grab = 64;  // tuples per work-cursor atomic: the live window of the record array stays near one bin
+  uint32_t filter_grab = 256;  // tuples per work-cursor atomic (measured at 2^20 pairs: 32 -> 44 ms, 64 -> 30 ms, 128 -> 21 ms, 256 -> 20 ms)
   ab2dev::SeedTuple *d_tup = nullptr, *d_tup_b = nullptr;
-  uint4 *d_pay_b = nullptr;
   uint32_t *d_planes = nullptr, *d_bin_hist = nullptr, *d_surv_count = nullptr;
   uint8_t *d_strand_flag = nullptr;
   uint2 *d_surv = nullptr;
@@ -360,7 +359,6 @@ ab2dev::FilterParams filter_params(const abg_mapper *m) {
   F.bin_hist = m->d_bin_hist;
   F.n_binned = m->d_bin_work + 1;
   F.tup_b = m->d_tup_b;
-  F.pay_b = m->d_pay_b;
   F.ctx[0] = ix.ctx;
   F.ctx[1] = ix.ctx_t;
   F.ctx[2] = ix.ctx_a;
@@ -1020,8 +1018,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       while ((total_rec >> shift) + 1 > ab2dev::kMaxBins) ++shift;
       m->bin_shift = shift;
       m->n_bins = (uint32_t)(total_rec >> shift) + 1u;
-      if (const char *eg = std::getenv("ABISMAL_B200_FILTER_GRAB"))  // tuning: 32 .. 4096 tuples
-        if (std::atoi(eg) >= 32 && std::atoi(eg) <= 4096) m->filter_grab = (uint32_t)std::atoi(eg) / 32u * 32u;
+      if (const char *eg = std::getenv("ABISMAL_B200_FILTER_GRAB"))  // tuning: 32 .. 4096 tuples, 0 = static distribution
+        if (std::atoi(eg) == 0 || (std::atoi(eg) >= 32 && std::atoi(eg) <= 4096)) m->filter_grab = (uint32_t)std::atoi(eg) / 32u * 32u;
       m->surv_cap = ab2dev::kSurvSlots;
       if (const char *ec = std::getenv("ABISMAL_B200_SURV_CAP"))  // testing aid: fewer listed survivors per strand
         if (std::atol(ec) > 0) m->surv_cap = std::min<uint32_t>(ab2dev::kSurvSlots, (uint32_t)std::atol(ec));
@@ -1044,19 +1042,17 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       };
       grab((void **)&m->d_tup, cap * sizeof(ab2dev::SeedTuple));
       grab((void **)&m->d_tup_b, cap * sizeof(ab2dev::SeedTuple));
-      grab((void **)&m->d_pay_b, cap * 32);
       grab((void **)&m->d_planes, n_strands * 2 * m->pw * 4);
       grab((void **)&m->d_strand_flag, n_strands);
-      grab((void **)&m->d_bin_hist, (size_t)m->n_bins * n_sm * kScatterCtasPerSm * 4);
+      grab((void **)&m->d_bin_hist, (size_t)m->n_bins * n_sm * kScatterCtasPerSmMax * 4);
       grab((void **)&m->d_surv_count, n_strands * 4);
       grab((void **)&m->d_surv, n_strands * m->surv_cap * sizeof(uint2));
       grab((void **)&m->d_bin_work, 4 * sizeof(unsigned int));
       if (!ok) {
-        for (void *q : {(void *)m->d_tup, (void *)m->d_tup_b, (void *)m->d_pay_b, (void *)m->d_planes, (void *)m->d_strand_flag,
+        for (void *q : {(void *)m->d_tup, (void *)m->d_tup_b, (void *)m->d_planes, (void *)m->d_strand_flag,
                         (void *)m->d_bin_hist, (void *)m->d_surv_count, (void *)m->d_surv, (void *)m->d_bin_work})
           cudaFree(q);
         m->d_tup = m->d_tup_b = nullptr;
-        m->d_pay_b = nullptr;
         m->d_planes = m->d_bin_hist = m->d_surv_count = nullptr;
         m->d_strand_flag = nullptr;
         m->d_surv = nullptr;
@@ -1065,7 +1061,11 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       }
       else {
         m->grid_h = n_sm * per_h;
-        m->grid_sc = n_sm * kScatterCtasPerSm;  // 1024-thread CTAs; every CTA has its own write range in every bin
+        // 1024-thread CTAs; every CTA has its own write range in every bin, and the scatter slows down with the
+        // number of open ranges (measured: 2 CTAs per SM 32 ms, 1 CTA per SM 27 ms with the payloads still written here)
+        m->grid_sc = n_sm;
+        if (const char *ec = std::getenv("ABISMAL_B200_SCATTER_CTAS"))
+          if (std::atoi(ec) >= 1 && std::atoi(ec) <= kScatterCtasPerSmMax) m->grid_sc = n_sm * std::atoi(ec);
         m->grid_f = n_sm * per_f;
         for (int k = 0; k < 3; ++k) ABG_M(cudaEventCreate(&m->ev_b[k]));
         ABG_M(cudaEventCreateWithFlags(&m->ev_bins, cudaEventDisableTiming));
@@ -1192,7 +1192,6 @@ void abg_mapper_destroy(abg_mapper *m) {
   cudaFree(m->d_counters);
   cudaFree(m->d_tup);
   cudaFree(m->d_tup_b);
-  cudaFree(m->d_pay_b);
   cudaFree(m->d_planes);
   cudaFree(m->d_strand_flag);
   cudaFree(m->d_bin_hist);

@@ -137,23 +137,9 @@ __device__ __noinline__ EmitResult emit_strand(TupleAlloc al, int end, uint32_t 
   const uint32_t bound = (uint32_t)invalid_hit_diffs(readlen);
   const uint32_t meta_strand = (bound << 18) | (g_to_a ? (1u << 30) : 0u);
   bool bad = false;
-  // the probes of the next 32 offsets are requested into L1 while this round's are consumed (the compact counter
-  // blocks and the bitmaps live in L2: the round trip is the kernel's longest stall)
-  auto prefetch_probes = [&](uint32_t i) {
-    if (i >= n_off) return;
-    const uint32_t k = __brev(plane_window(p2, i)) >> 7;
-    if (ix.cc != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ix.cc + 2 * (size_t)(k / kCcKeys)));
-    if (bits3 != nullptr) {
-      const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
-      const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(bits3 + (k3 >> 5)));
-    }
-  };
-  prefetch_probes((uint32_t)lane);
   for (uint32_t base_off = 0; base_off < n_off; base_off += 32) {
     const uint32_t i = base_off + (uint32_t)lane;
     const bool active = i < n_off;
-    prefetch_probes(i + 32u);
     const bool in_spec = i < specific_lim, in_sens = i < lim_two;
     SeedTuple t2, t3;
     bool has2 = false, has3 = false;
@@ -299,7 +285,6 @@ struct FilterParams {
   uint32_t *bin_hist;      // in: tuples per bin; bin_prefix_kernel turns it into the bins' write cursors
   uint32_t *n_binned;      // out of bin_prefix_kernel: tuples in all bins
   SeedTuple *tup_b;        // binned tuples
-  uint4 *pay_b;            // their payloads: 2 x uint4 per tuple = {lo, hi} planes of four 32-base chunks
   const uint4 *ctx[3];     // record arrays of the three tables
   uint64_t n_tab[3];       // entries per table (records of array a start at a * n_tab)
   uint32_t *surv_count;
@@ -378,8 +363,9 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(FilterParam
   __syncthreads();
   uint64_t i0, i1;
   cta_range(F, i0, i1);
-  // the kernel is bound by memory latency (tuple -> planes of its strand -> two scattered stores): the next tuple
-  // is in flight while this one is handled, and two CTAs of 1024 threads share an SM
+  // tuples only: their payloads (the 128 read bases a tuple's records are compared with) are built by the filter
+  // kernel from the strand's planes, so the scatter writes 16 bytes per tuple and its write frontier (one open
+  // line per bin and CTA) stays in L2.  The next tuple is in flight while this one is placed.
   const uint4 *src = reinterpret_cast<const uint4 *>(F.tup);
   uint64_t i = i0 + threadIdx.x;
   uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
@@ -388,29 +374,9 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(FilterParam
     const uint4 raw = nxt;
     if (i + blockDim.x < i1) nxt = __ldcs(src + i + blockDim.x);
     if ((raw.y >> 8) == 0u) continue;
-    const uint32_t meta = raw.w;
-    const uint64_t g = F.rec_base[tuple_table(meta)] + ((uint64_t)raw.x | ((uint64_t)(raw.y & 255u) << 32));
-    // the 128 read bases from q0 = offset - 32 a (a = min(offset / 32, 3)), as four {lo, hi} plane words
-    const uint32_t off = meta & 1023u;
-    const uint32_t q0 = off - 32u * min((uint32_t)(kCtxArrays - 1), off >> 5);
-    const uint32_t sh = q0 & 31u;
-    const uint2 *pl = reinterpret_cast<const uint2 *>(F.planes) + (size_t)raw.z * F.pw + (q0 >> 5);
-    uint2 v[5];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) v[c] = __ldg(pl + c);
+    const uint64_t g = F.rec_base[tuple_table(raw.w)] + ((uint64_t)raw.x | ((uint64_t)(raw.y & 255u) << 32));
     const uint32_t at = atomicAdd(s_bins + (uint32_t)(g >> F.bin_shift), 1u);
-    __stcs(reinterpret_cast<uint4 *>(F.tup_b) + at, raw);
-    // g_to_a strands are stored complemented (A<->T, C<->G in the 2-bit code): "read A also matches genome G"
-    // becomes "read T also matches genome C", the rule of the other strands, once the record is complemented too
-    const uint32_t x = ((meta >> 30) & 1u) ? ~0u : 0u;
-    const uint32_t p0 = __funnelshift_r(v[0].x, v[1].x, sh) ^ x, p1 = __funnelshift_r(v[0].y, v[1].y, sh) ^ x;
-    const uint32_t p2 = __funnelshift_r(v[1].x, v[2].x, sh) ^ x, p3 = __funnelshift_r(v[1].y, v[2].y, sh) ^ x;
-    const uint32_t p4 = __funnelshift_r(v[2].x, v[3].x, sh) ^ x, p5 = __funnelshift_r(v[2].y, v[3].y, sh) ^ x;
-    const uint32_t p6 = __funnelshift_r(v[3].x, v[4].x, sh) ^ x, p7 = __funnelshift_r(v[3].y, v[4].y, sh) ^ x;
-    // one 32-byte store = one sector operation (the scatter is bound by the rate of scattered sector writes)
-    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(F.pay_b + 2 * (size_t)at), "r"(p0), "r"(p1), "r"(p2),
-                 "r"(p3), "r"(p4), "r"(p5), "r"(p6), "r"(p7)
-                 : "memory");
+    reinterpret_cast<uint4 *>(F.tup_b)[at] = raw;
   }
 }
 
@@ -456,15 +422,28 @@ __device__ __forceinline__ void filter_candidate(const FilterParams &F, const ui
 template <bool PIPE>
 __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams F) {
   __shared__ uint4 s_hdr[8][32];
+  __shared__ uint4 s_pay[8][32][2];  // per tuple: {lo, hi} plane words of the 128 read bases its records are compared with
   __shared__ uint32_t s_excl[8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = *F.n_binned;
-  for (;;) {
-    uint32_t g0 = 0;
-    if (lane == 0) g0 = atomicAdd(F.work, F.grab);
-    g0 = __shfl_sync(FULL, g0, 0);
-    if (g0 >= n) break;
-    const uint32_t g1 = min(n, g0 + F.grab);
+  // Work distribution.  grab != 0: a warp takes `grab` tuples at a time from a global cursor.  grab == 0: static,
+  // warp w of the grid takes the groups of 32 tuples w, w + W, w + 2 W, ...: no atomics, and the grid's live
+  // window of the tuple array (hence of the record array: tuples are in bin order) is as narrow as it gets.
+  const uint32_t n_warps = gridDim.x * 8u, warp_id = blockIdx.x * 8u + (uint32_t)wid;
+  for (uint64_t round = 0;; ++round) {
+    uint32_t g0 = 0, g1;
+    if (F.grab != 0u) {
+      if (lane == 0) g0 = atomicAdd(F.work, F.grab);
+      g0 = __shfl_sync(FULL, g0, 0);
+      if (g0 >= n) break;
+      g1 = min(n, g0 + F.grab);
+    }
+    else {
+      const uint64_t at = (round * n_warps + warp_id) * 32u;
+      if (at >= n) break;
+      g0 = (uint32_t)at;
+      g1 = min(n, g0 + 32u);
+    }
     for (uint32_t w0 = g0; w0 < g1; w0 += 32) {
       uint4 raw = make_uint4(0u, 0u, 0u, 0u);
       if (w0 + (uint32_t)lane < n) raw = __ldcs(reinterpret_cast<const uint4 *>(F.tup_b) + w0 + lane);
@@ -475,6 +454,23 @@ __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams 
       __syncwarp();
       s_hdr[wid][lane] = raw;
       s_excl[wid][lane] = excl;
+      if (tot != 0u) {
+        // the 128 read bases from q0 = offset - 32 a (a = min(offset / 32, 3)): five {lo, hi} words of the strand's
+        // planes, shifted.  g_to_a strands are compared complemented (A<->T, C<->G in the 2-bit code): "read A
+        // also matches genome G" becomes "read T also matches genome C", the rule of the other strands.
+        const uint32_t off = raw.w & 1023u;
+        const uint32_t q0 = off - 32u * min((uint32_t)(kCtxArrays - 1), off >> 5);
+        const uint32_t sh = q0 & 31u;
+        const uint2 *pl = reinterpret_cast<const uint2 *>(F.planes) + (size_t)raw.z * F.pw + (q0 >> 5);
+        uint2 v[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) v[c] = __ldg(pl + c);
+        const uint32_t x = ((raw.w >> 30) & 1u) ? ~0u : 0u;
+        s_pay[wid][lane][0] = make_uint4(__funnelshift_r(v[0].x, v[1].x, sh) ^ x, __funnelshift_r(v[0].y, v[1].y, sh) ^ x,
+                                         __funnelshift_r(v[1].x, v[2].x, sh) ^ x, __funnelshift_r(v[1].y, v[2].y, sh) ^ x);
+        s_pay[wid][lane][1] = make_uint4(__funnelshift_r(v[2].x, v[3].x, sh) ^ x, __funnelshift_r(v[2].y, v[3].y, sh) ^ x,
+                                         __funnelshift_r(v[3].x, v[4].x, sh) ^ x, __funnelshift_r(v[3].y, v[4].y, sh) ^ x);
+      }
       __syncwarp();
       // owner tuple of candidate c0 + lane: tuples that end at or before c0, plus the tuples that start inside
       // (c0, c0 + lane] (every binned tuple has at least one candidate); -> the candidate's record, or false
@@ -497,8 +493,7 @@ __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams 
           const uint4 h = s_hdr[wid][o];
           uint32_t w[8];
           load_ctx(F.ctx[tuple_table(h.w)] + 2 * rec, w);
-          const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
-          filter_candidate(F, h, rec, w, pa, pb);
+          filter_candidate(F, h, rec, w, s_pay[wid][o][0], s_pay[wid][o][1]);
         }
       }
       else {
@@ -515,8 +510,7 @@ __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams 
             if (ok_n) load_ctx(F.ctx[tuple_table(s_hdr[wid][o_n].w)] + 2 * rec_n, w_n);
           }
           if (ok) {
-            const uint4 pa = __ldg(F.pay_b + 2 * (size_t)(w0 + o)), pb = __ldg(F.pay_b + 2 * (size_t)(w0 + o) + 1);
-            filter_candidate(F, s_hdr[wid][o], rec, w, pa, pb);
+            filter_candidate(F, s_hdr[wid][o], rec, w, s_pay[wid][o][0], s_pay[wid][o][1]);
           }
           ok = ok_n;
           o = o_n;
