@@ -370,10 +370,14 @@ class Mapper:
         return bool(self.lib.abg_mapper_binned(self._h))
 
     def bin_stats(self):
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 8)()
         self._check(self.lib.abg_mapper_bin_stats(self._h, out))
-        keys = ("strands", "strands_direct", "tuples", "survivors", "bins", "tuple_cap")
-        return dict(zip(keys, [int(x) for x in out]))
+        keys = ("strands", "strands_direct", "tuples", "survivors", "bins", "tuple_cap", "variants", "filter_grab")
+        d = dict(zip(keys, [int(x) for x in out]))
+        v = d.pop("variants")
+        d["scatter"] = "tile-sorted" if v & 1 else "direct"
+        d["filter"] = ("pipelined, " if v & 2 else "") + ("static distribution" if d["filter_grab"] == 0 else "work cursor")
+        return d
 
     def last_run_stats(self):
         """Diagnostics of the last run(): redo pairs, set-arena use, tasks per band class (abg_mapper_last_run_stats)."""

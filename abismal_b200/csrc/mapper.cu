@@ -13,6 +13,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 
 #include "abismal_b200.h"
@@ -78,12 +80,63 @@ int make_bitmap(const uint32_t *d_counter, uint64_t n_buckets, uint32_t **out) {
   return ABG_OK;
 }
 
+// Host -> device copy of a large array that is usually a read-only file mapping (pageable, not yet touched):
+// several threads copy 16 MB pieces into their own page-locked slots and send them on their own streams, so
+// the page faults, the host copies and the DMA of different pieces overlap.  (One cudaMemcpy of the 2.7 GB
+// index of a 3.1 Gbp genome is bound by a single thread's page faults and staging copy.)
+int copy_to_device(void *dst, const void *src, size_t bytes) {
+  constexpr size_t kPiece = 16u << 20;
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  (void)cudaGetLastError();
+  const unsigned hw = std::thread::hardware_concurrency();
+  const unsigned n_thr = std::min<unsigned>(8u, std::max(1u, hw / 2u));
+  if (pinned || bytes < 4 * kPiece || n_thr < 2) {
+    ABG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return ABG_OK;
+  }
+  int device = 0;
+  ABG_CUDA(cudaGetDevice(&device));
+  const size_t n_pieces = (bytes + kPiece - 1) / kPiece;
+  std::atomic<int> err{0};
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < n_thr; ++t)
+    th.emplace_back([&, t] {
+      void *slot = nullptr;
+      cudaStream_t st = nullptr;
+      if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost(&slot, kPiece) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+        err = 1;
+      }
+      else {
+        for (size_t c = t; c < n_pieces && !err; c += n_thr) {
+          const size_t o = c * kPiece, len = std::min(kPiece, bytes - o);
+          if (cudaStreamSynchronize(st) != cudaSuccess) err = 1;  // the slot's previous piece has left
+          std::memcpy(slot, static_cast<const char *>(src) + o, len);
+          if (cudaMemcpyAsync(static_cast<char *>(dst) + o, slot, len, cudaMemcpyHostToDevice, st) != cudaSuccess) err = 1;
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) err = 1;
+      }
+      if (st) cudaStreamDestroy(st);
+      if (slot) cudaFreeHost(slot);
+    });
+  for (std::thread &x : th) x.join();
+  if (err) {
+    (void)cudaGetLastError();
+    ABG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));  // plain copy; reports its own error if any
+  }
+  return ABG_OK;
+}
+
 template <class T>
 int upload(const T *host, uint64_t n, uint64_t n_alloc, T **dev) {
   *dev = nullptr;
   ABG_CUDA(cudaMalloc(reinterpret_cast<void **>(dev), std::max<uint64_t>(n_alloc, 1) * sizeof(T)));
   if (n_alloc > n) ABG_CUDA(cudaMemset(*dev + n, 0, (n_alloc - n) * sizeof(T)));
-  if (n) ABG_CUDA(cudaMemcpy(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  if (n) {
+    int rc = copy_to_device(*dev, host, n * sizeof(T));
+    if (rc != ABG_OK) return rc;
+  }
   return ABG_OK;
 }
 
@@ -117,6 +170,7 @@ constexpr uint32_t kOvfPerItem = 256;  // overflow arena entries per pair of max
 // traceback allocations per read / pair (in tasks of the first class); beyond these the alignment runs in the warp
 constexpr uint32_t kTaskCapPe[3] = {40, 32, 8}, kTaskCapSe[3] = {24, 8, 8};  // 2 GB per 2^20 pairs
 constexpr uint32_t kTbTasksPe = 4, kTbTasksSe = 2;
+constexpr uint32_t kMaxFilterCursors = 64, kBinWorkWords = 2 + kMaxFilterCursors;
 constexpr int kScatterCtasPerSmMax = 2;  // count_kernel / scatter_kernel: at most this many CTAs per SM
 
 struct abg_mapper {
@@ -170,13 +224,16 @@ struct abg_mapper {
   uint32_t spi = 1, bin_shift = 0, n_bins = 0, tup_cap = 0, pw = 0, surv_cap = 0;
   const void *kernel_h = nullptr;
   int grid_h = 0, grid_sc = 0, grid_f = 0;
+  bool scatter_sorted = true;  // scatter_sorted_kernel: tuples leave in runs per bin (shared-memory tile sort); measured 7.4 vs 12.6 ms
+  uint32_t filter_cursors = 1;  // interleaved work cursors of the filter
+  uint32_t filter_cache = 1;  // bit 0 planes loaded evict-first (measured 24.2 vs 25.3 ms), bit 1 records loaded with the L2 evict-last hint (no gain)
   bool filter_pipe = false;  // filter_kernel<true>: two record gathers per lane in flight
   uint32_t filter_grab = 256;  // tuples per work-cursor atomic (measured at 2^20 pairs: 32 -> 44 ms, 64 -> 30 ms, 128 -> 21 ms, 256 -> 20 ms)
   ab2dev::SeedTuple *d_tup = nullptr, *d_tup_b = nullptr;
   uint32_t *d_planes = nullptr, *d_bin_hist = nullptr, *d_surv_count = nullptr;
   uint8_t *d_strand_flag = nullptr;
   uint2 *d_surv = nullptr;
-  unsigned int *d_bin_work = nullptr;  // [0] tuple slots handed out, [1] tuples binned, [2] filter_kernel's work cursor
+  unsigned int *d_bin_work = nullptr;  // [0] tuple slots handed out, [1] tuples binned, [2 ..] filter_kernel's work cursors (kBinWorkWords in all)
   cudaEvent_t ev_b[3] = {nullptr, nullptr, nullptr};  // abg_mapper_run: after hash_kernel, scatter_kernel, filter_kernel
   cudaEvent_t ev_bins = nullptr;                      // abg_map_batch: the batch's tuples are filtered
   float bin_ms[3] = {0.f, 0.f, 0.f};
@@ -369,12 +426,14 @@ ab2dev::FilterParams filter_params(const abg_mapper *m) {
   F.surv_cap = m->surv_cap;
   F.work = m->d_bin_work + 2;
   F.grab = m->filter_grab;
+  F.cache = m->filter_cache;
+  F.n_cursors = m->filter_cursors;
   return F;
 }
 
 // clears the batch-wide state of the binned kernels (n = reads / pairs of the whole batch)
 int reset_bins(const abg_mapper *m, uint32_t n, cudaStream_t st) {
-  ABG_CUDA(cudaMemsetAsync(m->d_bin_work, 0, 4 * sizeof(unsigned int), st));
+  ABG_CUDA(cudaMemsetAsync(m->d_bin_work, 0, kBinWorkWords * sizeof(unsigned int), st));
   ABG_CUDA(cudaMemsetAsync(m->d_surv_count, 0, (size_t)n * m->spi * 4, st));
   return ABG_OK;
 }
@@ -399,10 +458,12 @@ int launch_bins(const abg_mapper *m, cudaStream_t st, const cudaEvent_t *ev_b = 
   const size_t sm = (size_t)m->n_bins * 4;
   ab2dev::count_kernel<<<m->grid_sc, ab2dev::kScatterThreads, sm, st>>>(F);
   ab2dev::bin_prefix_kernel<<<1, 1024, 0, st>>>(F, (uint32_t)m->grid_sc);
-  ab2dev::scatter_kernel<<<m->grid_sc, ab2dev::kScatterThreads, sm, st>>>(F);
+  if (m->scatter_sorted) ab2dev::scatter_sorted_kernel<<<m->grid_sc, ab2dev::kScatterThreads, ab2dev::sort_scatter_smem(m->n_bins), st>>>(F);
+  else ab2dev::scatter_kernel<<<m->grid_sc, ab2dev::kScatterThreads, sm, st>>>(F);
   if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[1], st));
-  if (m->filter_pipe) ab2dev::filter_kernel<true><<<m->grid_f, 256, 0, st>>>(F);
-  else ab2dev::filter_kernel<false><<<m->grid_f, 256, 0, st>>>(F);
+  if (m->filter_pipe) ab2dev::filter_kernel<true, false><<<m->grid_f, 256, 0, st>>>(F);
+  else if (m->filter_cache & 2u) ab2dev::filter_kernel<false, true><<<m->grid_f, 256, 0, st>>>(F);
+  else ab2dev::filter_kernel<false, false><<<m->grid_f, 256, 0, st>>>(F);
   if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[2], st));
   ABG_CUDA(cudaGetLastError());
   return ABG_OK;
@@ -996,12 +1057,15 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       // strand gathers its own records, the round-1 seeding)
       const char *e = std::getenv("ABISMAL_B200_BINS");
       const bool have_ctx = ix->ctx != nullptr && (ix->dev.n_ctx3 == 0 || (ix->ctx_t != nullptr && ix->ctx_a != nullptr));
-      m->use_bins = !(e && std::atoi(e) == 0) && !m->overlap && have_ctx && m->ml / 32u + 5u <= 32u;  // a plane of the read fits one word per lane
+      m->use_bins = !(e && std::atoi(e) == 0) && !m->overlap && have_ctx && m->ml / 32u + 5u <= 32u;  // (pw <= 32)  // a plane of the read fits one word per lane
     }
     if (m->use_bins) {
       const bool rp = (p->mode & ABG_MODE_RANDOM_PBAT) != 0;
       m->spi = m->paired ? (rp ? 8u : 4u) : (rp ? 4u : 2u);
-      m->pw = m->ml / 32u + 5u;
+      // {lo, hi} words per strand: the whole read (replay's match masks) and the five words from q0 / 32 that a
+      // tuple's 128 compared bases span (q0 = offset - 96 for offsets >= 128, offset <= length - 25); 40 bytes
+      // per strand for 150-base reads -- the filter gathers them at random, the smaller the array the better
+      m->pw = std::max(m->ml / 32u, (max_read_len > 152u ? ((max_read_len - 121u) >> 5) : 0u) + 5u);
       const uint64_t n_strands = (uint64_t)max_batch * m->spi;
       const char *ef = std::getenv("ABISMAL_B200_TUPLE_FACTOR");
       const double factor = (ef && std::atof(ef) > 0.0) ? std::atof(ef) : 1.25;
@@ -1014,7 +1078,7 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       m->tup_cap = (uint32_t)cap;
       const uint64_t total_rec = (uint64_t)ab2dev::kCtxArrays * (ix->dev.n_ctx + 2 * ix->dev.n_ctx3);
       const char *es = std::getenv("ABISMAL_B200_BIN_SHIFT");
-      uint32_t shift = (es && std::atoi(es) >= 10 && std::atoi(es) <= 30) ? (uint32_t)std::atoi(es) : 19u;  // 16 MB of records
+      uint32_t shift = (es && std::atoi(es) >= 10 && std::atoi(es) <= 30) ? (uint32_t)std::atoi(es) : 20u;  // 32 MB of records per bin (the filter does not care between 16 and 32 MB, the scatter prefers fewer bins: 5.7 vs 7.4 ms)
       while ((total_rec >> shift) + 1 > ab2dev::kMaxBins) ++shift;
       m->bin_shift = shift;
       m->n_bins = (uint32_t)(total_rec >> shift) + 1u;
@@ -1030,8 +1094,11 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       int per_h = 0, per_f = 0;
       ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_h, m->kernel_h, ab2dev::kThreadsPerBlock, m->smem_s));
       if (const char *ep = std::getenv("ABISMAL_B200_FILTER_PIPE")) m->filter_pipe = std::atoi(ep) != 0;
-      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, m->filter_pipe ? (const void *)ab2dev::filter_kernel<true>
-                                                                                   : (const void *)ab2dev::filter_kernel<false>, 256, 0));
+      if (const char *ek = std::getenv("ABISMAL_B200_FILTER_CURSORS"))
+        if (std::atoi(ek) >= 1 && std::atoi(ek) <= (int)kMaxFilterCursors) m->filter_cursors = (uint32_t)std::atoi(ek);
+      if (const char *ec2 = std::getenv("ABISMAL_B200_FILTER_CACHE")) m->filter_cache = (uint32_t)std::atoi(ec2) & 3u;
+      ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, m->filter_pipe ? (const void *)ab2dev::filter_kernel<true, false>
+                                                                                   : (const void *)ab2dev::filter_kernel<false, false>, 256, 0));
       // any allocation that fails switches the binned path off (the direct path needs none of this memory)
       bool ok = per_h >= 1 && per_f >= 1;
       auto grab = [&](void **ptr, size_t bytes) {
@@ -1047,7 +1114,7 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       grab((void **)&m->d_bin_hist, (size_t)m->n_bins * n_sm * kScatterCtasPerSmMax * 4);
       grab((void **)&m->d_surv_count, n_strands * 4);
       grab((void **)&m->d_surv, n_strands * m->surv_cap * sizeof(uint2));
-      grab((void **)&m->d_bin_work, 4 * sizeof(unsigned int));
+      grab((void **)&m->d_bin_work, kBinWorkWords * sizeof(unsigned int));
       if (!ok) {
         for (void *q : {(void *)m->d_tup, (void *)m->d_tup_b, (void *)m->d_planes, (void *)m->d_strand_flag,
                         (void *)m->d_bin_hist, (void *)m->d_surv_count, (void *)m->d_surv, (void *)m->d_bin_work})
@@ -1064,8 +1131,18 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
         // 1024-thread CTAs; every CTA has its own write range in every bin, and the scatter slows down with the
         // number of open ranges (measured: 2 CTAs per SM 32 ms, 1 CTA per SM 27 ms with the payloads still written here)
         m->grid_sc = n_sm;
+        if (const char *es2 = std::getenv("ABISMAL_B200_SCATTER_SORT")) m->scatter_sorted = std::atoi(es2) != 0;
+        if (m->scatter_sorted) {
+          const size_t need = ab2dev::sort_scatter_smem(m->n_bins);
+          if (m->n_bins > ab2dev::kSortMaxBins ||
+              cudaFuncSetAttribute((const void *)ab2dev::scatter_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess) {
+            (void)cudaGetLastError();
+            m->scatter_sorted = false;
+          }
+        }
         if (const char *ec = std::getenv("ABISMAL_B200_SCATTER_CTAS"))
           if (std::atoi(ec) >= 1 && std::atoi(ec) <= kScatterCtasPerSmMax) m->grid_sc = n_sm * std::atoi(ec);
+        if (m->scatter_sorted) m->grid_sc = n_sm;
         m->grid_f = n_sm * per_f;
         for (int k = 0; k < 3; ++k) ABG_M(cudaEventCreate(&m->ev_b[k]));
         ABG_M(cudaEventCreateWithFlags(&m->ev_bins, cudaEventDisableTiming));
@@ -1502,9 +1579,9 @@ uint32_t abg_mapper_launches_per_run(const abg_mapper *m) {
   return (m && m->cur_n) ? (m->split ? (m->overlap ? 4u : (m->use_tasks ? 5u : 3u)) + (m->use_bins ? 4u : 0u) : 1u) : 0u;
 }
 int abg_mapper_binned(const abg_mapper *m) { return (m && m->use_bins) ? 1 : 0; }
-int abg_mapper_bin_stats(abg_mapper *m, uint64_t out[6]) {
+int abg_mapper_bin_stats(abg_mapper *m, uint64_t out[8]) {
   if (!m || !out) return fail(ABG_ERR_INVALID, "abg_mapper_bin_stats: null argument");
-  for (int k = 0; k < 6; ++k) out[k] = 0;
+  for (int k = 0; k < 8; ++k) out[k] = 0;
   if (!m->use_bins) return ABG_OK;
   ABG_CUDA(cudaSetDevice(m->idx->device));
   ABG_CUDA(cudaDeviceSynchronize());
@@ -1529,6 +1606,8 @@ int abg_mapper_bin_stats(abg_mapper *m, uint64_t out[6]) {
   out[3] = surv;        // prefilter survivors of the listed strands
   out[4] = m->n_bins;
   out[5] = m->tup_cap;
+  out[6] = (m->scatter_sorted ? 1u : 0u) | (m->filter_pipe ? 2u : 0u);
+  out[7] = m->filter_grab;
   return ABG_OK;
 }
 uint32_t abg_mapper_chunk(const abg_mapper *m) { return m ? m->chunk : 0u; }

@@ -147,9 +147,15 @@ __device__ __noinline__ EmitResult emit_strand(TupleAlloc al, int end, uint32_t 
       const uint32_t k = __brev(plane_window(p2, i)) >> 7;
       const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
       const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
-      uint32_t s2, e2, s3, e3;
+      // the bitmap word of the three-letter bucket is requested before the two-letter probe is decoded (both
+      // come from L2; the kernel's longest stalls are these round trips)
+      const uint32_t bw3 = bits3 != nullptr ? __ldg(bits3 + (k3 >> 5)) : ~0u;
+      uint32_t s2, e2, s3 = 0, e3 = 0;
       probe_two(ix, k, s2, e2);
-      probe(counter3, bits3, k3, s3, e3);
+      if ((bw3 >> (k3 & 31u)) & 1u) {
+        s3 = __ldg(counter3 + k3);
+        e3 = __ldg(counter3 + k3 + 1);
+      }
       const uint32_t d_two = e2 - s2, d_three = e3 - s3;
       // the sensitive phase's bucket rule (abismal.cpp:1351-1370), on the raw bucket sizes
       const bool el2 = d_two != 0u && d_two <= maxc && (d_three == 0u || d_two <= 10u * d_three);
@@ -292,6 +298,8 @@ struct FilterParams {
   uint32_t surv_cap;
   unsigned int *work;      // filter_kernel's work cursor
   uint32_t grab;           // tuples a filter warp takes per work-cursor atomic (a multiple of 32)
+  uint32_t n_cursors;      // interleaved work cursors of the filter (F.work[0 .. n_cursors))
+  uint32_t cache;          // tuning: bit 0 planes loaded evict-first, bit 1 records loaded with the L2 evict-last hint
 };
 
 // Binning without global atomics: CTA c of count_kernel and of scatter_kernel owns the same contiguous range of
@@ -380,6 +388,92 @@ __global__ void __launch_bounds__(kScatterThreads, 2) scatter_kernel(FilterParam
   }
 }
 
+// The same scatter through a shared-memory tile: the CTA sorts kSortTile tuples by bin in shared memory (counting
+// sort: shared-memory atomics give the rank, one block scan the offsets) and writes them out in bin order, so
+// the tuples of one bin leave as one run of consecutive addresses (~7 tuples = 107 bytes per bin and tile at
+// 1227 bins) instead of one 16-byte store per tuple into 1227 open lines.  Same (bin, CTA) write ranges as
+// scatter_kernel.  Shared memory: the tile + three words per bin (n_bins <= kSortMaxBins).
+constexpr uint32_t kSortPerThread = 8, kSortTile = kSortPerThread * kScatterThreads, kSortMaxBins = 2048;
+__host__ __device__ __forceinline__ size_t sort_scatter_smem(uint32_t n_bins) { return (size_t)kSortTile * 16u + 3u * (size_t)n_bins * 4u + 32u * 4u; }
+
+__global__ void __launch_bounds__(kScatterThreads, 1) scatter_sorted_kernel(FilterParams F) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  uint4 *tile = reinterpret_cast<uint4 *>(s_raw);
+  uint32_t *cursor = reinterpret_cast<uint32_t *>(s_raw + (size_t)kSortTile * 16u);
+  uint32_t *hist = cursor + F.n_bins, *off = hist + F.n_bins, *wsum = off + F.n_bins;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  for (uint32_t b = tid; b < F.n_bins; b += blockDim.x) {
+    cursor[b] = F.bin_hist[(size_t)b * gridDim.x + blockIdx.x];
+    hist[b] = 0u;
+  }
+  __syncthreads();
+  uint64_t i0, i1;
+  cta_range(F, i0, i1);
+  const uint4 *src = reinterpret_cast<const uint4 *>(F.tup);
+  const uint32_t per = (F.n_bins + kScatterThreads - 1u) / kScatterThreads;  // bins per thread in the scan
+  for (uint64_t base = i0; base < i1; base += kSortTile) {
+    uint4 raw[kSortPerThread];
+    uint32_t bin[kSortPerThread], rk[kSortPerThread];
+#pragma unroll
+    for (uint32_t k = 0; k < kSortPerThread; ++k) {
+      const uint64_t i = base + (uint64_t)k * kScatterThreads + tid;
+      raw[k] = i < i1 ? __ldcs(src + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < kSortPerThread; ++k) {
+      bin[k] = ~0u;
+      rk[k] = 0u;
+      if ((raw[k].y >> 8) != 0u) {
+        const uint64_t g = F.rec_base[tuple_table(raw[k].w)] + ((uint64_t)raw[k].x | ((uint64_t)(raw[k].y & 255u) << 32));
+        bin[k] = (uint32_t)(g >> F.bin_shift);
+        rk[k] = atomicAdd(hist + bin[k], 1u);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of hist -> off
+    uint32_t sum = 0;
+    for (uint32_t q = 0; q < per; ++q) {
+      const uint32_t b = tid * per + q;
+      sum += b < F.n_bins ? hist[b] : 0u;
+    }
+    const uint32_t incl = warp_incl_scan_add(sum, (int)lane);
+    if (lane == 31u) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0u) {
+      const uint32_t v = wsum[lane];
+      const uint32_t iv = warp_incl_scan_add(v, (int)lane);
+      wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t acc = wsum[wid] + incl - sum;
+    for (uint32_t q = 0; q < per; ++q) {
+      const uint32_t b = tid * per + q;
+      if (b < F.n_bins) {
+        off[b] = acc;
+        acc += hist[b];
+      }
+    }
+    __syncthreads();
+    const uint32_t total = off[F.n_bins - 1u] + hist[F.n_bins - 1u];
+#pragma unroll
+    for (uint32_t k = 0; k < kSortPerThread; ++k)
+      if (bin[k] != ~0u) tile[off[bin[k]] + rk[k]] = raw[k];
+    __syncthreads();
+    for (uint32_t j = tid; j < total; j += kScatterThreads) {
+      const uint4 t = tile[j];
+      const uint64_t g = F.rec_base[tuple_table(t.w)] + ((uint64_t)t.x | ((uint64_t)(t.y & 255u) << 32));
+      const uint32_t b = (uint32_t)(g >> F.bin_shift);
+      reinterpret_cast<uint4 *>(F.tup_b)[cursor[b] + (j - off[b])] = t;
+    }
+    __syncthreads();
+    for (uint32_t b = tid; b < F.n_bins; b += blockDim.x) {
+      cursor[b] += hist[b];
+      hist[b] = 0u;
+    }
+    __syncthreads();
+  }
+}
+
 // mismatch bits of 32 bases: genome planes (glo, ghi) against read planes (rlo, rhi), both complemented for
 // g_to_a strands, so that the one conversion rule left is "read T (11) also matches genome C (01)"
 __device__ __forceinline__ uint32_t mismatch_bits(uint32_t glo, uint32_t ghi, uint32_t rlo, uint32_t rhi) {
@@ -390,6 +484,14 @@ __device__ __forceinline__ uint32_t low_mask(int k) {  // k low bits set, k in [
   uint32_t r;
   asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(k));  // shifts of 32 and more give 0
   return r - 1u;
+}
+
+// a record with the L2 evict-last hint (the records of a bin are what the filter wants to keep in L2)
+__device__ __forceinline__ void load_ctx_keep(const uint4 *p, uint32_t (&w)[8], uint64_t policy) {
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p), "l"(policy));
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p + 1), "l"(policy));
 }
 
 // One candidate per lane: record against payload -> lower bound of the distance -> survivor entry.
@@ -419,13 +521,16 @@ __device__ __forceinline__ void filter_candidate(const FilterParams &F, const ui
 
 // PIPE: the record of the next 32 candidates is in flight while this round's is compared (the kernel waits on
 // the record gathers; a second gather per lane in flight costs 11 registers).
-template <bool PIPE>
+// KEEP: the records are loaded with the L2 evict-last hint (tuning).
+template <bool PIPE, bool KEEP>
 __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams F) {
   __shared__ uint4 s_hdr[8][32];
   __shared__ uint4 s_pay[8][32][2];  // per tuple: {lo, hi} plane words of the 128 read bases its records are compared with
   __shared__ uint32_t s_excl[8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = *F.n_binned;
+  uint64_t keep_policy = 0;
+  if (KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
   // Work distribution.  grab != 0: a warp takes `grab` tuples at a time from a global cursor.  grab == 0: static,
   // warp w of the grid takes the groups of 32 tuples w, w + W, w + 2 W, ...: no atomics, and the grid's live
   // window of the tuple array (hence of the record array: tuples are in bin order) is as narrow as it gets.
@@ -433,10 +538,17 @@ __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams 
   for (uint64_t round = 0;; ++round) {
     uint32_t g0 = 0, g1;
     if (F.grab != 0u) {
-      if (lane == 0) g0 = atomicAdd(F.work, F.grab);
-      g0 = __shfl_sync(FULL, g0, 0);
-      if (g0 >= n) break;
-      g1 = min(n, g0 + F.grab);
+      // n_cursors interleaved work cursors (cursor c hands out the pieces c, c + C, c + 2 C, ... of `grab` tuples):
+      // the atomics of the grid spread over C addresses, so pieces can be small -- a narrow live window of the
+      // record array -- without the one-address atomic rate becoming the limit
+      const uint32_t c = warp_id % F.n_cursors;
+      uint32_t k = 0;
+      if (lane == 0) k = atomicAdd(F.work + c, 1u);
+      k = __shfl_sync(FULL, k, 0);
+      const uint64_t at = ((uint64_t)k * F.n_cursors + c) * F.grab;
+      if (at >= n) break;
+      g0 = (uint32_t)at;
+      g1 = (uint32_t)min((uint64_t)n, at + F.grab);
     }
     else {
       const uint64_t at = (round * n_warps + warp_id) * 32u;
@@ -463,8 +575,14 @@ __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams 
         const uint32_t sh = q0 & 31u;
         const uint2 *pl = reinterpret_cast<const uint2 *>(F.planes) + (size_t)raw.z * F.pw + (q0 >> 5);
         uint2 v[5];
+        if (F.cache & 1u) {
 #pragma unroll
-        for (int c = 0; c < 5; ++c) v[c] = __ldg(pl + c);
+          for (int c = 0; c < 5; ++c) v[c] = __ldcs(pl + c);
+        }
+        else {
+#pragma unroll
+          for (int c = 0; c < 5; ++c) v[c] = __ldg(pl + c);
+        }
         const uint32_t x = ((raw.w >> 30) & 1u) ? ~0u : 0u;
         s_pay[wid][lane][0] = make_uint4(__funnelshift_r(v[0].x, v[1].x, sh) ^ x, __funnelshift_r(v[0].y, v[1].y, sh) ^ x,
                                          __funnelshift_r(v[1].x, v[2].x, sh) ^ x, __funnelshift_r(v[1].y, v[2].y, sh) ^ x);
@@ -492,7 +610,8 @@ __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams 
           if (!locate(c0, o, rec)) continue;
           const uint4 h = s_hdr[wid][o];
           uint32_t w[8];
-          load_ctx(F.ctx[tuple_table(h.w)] + 2 * rec, w);
+          if (KEEP) load_ctx_keep(F.ctx[tuple_table(h.w)] + 2 * rec, w, keep_policy);
+          else load_ctx(F.ctx[tuple_table(h.w)] + 2 * rec, w);
           filter_candidate(F, h, rec, w, s_pay[wid][o][0], s_pay[wid][o][1]);
         }
       }

@@ -195,8 +195,9 @@ void abg_mapper_last_seed_times(const abg_mapper *m, float out[4]);
 int abg_mapper_binned(const abg_mapper *m);
 /* Diagnostics of the last batch (binned seeding): out[0] strands, out[1] strands that took the direct path
  * (reads with N, survivor or tuple overflow), out[2] tuples binned, out[3] prefilter survivors, out[4] bins,
- * out[5] tuple capacity. */
-int abg_mapper_bin_stats(abg_mapper *m, uint64_t out[6]);
+ * out[5] tuple capacity, out[6] kernel variants in use (bit 0 tile-sorted scatter, bit 1 pipelined filter),
+ * out[7] tuples a filter warp takes per work-cursor step (0 = static distribution). */
+int abg_mapper_bin_stats(abg_mapper *m, uint64_t out[8]);
 uint32_t abg_mapper_launches_per_run(const abg_mapper *m);
 int abg_mapper_get_counters(const abg_mapper *m, abg_work_counters *out);
 /* Diagnostics of the most recent abg_mapper_run (after abg_mapper_sync): out[0] pairs left to the redo kernel,

@@ -144,6 +144,45 @@ def test_binned_seeding_overflow_paths(workspace, rep_index, gpu, monkeypatch):
         m.close()
 
 
+BIN_VARIANTS = [
+    ("many_bins", {"ABISMAL_B200_BIN_SHIFT": "11"}),                      # hundreds of bins on the test genome
+    ("direct_scatter", {"ABISMAL_B200_SCATTER_SORT": "0", "ABISMAL_B200_BIN_SHIFT": "11"}),
+    ("static_filter", {"ABISMAL_B200_FILTER_GRAB": "0", "ABISMAL_B200_BIN_SHIFT": "12"}),
+    ("small_grab_two_ctas", {"ABISMAL_B200_FILTER_GRAB": "32", "ABISMAL_B200_SCATTER_SORT": "0", "ABISMAL_B200_SCATTER_CTAS": "2",
+                             "ABISMAL_B200_BIN_SHIFT": "13"}),
+    ("interleaved_cursors", {"ABISMAL_B200_FILTER_GRAB": "32", "ABISMAL_B200_FILTER_CURSORS": "16", "ABISMAL_B200_BIN_SHIFT": "12"}),
+    ("pipelined_filter", {"ABISMAL_B200_FILTER_PIPE": "1", "ABISMAL_B200_BIN_SHIFT": "12"}),
+    ("cache_hints", {"ABISMAL_B200_FILTER_CACHE": "3", "ABISMAL_B200_BIN_SHIFT": "12"}),
+]
+
+
+@pytest.mark.parametrize("variant,env", BIN_VARIANTS, ids=[v[0] for v in BIN_VARIANTS])
+@pytest.mark.parametrize("tag,mode,kw,files", [c for c in RECORD_CASES if c[0] in ("se_rpbat", "pe_pbat")], ids=["se_rpbat", "pe_pbat"])
+def test_binned_seeding_kernel_variants(workspace, rep_index, gpu, monkeypatch, tag, mode, kw, files, variant, env):
+    """The tuning switches of the binned kernels (bin size, tile-sorted scatter, static / small-grab filter work
+    distribution, pipelined filter) change the order in which tuples and survivors are produced, never the
+    records.  The small bin sizes give the test genome hundreds of bins (the default puts it in a handful)."""
+    from abismal_b200 import Mapper
+    ixf, ix, kind = rep_index
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    b = [_fq(workspace, f, kind=kind) for f in files]
+    m = Mapper(ix, mode=mode, max_batch=b[0].n, max_read_len=max([x.max_len for x in b] + [64]), **kw)
+    for k in env:
+        monkeypatch.delenv(k)
+    assert m.binned
+    st = m.bin_stats()
+    o = helpers.OracleMapper(ixf, mode=mode, **kw)
+    helpers.assert_results_equal(m.map_batch(*b), o.map_batch(*b), bool(mode & 1))
+    st = m.bin_stats()
+    assert st["bins"] >= 32, st
+    assert (st["scatter"] == "tile-sorted") == (env.get("ABISMAL_B200_SCATTER_SORT", "1") == "1"), st
+    assert st["filter"].startswith("pipelined") == ("ABISMAL_B200_FILTER_PIPE" in env), st
+    assert (st["filter_grab"] == 0) == (env.get("ABISMAL_B200_FILTER_GRAB") == "0"), st
+    o.close()
+    m.close()
+
+
 @pytest.mark.parametrize("tag,mode,kw,files", [c for c in RECORD_CASES if c[0] in ("se", "pe", "pe_rpbat_ambig")],
                          ids=["se", "pe", "pe_rpbat_ambig"])
 def test_records_equal_oracle_with_alignments_in_the_warp(workspace, rep_index, gpu, monkeypatch, tag, mode, kw, files):
