@@ -98,8 +98,7 @@ void IndexFile::read(const std::string &path, bool map_file) {
     struct stat st;
     if (at < 0 || fstat(fileno(in), &st) != 0) throw std::runtime_error(error_msg);
     const size_t len = static_cast<size_t>(st.st_size);
-    // (not pre-faulted: abg_index_create touches the pages from several threads while it copies them to the device)
-    void *base = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fileno(in), 0);
+    void *base = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fileno(in), 0);
     if (base == MAP_FAILED) throw std::runtime_error(error_msg);
     map_base_ = base;
     map_len_ = len;

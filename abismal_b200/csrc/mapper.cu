@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <atomic>
 #include <vector>
@@ -82,15 +83,16 @@ int make_bitmap(const uint32_t *d_counter, uint64_t n_buckets, uint32_t **out) {
 
 // Host -> device copy of a large array that is usually a read-only file mapping (pageable, not yet touched):
 // several threads copy 16 MB pieces into their own page-locked slots and send them on their own streams, so
-// the page faults, the host copies and the DMA of different pieces overlap.  (One cudaMemcpy of the 2.7 GB
-// index of a 3.1 Gbp genome is bound by a single thread's page faults and staging copy.)
+// the page faults, the host copies and the DMA of different pieces overlap.
 int copy_to_device(void *dst, const void *src, size_t bytes) {
   constexpr size_t kPiece = 16u << 20;
   cudaPointerAttributes at;
   const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
   (void)cudaGetLastError();
-  const unsigned hw = std::thread::hardware_concurrency();
-  const unsigned n_thr = std::min<unsigned>(8u, std::max(1u, hw / 2u));
+  // Off by default: measured next to the front end's reader threads on a 16-core box it was slower than the
+  // single cudaMemcpy (1.8-2.3 s against 1.5 s for 2.7 GB).  ABISMAL_B200_UPLOAD_THREADS=N turns it on.
+  unsigned n_thr = 1;
+  if (const char *e = std::getenv("ABISMAL_B200_UPLOAD_THREADS")) n_thr = (unsigned)std::max(1, std::min(16, std::atoi(e)));
   if (pinned || bytes < 4 * kPiece || n_thr < 2) {
     ABG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
     return ABG_OK;
@@ -684,6 +686,18 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
   if (!ix) return fail(ABG_ERR_INVALID, "out of host memory");
   ix->device = device;
   int rc;
+  // ABISMAL_B200_VERBOSE=1: where the load time goes (stderr)
+  const bool verbose = std::getenv("ABISMAL_B200_VERBOSE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!verbose) return;
+    (void)cudaDeviceSynchronize();
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[abg_index_create] %s: %.3f s\n", what, std::chrono::duration<double>(t - t_last).count());
+    t_last = t;
+  };
+  (void)cudaFree(nullptr);
+  lap("context");
   // two spare zero words: the compare's look-ahead word and 16-byte loads
   if ((rc = upload(v->genome, v->genome_words, v->genome_words + 4, &ix->genome)) ||
       (rc = upload(v->counter, v->counter_size + 1, v->counter_size + 1, &ix->counter)) ||
@@ -695,6 +709,7 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
     abg_index_destroy(ix);
     return rc;
   }
+  lap("arrays of the index file to HBM");
   if ((rc = make_bitmap(ix->counter, v->counter_size, &ix->bits)) ||
       (rc = make_bitmap(ix->counter_t, v->counter_size_three, &ix->bits_t)) ||
       (rc = make_bitmap(ix->counter_a, v->counter_size_three, &ix->bits_a))) {
@@ -824,6 +839,7 @@ int abg_index_create(const abg_index_view *v, int device, abg_index **out) {
   ix->dev.index_a = ix->index_a;
   ix->dev.max_candidates = v->max_candidates;
   ix->dev.window_size = v->window_size ? v->window_size : 20u;
+  lap("derived arrays (bitmaps, 2-bit genome, seed-context records, compact counters)");
   *out = ix;
   return ABG_OK;
 }
@@ -983,9 +999,12 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
                 : minb_s == 5 ? (const void *)ab2dev::seed_kernel<5>
                 : minb_s == 6 ? (const void *)ab2dev::seed_kernel<6>
                               : (const void *)ab2dev::seed_kernel<4>;
-    m->kernel_a = m->minb == 2 ? (const void *)ab2dev::align_kernel<2>
-                : m->minb == 4 ? (const void *)ab2dev::align_kernel<4>
-                               : (const void *)ab2dev::align_kernel<3>;
+    int minb_a = m->minb;
+    if (const char *e = std::getenv("ABISMAL_B200_MINB_ALIGN"))  // tuning: the selection kernel's own register bound
+      if (std::atoi(e) >= 2 && std::atoi(e) <= 4) minb_a = std::atoi(e);
+    m->kernel_a = minb_a == 2 ? (const void *)ab2dev::align_kernel<2>
+                : minb_a == 4 ? (const void *)ab2dev::align_kernel<4>
+                              : (const void *)ab2dev::align_kernel<3>;
     int per_s = 0, per_a = 0;
     // one shared-memory carve-out for every kernel of the path: CTAs of kernels that ask for different
     // carve-outs cannot share an SM (the overlapped launch co-schedules seed_kernel and align_kernel)
@@ -1036,9 +1055,12 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       m->use_tasks = !(e && std::atoi(e) == 0) && !m->overlap && m->ml <= ab2dev::kDpMaxMl;
     }
     if (m->use_tasks) {
-      m->kernel_e = m->minb == 2 ? (const void *)ab2dev::enum_kernel<2>
-                  : m->minb == 4 ? (const void *)ab2dev::enum_kernel<4>
-                                 : (const void *)ab2dev::enum_kernel<3>;
+      int minb_e = m->minb;
+      if (const char *ee = std::getenv("ABISMAL_B200_MINB_ENUM"))  // tuning: enum_kernel's own register bound
+        if (std::atoi(ee) >= 2 && std::atoi(ee) <= 4) minb_e = std::atoi(ee);
+      m->kernel_e = minb_e == 2 ? (const void *)ab2dev::enum_kernel<2>
+                  : minb_e == 4 ? (const void *)ab2dev::enum_kernel<4>
+                                : (const void *)ab2dev::enum_kernel<3>;
       m->smem_d = ab2dev::dp_block_smem_bytes(m->ml);
       int per_e = 0, per_d = 0;
       for (const void *k : {m->kernel_e, (const void *)ab2dev::dp_kernel})

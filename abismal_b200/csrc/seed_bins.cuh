@@ -130,6 +130,7 @@ __device__ __noinline__ EmitResult emit_strand(TupleAlloc al, int end, uint32_t 
   const uint32_t *index3 = g_to_a ? ix.index_a : ix.index_t;
   const uint32_t *bits3 = g_to_a ? ix.bits_a : ix.bits_t;
   const uint32_t maxc = P.max_candidates;
+  const bool have3 = ix.n_ctx3 != 0;  // entries in the three-letter tables at all
   const uint32_t specific_len = min(readlen - P.window_size, readlen >> 1);
   const uint32_t specific_lim = max(P.window_size, readlen >> 1);
   const uint32_t lim_two = readlen - 25u + 1u;
@@ -145,11 +146,15 @@ __device__ __noinline__ EmitResult emit_strand(TupleAlloc al, int end, uint32_t 
     bool has2 = false, has3 = false;
     if (active) {
       const uint32_t k = __brev(plane_window(p2, i)) >> 7;
-      const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
-      const uint32_t k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
-      // the bitmap word of the three-letter bucket is requested before the two-letter probe is decoded (both
-      // come from L2; the kernel's longest stalls are these round trips)
-      const uint32_t bw3 = bits3 != nullptr ? __ldg(bits3 + (k3 >> 5)) : ~0u;
+      // (an index without three-letter entries -- random genomes -- has nothing to hash for)
+      uint32_t k3 = 0, bw3 = 0;
+      if (have3) {
+        const uint32_t x0 = plane_window(p3a, i) & 0xffffu, x1 = plane_window(p3b, i) & 0xffffu;
+        k3 = T3[x0 & 255u] + T3[256 + (x0 >> 8)] + 2u * (T3[x1 & 255u] + T3[256 + (x1 >> 8)]);
+        // the bitmap word of the three-letter bucket is requested before the two-letter probe is decoded (both
+        // come from L2; the kernel's longest stalls are these round trips)
+        bw3 = bits3 != nullptr ? __ldg(bits3 + (k3 >> 5)) : ~0u;
+      }
       uint32_t s2, e2, s3 = 0, e3 = 0;
       probe_two(ix, k, s2, e2);
       if ((bw3 >> (k3 & 31u)) & 1u) {
@@ -519,14 +524,14 @@ __device__ __forceinline__ void filter_candidate(const FilterParams &F, const ui
   }
 }
 
-// PIPE: the record of the next 32 candidates is in flight while this round's is compared (the kernel waits on
-// the record gathers; a second gather per lane in flight costs 11 registers).
-// KEEP: the records are loaded with the L2 evict-last hint (tuning).
+// PIPE: the records of the next 32 candidates travel to shared memory (cp.async, no registers) while this round's
+// are compared: the kernel waits on the record gathers, one dependent round trip per 32 candidates.
 template <bool PIPE, bool KEEP>
-__global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams F) {
+__global__ void __launch_bounds__(256, 6) filter_kernel(FilterParams F) {
   __shared__ uint4 s_hdr[8][32];
   __shared__ uint4 s_pay[8][32][2];  // per tuple: {lo, hi} plane words of the 128 read bases its records are compared with
   __shared__ uint32_t s_excl[8][32];
+  __shared__ uint4 s_ctx[PIPE ? 8 : 1][2][PIPE ? 32 : 1][2];  // PIPE: two stages of one record per lane
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t n = *F.n_binned;
   uint64_t keep_policy = 0;
@@ -616,27 +621,38 @@ __global__ void __launch_bounds__(256, PIPE ? 4 : 6) filter_kernel(FilterParams 
         }
       }
       else {
-        uint32_t o = 0, w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        auto fetch = [&](int stage, uint32_t o_, uint64_t rec_) {
+          const uint4 *src = F.ctx[tuple_table(s_hdr[wid][o_].w)] + 2 * rec_;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_ctx[wid][stage][lane][0]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 1) : "memory");
+        };
+        uint32_t o = 0;
         uint64_t rec = 0;
         bool ok = total != 0u && locate(0u, o, rec);
-        if (ok) load_ctx(F.ctx[tuple_table(s_hdr[wid][o].w)] + 2 * rec, w);
-        for (uint32_t c0 = 0; c0 < total; c0 += 32) {
-          uint32_t o_n = 0, w_n[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (ok) fetch(0, o, rec);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        int stage = 0;
+        for (uint32_t c0 = 0; c0 < total; c0 += 32, stage ^= 1) {
+          uint32_t o_n = 0;
           uint64_t rec_n = 0;
           bool ok_n = false;
           if (c0 + 32u < total) {  // (warp-uniform)
             ok_n = locate(c0 + 32u, o_n, rec_n);
-            if (ok_n) load_ctx(F.ctx[tuple_table(s_hdr[wid][o_n].w)] + 2 * rec_n, w_n);
+            if (ok_n) fetch(stage ^ 1, o_n, rec_n);
           }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 1;" ::: "memory");  // this round's record (committed one group earlier) has landed
           if (ok) {
+            const uint4 x = s_ctx[wid][stage][lane][0], y = s_ctx[wid][stage][lane][1];
+            const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
             filter_candidate(F, s_hdr[wid][o], rec, w, s_pay[wid][o][0], s_pay[wid][o][1]);
           }
           ok = ok_n;
           o = o_n;
           rec = rec_n;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) w[q] = w_n[q];
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
     }
   }

@@ -500,18 +500,25 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
                 # its launch time comes from CUDA events recorded on the launching stream between the kernels
                 ms_per_launch = phase_ms[0] / args.steps
                 achieved = seed_bytes * b[0].n / (ms_per_launch / 1e3) / 1e9
-                traffic, gather = None, None
+                traffic, gather, traffic_note = None, None, None
+                tj = None
                 try:
                     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                         tj = json.load(f)
-                    tj = tj.get(args.mode, tj if args.mode == "pbat" else None)
-                    want_kernel = "seeding" if m.binned else "seed_kernel"
-                    if tj is None or not tj.get("kernel", "").startswith(want_kernel):
-                        raise KeyError("traffic.json holds no capture of the seeding kernels for this mode")
-                    # ncu --set full capture of the same kernel on a smaller batch of the same reads, scaled to
-                    # this launch's batch (the kernel's work is linear in the number of pairs)
+                    # per mode: the ncu --set full capture of the seeding kernels that run (binned: four phases;
+                    # ABISMAL_B200_BINS=0: round 1's seed_kernel, kept under "round1_seed_kernel")
+                    tj = tj.get(args.mode) if m.binned else tj.get("round1_seed_kernel" if args.mode == "pbat" else None)
+                except Exception:
+                    tj = None
+                if tj is not None:
                     per = float(tj.get("units_per_pair", 1.0))
                     traffic = float(tj["dram_bytes_per_pair"]) * b[0].n / per
+                    traffic_note = "%s, %d %s in the capture%s" % (
+                        tj.get("source", "profiles/traffic.json"), int(tj["pairs_in_capture"]), unit,
+                        "" if int(tj["pairs_in_capture"]) == b[0].n // int(per) else " (scaled to this batch)")
+                if tj is not None and not m.binned and "l1_miss_sectors_per_pair" in tj:
+                    # one warp per strand: every examined candidate is a random sector, compared with the
+                    # random-gather ceiling of the microbenchmark
                     sect_s = float(tj["l1_miss_sectors_per_pair"]) * b[0].n / per / (ms_per_launch / 1e3) / 1e9
                     gather = {"achieved_gsectors_per_s": sect_s,
                               "ceiling_gsectors_per_s": float(tj["random_gather_ceiling_gsectors_per_s"]),
@@ -523,14 +530,13 @@ def run(args, sync, torch, dist, local_rank, world, use_dist):
                         gather["dram_gsectors_per_s"] = dsec
                         gather["bucket_contiguous_ceiling_gsectors_per_s"] = float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
                         gather["dram_frac_of_contiguous_ceiling"] = dsec / float(tj["bucket_contiguous_ceiling_gsectors_per_s"])
-                except Exception:
-                    pass
                 out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                                   "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                                   "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                                   "peak_source": peak_src,
                                    "algorithmic_bytes_per_%s" % unit[:-1]: seed_bytes,
                                    "algorithmic_bytes_per_%s_whole_path" % unit[:-1]: seed_bytes + dp_bytes,
                                    "whole_step_frac": (seed_bytes + dp_bytes) * b[0].n / (dev_ms / args.steps / 1e3) / 1e9 / peak,
-                                   "kernel": ("seeding = hash_kernel + scatter_kernel + filter_kernel + seed_kernel (one launch each "
+                                   "kernel": ("seeding = hash_kernel + count/prefix/scatter + filter_kernel + seed_kernel (one launch each "
                                               "per batch; the algorithmic bytes of process_seeds are spread over them)")
                                              if m.binned else "seed_kernel",
                                    "ms_per_launch": ms_per_launch, "kernels": out["kernels"],

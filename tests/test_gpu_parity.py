@@ -149,7 +149,7 @@ BIN_VARIANTS = [
     ("direct_scatter", {"ABISMAL_B200_SCATTER_SORT": "0", "ABISMAL_B200_BIN_SHIFT": "11"}),
     ("static_filter", {"ABISMAL_B200_FILTER_GRAB": "0", "ABISMAL_B200_BIN_SHIFT": "12"}),
     ("small_grab_two_ctas", {"ABISMAL_B200_FILTER_GRAB": "32", "ABISMAL_B200_SCATTER_SORT": "0", "ABISMAL_B200_SCATTER_CTAS": "2",
-                             "ABISMAL_B200_BIN_SHIFT": "13"}),
+                             "ABISMAL_B200_BIN_SHIFT": "12"}),
     ("interleaved_cursors", {"ABISMAL_B200_FILTER_GRAB": "32", "ABISMAL_B200_FILTER_CURSORS": "16", "ABISMAL_B200_BIN_SHIFT": "12"}),
     ("pipelined_filter", {"ABISMAL_B200_FILTER_PIPE": "1", "ABISMAL_B200_BIN_SHIFT": "12"}),
     ("cache_hints", {"ABISMAL_B200_FILTER_CACHE": "3", "ABISMAL_B200_BIN_SHIFT": "12"}),
