@@ -5,6 +5,7 @@
 #define ABISMAL_B200_INDEX_FILE_HPP
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -35,15 +36,15 @@ struct IndexFile {
   IndexFile &operator=(const IndexFile &) = delete;
   ~IndexFile();
 
-  // throws std::runtime_error with the reference's messages.  map_file: leave the arrays in a read-only
-  // mapping of the file instead of copying them into the vectors (they are only read once, by the upload
-  // to HBM); view() then points into the mapping.
+  // throws std::runtime_error with the reference's messages.  map_file: the arrays stay in one buffer filled
+  // by several threads (pread) instead of the vectors -- they are only read once, by the upload to HBM;
+  // view() then points into that buffer.
   void read(const std::string &path, bool map_file = false);
   abg_index_view view() const;
 
 private:
-  void *map_base_ = nullptr;
-  size_t map_len_ = 0;
+  std::unique_ptr<unsigned char[]> bulk_;
+  size_t bulk_len_ = 0;
   abg_index_view mapped_{};
 };
 

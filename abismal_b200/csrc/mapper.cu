@@ -223,7 +223,7 @@ struct abg_mapper {
   float task_ms[2] = {0.f, 0.f};
   // binned seeding (seed_bins.cuh): hash_kernel -> scatter_kernel -> filter_kernel in front of seed_kernel
   bool use_bins = false;
-  uint32_t spi = 1, bin_shift = 0, n_bins = 0, tup_cap = 0, pw = 0, surv_cap = 0;
+  uint32_t spi = 1, bin_shift = 0, n_bins = 0, tup_cap = 0, pw = 0, surv_cap = 0, acc_cap = 32;
   const void *kernel_h = nullptr;
   int grid_h = 0, grid_sc = 0, grid_f = 0;
   bool scatter_sorted = true;  // scatter_sorted_kernel: tuples leave in runs per bin (shared-memory tile sort); measured 7.4 vs 12.6 ms
@@ -342,6 +342,7 @@ void fill_params(const abg_mapper *m, ab2dev::KernelParams &P, uint32_t c0, uint
     B.surv_count = m->d_surv_count;
     B.surv = m->d_surv;
     B.surv_cap = m->surv_cap;
+    B.acc_cap = m->acc_cap;
     B.spi = m->spi;
     B.sid_base = c0 * m->spi;
   }
@@ -1107,6 +1108,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       if (const char *eg = std::getenv("ABISMAL_B200_FILTER_GRAB"))  // tuning: 32 .. 4096 tuples, 0 = static distribution
         if (std::atoi(eg) == 0 || (std::atoi(eg) >= 32 && std::atoi(eg) <= 4096)) m->filter_grab = (uint32_t)std::atoi(eg) / 32u * 32u;
       m->surv_cap = ab2dev::kSurvSlots;
+      if (const char *ea = std::getenv("ABISMAL_B200_ACC_CAP"))  // testing aid: 0 sends every strand through the general replay
+        if (std::atoi(ea) >= 0 && std::atoi(ea) <= 32) m->acc_cap = (uint32_t)std::atoi(ea);
       if (const char *ec = std::getenv("ABISMAL_B200_SURV_CAP"))  // testing aid: fewer listed survivors per strand
         if (std::atol(ec) > 0) m->surv_cap = std::min<uint32_t>(ab2dev::kSurvSlots, (uint32_t)std::atol(ec));
       m->kernel_h = (const void *)ab2dev::hash_kernel<4>;

@@ -136,6 +136,7 @@ struct BinParams {
   uint32_t *surv_count;       // [strand] prefilter survivors found (may exceed surv_cap: then the strand takes the direct path)
   uint2 *surv;                // [strand][surv_cap]: {entry number in its index table, offset | table << 10 | spec << 11 | sens << 12}
   uint32_t surv_cap;
+  uint32_t acc_cap;           // survivors a strand may keep for the short replay (<= 32); more: all are ranked and replayed
   uint32_t spi;               // strands per read / pair
   uint32_t sid_base;          // strand number of the first strand of this launch (sub-batches of one batch)
   uint32_t pad;

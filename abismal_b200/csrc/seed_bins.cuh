@@ -672,6 +672,78 @@ __device__ __forceinline__ void ensure_encoded(const Warp &W, int end, uint32_t 
   build_packed(end, strand_code);
 }
 
+// The general replay of a strand's n <= kSurvSlots listed survivors (the match masks are in place): all of them
+// are ranked into the canonical order (offset, two-letter before three-letter, entry), deep-compared, and
+// replayed by one lane.  process_binned takes this path when more than 32 survivors could still be accepted
+// (reads in repeats); otherwise it ranks and replays only those.
+__device__ __noinline__ void replay_all(int set_id, int end, uint32_t strand_code, uint32_t sid, const char *seq, int n,
+                                        int n_words, int bound, const uint32_t *index3) {
+  const Warp W;
+  const BinParams &B = params().bp;
+  const int lane = W.lane;
+  uint64_t *keys = reinterpret_cast<uint64_t *>(W.log_pos());  // [kSurvSlots] (the survivor log's region)
+  uint8_t *perm = reinterpret_cast<uint8_t *>(W.stage());       // [kSurvSlots] (the staging region of replay_hits)
+  __syncwarp();
+  for (int k = lane; k < n; k += 32) {
+    const uint2 e = __ldcg(B.surv + (size_t)sid * B.surv_cap + k);
+    const uint64_t off = e.y & 1023u, is3 = (e.y >> 10) & 1u, fl = (e.y >> 11) & 3u;
+    keys[k] = (off << 36) | (is3 << 35) | ((uint64_t)e.x << 3) | fl;  // unique per candidate: fl never decides
+  }
+  __syncwarp();
+  for (int k = lane; k < n; k += 32) {
+    const uint64_t mine = keys[k];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += keys[j] < mine;
+    perm[rank] = (uint8_t)k;
+  }
+  __syncwarp();
+  uint32_t *res = reinterpret_cast<uint32_t *>(keys);  // slot k: {pos, d | pm << 16 | spec << 30 | sens << 31}
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int k = k0 + lane;
+    const bool valid = k < n;
+    const uint64_t key = valid ? keys[k] : 0ull;
+    const uint32_t entry = (uint32_t)(key >> 3), is3 = (uint32_t)(key >> 35) & 1u, off = (uint32_t)(key >> 36) & 1023u;
+    Deep1 r = compare_deep_one(index3, n_words, bound, valid, entry, off | (is3 << 31), true);
+    const bool deferred = valid && r.pm == kDeferredExact;
+    if (__any_sync(FULL, deferred)) {  // a window with N / IUPAC codes: the exact compare needs the packed read
+      ensure_encoded(W, end, strand_code, seq);
+      if (deferred) {
+        int mx = 0;
+        r.d = exact_compare(r.pos, n_words, bound, &mx);
+        r.pm = mx;
+      }
+    }
+    __syncwarp();
+    if (valid) {
+      res[2 * k] = r.pos;
+      res[2 * k + 1] = (uint32_t)(uint16_t)(int16_t)r.d | ((uint32_t)max(0, min(r.pm, 0x3fff)) << 16) | ((uint32_t)(key & 3u) << 30);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {  // one lane mutates the set (see replay_hits)
+    CandSet cs;
+    cs.load(W, set_id);
+    cs.set_specific();
+    for (int q = 0; q < n && !cs.sure_ambig; ++q) {
+      const int k = perm[q];
+      const uint32_t m = res[2 * k + 1];
+      if (((m >> 30) & 1u) == 0u) continue;  // bit 30: examined by the specific phase (tuple bit 28)
+      if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res[2 * k]);
+    }
+    if (cs.should_do_sensitive()) {
+      cs.set_sensitive();
+      for (int q = 0; q < n && !cs.sure_ambig; ++q) {
+        const int k = perm[q];
+        const uint32_t m = res[2 * k + 1];
+        if (((m >> 31) & 1u) == 0u) continue;  // bit 31: examined by the sensitive phase (tuple bit 29)
+        if ((int)((m >> 16) & 0x3fffu) <= cs.cutoff) cs.update(true, (int)(int16_t)(m & 0xffffu), strand_code, res[2 * k]);
+      }
+    }
+    cs.store_one_lane(W, set_id);
+  }
+  __syncwarp();
+}
+
 // Equivalent of process_seeds(set_id, end, strand_code) for strand `sid` when its survivors were listed.  The
 // match masks of the deep compare come from the 2-bit planes hash_kernel stored (no N in the read here), so the
 // read is not loaded and encoded a second time.
@@ -754,9 +826,8 @@ __device__ __noinline__ void process_binned(int set_id, int end, uint32_t strand
     }
     n_acc += __popc(km);
   }
-  if (n_acc > 32) {  // many acceptable candidates (repeats): the strand is seeded directly
-    ensure_encoded(W, end, strand_code, seq);
-    process_seeds(set_id, end, strand_code);
+  if (n_acc > (int)B.acc_cap) {  // many acceptable candidates (repeats): every survivor is ranked and replayed
+    replay_all(set_id, end, strand_code, sid, seq, n, n_words, bound, index3);
     return;
   }
   __syncwarp();

@@ -153,6 +153,8 @@ BIN_VARIANTS = [
     ("interleaved_cursors", {"ABISMAL_B200_FILTER_GRAB": "32", "ABISMAL_B200_FILTER_CURSORS": "16", "ABISMAL_B200_BIN_SHIFT": "12"}),
     ("pipelined_filter", {"ABISMAL_B200_FILTER_PIPE": "1", "ABISMAL_B200_BIN_SHIFT": "12"}),
     ("cache_hints", {"ABISMAL_B200_FILTER_CACHE": "3", "ABISMAL_B200_BIN_SHIFT": "12"}),
+    ("general_replay", {"ABISMAL_B200_ACC_CAP": "0", "ABISMAL_B200_BIN_SHIFT": "12"}),  # every strand ranks all its survivors
+    ("short_replay_of_3", {"ABISMAL_B200_ACC_CAP": "3", "ABISMAL_B200_BIN_SHIFT": "12"}),
 ]
 
 

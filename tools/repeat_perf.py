@@ -119,6 +119,8 @@ def main():
         tasks = "%s,ovf=%s,scale=%s" % (tasks, ovf, tscale)
         out["tasks=" + tasks] = {"ms": m.last_kernel_ms, "reads_per_s": 2.0 * b1.n / (m.last_kernel_ms / 1e3),
                                  "kernels_ms": dict(zip(m.KERNELS, m.last_kernel_times)),
+                                 "seeding_ms": dict(zip(m.SEED_KERNELS, m.last_seed_times)) if m.binned else None,
+                                 "binned_seeding": m.bin_stats() if m.binned else None,
                                  "pairs_mapped_frac": float((res.pe_r1["pos"] != 0).mean()),
                                  "run_stats": m.last_run_stats()}
         print("[rep] tasks=%s %s" % (tasks, json.dumps(out["tasks=" + tasks])), flush=True)
