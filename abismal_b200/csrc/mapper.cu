@@ -178,7 +178,7 @@ constexpr int kScatterCtasPerSmMax = 2;  // count_kernel / scatter_kernel: at mo
 struct abg_mapper {
   abg_index *idx = nullptr;
   abg_params params{};
-  uint32_t max_batch = 0, max_read_len = 0, ml = 0, chunk = 0;
+  uint32_t max_batch = 0, max_read_len = 0, ml = 0, chunk = 0, chunk2 = 0;
   bool paired = false, count_work = false;
   cudaStream_t stream = nullptr;                       // upload / run / download (split API)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;       // pipelined abg_map_batch
@@ -448,7 +448,7 @@ int launch_hash(const abg_mapper *m, const ab2dev::KernelParams &P, cudaStream_t
   Q.work_counter = P.work_counter + 12;
   Q.layout_kind = ab2dev::kLayoutSeed;
   const uint64_t wpb = ab2dev::kWarpsPerBlock;
-  const uint64_t n_work = (uint64_t)P.n * m->spi;
+  const uint64_t n_work = P.n;  // one warp per read / pair: all its strands
   void *args[] = {&Q};
   ABG_CUDA(cudaLaunchKernel(m->kernel_h, dim3((unsigned)std::min<uint64_t>((uint64_t)m->grid_h, (n_work + wpb - 1) / wpb)),
                             dim3(ab2dev::kThreadsPerBlock), args, m->smem_s, st));
@@ -915,6 +915,9 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     uint32_t c = v > 0 ? (uint32_t)v : 32768u;
     const uint32_t min_c = (max_batch + kMaxChunks - 1) / kMaxChunks;
     m->chunk = std::max(c, std::max(min_c, 1u));
+    // sub-batch size of the kernels after the filter (binned seeding); at least `chunk`
+    const char *e2 = std::getenv("ABISMAL_B200_CHUNK2");
+    m->chunk2 = (e2 && std::atol(e2) > 0) ? (uint32_t)std::atol(e2) : m->chunk;
   }
 
 #define ABG_M(call)                                                                         \
@@ -1544,10 +1547,14 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
     ABG_CUDA(cudaEventRecord(m->ev_bins, m->s_run[0]));
     ABG_CUDA(cudaStreamWaitEvent(m->s_run[1], m->ev_bins, 0));
   }
-  for (uint32_t j = 0; j < n_chunks; ++j) {
-    const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
+  // Binned seeding: the kernels after the filter may take larger sub-batches than the copies and the hashing
+  // (every launch has a tail; the copies back still overlap the next sub-batch's kernels)
+  const uint32_t chunk2 = bins ? std::max(chunk, m->chunk2) : chunk;
+  const uint32_t n_chunks2 = n ? (n + chunk2 - 1) / chunk2 : 0;
+  for (uint32_t j = 0; j < n_chunks2; ++j) {
+    const uint32_t c0 = j * chunk2, c1 = std::min(n, c0 + chunk2);
     cudaStream_t sr = m->s_run[j & 1];
-    ABG_CUDA(cudaStreamWaitEvent(sr, m->ev_in[j], 0));
+    if (!bins) ABG_CUDA(cudaStreamWaitEvent(sr, m->ev_in[j], 0));  // (binned: everything was hashed, hence copied, before the bins)
     ab2dev::KernelParams P;
     fill_params(m, P, c0, c1 - c0, j);
     // scratch set of this stream
@@ -1569,8 +1576,8 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
     ABG_CUDA(cudaMemcpyAsync(&m->counters, m->d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              m->s_d2h));
   // host side of each sub-batch as it lands, while the GPU works on the later ones
-  for (uint32_t j = 0; j < n_chunks; ++j) {
-    const uint32_t c0 = j * chunk, c1 = std::min(n, c0 + chunk);
+  for (uint32_t j = 0; j < n_chunks2; ++j) {
+    const uint32_t c0 = j * chunk2, c1 = std::min(n, c0 + chunk2);
     ABG_CUDA(cudaEventSynchronize(m->ev_out[j]));
     scatter_results(m, d, r, c0, c1 - c0);
   }

@@ -253,32 +253,42 @@ __global__ void __launch_bounds__(kThreadsPerBlock, MINB) hash_kernel(const __gr
   TupleAlloc al;
   al.cur = al.end = 0u;
   al.full = false;
-  const unsigned int n_work = P.n * B.spi;
+  // one read / pair per work item: its strands (2, 4 or 8 passes over one or two ends) share the loaded bases
+  const bool paired = (P.mode & ABG_MODE_PAIRED) != 0;
   for (;;) {
-    unsigned int w = 0;
-    if (lane == 0) w = atomicAdd(P.work_counter, 1u);
-    w = __shfl_sync(FULL, w, 0);
-    if (w >= n_work) break;
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(P.work_counter, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= P.n) break;
+    uint32_t o[2] = {0u, 0u}, len[2] = {0u, 0u};
+    o[0] = P.off[0][item];
+    len[0] = P.off[0][item + 1] - o[0];
+    if (paired) {
+      o[1] = P.off[1][item];
+      len[1] = P.off[1][item + 1] - o[1];
+    }
     if (lane == 0) {
       S->qkey[0] = S->qkey[1] = ~0u;
       S->packed_key = ~0u;
+      S->len[0] = len[0];
+      S->len[1] = len[1];
     }
     __syncwarp();
-    const unsigned int item = w / B.spi;
-    int end;
-    uint32_t flags;
-    strand_plan(P, (int)(w % B.spi), end, flags);
-    const uint32_t o = P.off[end][item], len = P.off[end][item + 1] - o;
-    if (lane == 0) S->len[end] = len;
-    __syncwarp();
-    uint32_t flag = 2u;
-    if (len != 0) {
-      load_end(W, end, P.seq[end] + o, len);
-      const EmitResult er = emit_strand(al, end, flags, B.sid_base + w);
-      al = er.al;
-      flag = er.flag;
+    if (len[0] != 0) load_end(W, 0, P.seq[0] + o[0], len[0]);
+    if (len[1] != 0) load_end(W, 1, P.seq[1] + o[1], len[1]);
+    for (uint32_t pass = 0; pass < B.spi; ++pass) {
+      const uint32_t w = item * B.spi + pass;
+      int end;
+      uint32_t flags;
+      strand_plan(P, (int)pass, end, flags);
+      uint32_t flag = 2u;
+      if (len[end] != 0) {
+        const EmitResult er = emit_strand(al, end, flags, B.sid_base + w);
+        al = er.al;
+        flag = er.flag;
+      }
+      if (lane == 0) B.strand_flag[B.sid_base + w] = (uint8_t)flag;
     }
-    if (lane == 0) B.strand_flag[B.sid_base + w] = (uint8_t)flag;
   }
   // the unused rest of the warp's last block: empty tuples
   for (uint32_t k = al.cur + (uint32_t)lane; k < al.end; k += 32) B.tup[k] = SeedTuple{0u, 0u, 0u, 0u};

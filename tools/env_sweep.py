@@ -38,6 +38,20 @@ for v in variants:
             best = (m.last_kernel_ms, list(m.last_seed_times) if m.binned else None, list(m.last_kernel_times))
     rec = {"ms": best[0], "reads_per_s": (2 if paired else 1) * b[0].n / best[0] * 1e3,
            "seeding_ms": dict(zip(m.SEED_KERNELS, best[1])) if best[1] else None, "phases_ms": dict(zip(m.KERNELS, best[2]))}
+    if os.environ.get("SWEEP_E2E"):
+        # end to end through abg_map_batch: page-locked host buffers in and out, copies inside the timed region
+        if "bp" not in globals():
+            from abismal_b200.capi import Results
+            bp = [x.to_pinned() for x in b]
+            rp = Results(b[0].n, paired, m.stride, pinned=True)
+        m.map_batch(*bp, results=rp)
+        t_e2e = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            m.map_batch(*bp, results=rp)
+            t_e2e.append(1e3 * (time.perf_counter() - t0))
+        rec["e2e_ms"] = min(t_e2e)
+        rec["e2e_reads_per_s"] = (2 if paired else 1) * b[0].n / min(t_e2e) * 1e3
     res = m.map_batch(*b)
     if first is None:
         first = res
