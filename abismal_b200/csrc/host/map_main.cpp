@@ -562,9 +562,10 @@ int map_main(int argc, char *argv[]) {
     if (!index_file.empty()) {
       if (verbose) log_msg("loading index " + index_file);
 #ifdef ABISMAL_ENGINE_ORACLE
-      index.read(index_file);
+      // (the test tool reads into vectors; ABISMAL_B200_INDEX_BULK=1 makes it take the product's loader)
+      index.read(index_file, std::getenv("ABISMAL_B200_INDEX_BULK") != nullptr);
 #else
-      index.read(index_file, true);  // arrays stay in a mapping of the file: they are read once, by the upload to HBM
+      index.read(index_file, true);  // arrays stay in one buffer filled by several threads: they are read once, by the upload to HBM
 #endif
       if (verbose)
         log_msg("loading time: " +

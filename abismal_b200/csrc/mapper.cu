@@ -1171,6 +1171,10 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
         if (const char *ec = std::getenv("ABISMAL_B200_SCATTER_CTAS"))
           if (std::atoi(ec) >= 1 && std::atoi(ec) <= kScatterCtasPerSmMax) m->grid_sc = n_sm * std::atoi(ec);
         if (m->scatter_sorted) m->grid_sc = n_sm;
+        // fewer resident filter warps = a narrower live window of the record array (every warp holds `grab` tuples of
+        // the bin-ordered stream): ABISMAL_B200_FILTER_CTAS caps the CTAs per SM
+        if (const char *ef2 = std::getenv("ABISMAL_B200_FILTER_CTAS"))
+          if (std::atoi(ef2) >= 1) per_f = std::min(per_f, std::atoi(ef2));
         m->grid_f = n_sm * per_f;
         for (int k = 0; k < 3; ++k) ABG_M(cudaEventCreate(&m->ev_b[k]));
         ABG_M(cudaEventCreateWithFlags(&m->ev_bins, cudaEventDisableTiming));

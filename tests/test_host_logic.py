@@ -143,3 +143,24 @@ def test_pipeline_batching_threads_and_sharding_do_not_change_the_output(workspa
         got = workspace.map_with(helpers.ORACLE_MAP, "pipe_%d" % k, args, pre=pre)
         assert helpers.sam_body(got[0]) == helpers.sam_body(base[0])
         assert open(got[1]).read() == open(base[1]).read()
+
+
+def test_index_loaded_by_the_bulk_reader_gives_the_same_output(workspace, monkeypatch):
+    """The product's index loader (the arrays of the file in one buffer, filled by several pread threads; the
+    header parsed as before) behind the same host code: byte-identical SAM and statistics.  The test tool reads
+    into vectors unless ABISMAL_B200_INDEX_BULK is set."""
+    workspace.need_trex()
+    args = ["-i", "tests/tRex1.idx", "tests/reads_pe_1.fq", "tests/reads_pe_2.fq"]
+    base = workspace.map_with(helpers.ORACLE_MAP, "bulk_a", args)
+    monkeypatch.setenv("ABISMAL_B200_INDEX_BULK", "1")
+    got = workspace.map_with(helpers.ORACLE_MAP, "bulk_b", args)
+    assert helpers.sam_body(got[0]) == helpers.sam_body(base[0])
+    assert open(got[1]).read() == open(base[1]).read()
+    # a truncated index file is refused with the reference's message, not read past its end
+    with open(workspace.path("tRex1.idx"), "rb") as f:
+        data = f.read()
+    with open(workspace.path("cut.idx"), "wb") as f:
+        f.write(data[:len(data) - 1000])
+    p = helpers.run([helpers.ORACLE_MAP, "map", "-i", "tests/cut.idx", "-o", "tests/cut.sam", "tests/reads_pe_1.fq",
+                     "tests/reads_pe_2.fq"], cwd=workspace.dir, check=False)
+    assert p.returncode != 0 and "failed loading index file" in p.stderr

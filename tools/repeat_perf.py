@@ -126,6 +126,8 @@ def main():
         print("[rep] tasks=%s %s" % (tasks, json.dumps(out["tasks=" + tasks])), flush=True)
         m.close()
     ix.close()
+    for k in ("ABISMAL_B200_TASKS", "ABISMAL_B200_OVF_PER_ITEM", "ABISMAL_B200_TASK_SCALE"):
+        os.environ.pop(k, None)  # the front end below runs with its defaults
     # reference binary on a sample + SAM parity through the front end
     s = []
     for e in (1, 2):
@@ -141,7 +143,9 @@ def main():
     subprocess.check_call([REF, "map", "-t", str(n_cpu), "-i", idx, "-o", d + "/ref.sam"] + s, stderr=subprocess.DEVNULL)
     ref_s = time.perf_counter() - t
     t = time.perf_counter()
-    subprocess.check_call([CLI, "map", "-i", idx, "-o", d + "/ours.sam"] + s, stderr=subprocess.DEVNULL)
+    p = subprocess.run([CLI, "map", "-i", idx, "-o", d + "/ours.sam"] + s, stderr=subprocess.PIPE, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("abismal-b200 map failed: " + p.stderr[-1500:])
     ours_s = time.perf_counter() - t
     a = sorted(ln for ln in open(d + "/ref.sam", "rb") if not ln.startswith(b"@PG"))
     b = sorted(ln for ln in open(d + "/ours.sam", "rb") if not ln.startswith(b"@PG"))
