@@ -25,6 +25,9 @@ for r in rows[2:]:
     ms = float(r[i_t]) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}[units[i_t]]
     kern[name] = {"dram_bytes_read": col(r, "dram__bytes_read.sum"), "dram_bytes_write": col(r, "dram__bytes_write.sum"),
                   "ms_under_ncu": ms, "l2_hit_pct": float(r[hdr.index("lts__t_sector_hit_rate.pct")])}
+SEEDING = ("hash_kernel", "count_kernel", "bin_prefix_kernel", "scatter_sorted_kernel", "scatter_kernel", "filter_kernel", "seed_kernel")
+other = {k: v for k, v in kern.items() if k not in SEEDING}
+kern = {k: v for k, v in kern.items() if k in SEEDING}
 total = sum(k["dram_bytes_read"] + k["dram_bytes_write"] for k in kern.values())
 try:
     doc = json.load(open(out_path))
@@ -33,6 +36,7 @@ try:
 except Exception:
     doc = {}
 doc[mode] = {"kernel": "seeding (binned): " + " + ".join(kern), "source": os.path.basename(rep) + " (ncu --set full --clock-control none)",
-             "pairs_in_capture": pairs, "units_per_pair": 1.0, "kernels": kern, "dram_bytes": total, "dram_bytes_per_pair": total / pairs}
+             "pairs_in_capture": pairs, "units_per_pair": 1.0, "kernels": kern, "dram_bytes": total, "dram_bytes_per_pair": total / pairs,
+             "other_kernels_of_the_step": other}
 json.dump(doc, open(out_path, "w"), indent=1)
 print(json.dumps(doc[mode], indent=1))
