@@ -229,6 +229,7 @@ struct abg_mapper {
   bool scatter_sorted = true;  // scatter_sorted_kernel: tuples leave in runs per bin (shared-memory tile sort); measured 7.4 vs 12.6 ms
   uint32_t filter_cursors = 1;  // interleaved work cursors of the filter
   uint32_t filter_cache = 1;  // bit 0 planes loaded evict-first (measured 24.2 vs 25.3 ms), bit 1 records loaded with the L2 evict-last hint (no gain)
+  bool filter_minb8 = false;  // tuning: filter_kernel bounded for 8 CTAs per SM (32 registers)
   bool filter_pipe = false;  // filter_kernel<true>: two record gathers per lane in flight
   uint32_t filter_grab = 256;  // tuples per work-cursor atomic (measured at 2^20 pairs: 32 -> 44 ms, 64 -> 30 ms, 128 -> 21 ms, 256 -> 20 ms)
   ab2dev::SeedTuple *d_tup = nullptr, *d_tup_b = nullptr;
@@ -455,7 +456,7 @@ int launch_hash(const abg_mapper *m, const ab2dev::KernelParams &P, cudaStream_t
   return ABG_OK;
 }
 
-// bins of everything hashed since reset_bins: write cursors, scatter (+ payloads), prefilter -> survivor lists
+// bins of everything hashed since reset_bins: write cursors, scatter, prefilter -> survivor lists
 int launch_bins(const abg_mapper *m, cudaStream_t st, const cudaEvent_t *ev_b = nullptr) {
   ab2dev::FilterParams F = filter_params(m);
   const size_t sm = (size_t)m->n_bins * 4;
@@ -465,6 +466,7 @@ int launch_bins(const abg_mapper *m, cudaStream_t st, const cudaEvent_t *ev_b = 
   else ab2dev::scatter_kernel<<<m->grid_sc, ab2dev::kScatterThreads, sm, st>>>(F);
   if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[1], st));
   if (m->filter_pipe) ab2dev::filter_kernel<true, false><<<m->grid_f, 256, 0, st>>>(F);
+  else if (m->filter_minb8) ab2dev::filter_kernel<false, false, 8><<<m->grid_f, 256, 0, st>>>(F);
   else if (m->filter_cache & 2u) ab2dev::filter_kernel<false, true><<<m->grid_f, 256, 0, st>>>(F);
   else ab2dev::filter_kernel<false, false><<<m->grid_f, 256, 0, st>>>(F);
   if (ev_b) ABG_CUDA(cudaEventRecord(ev_b[2], st));
@@ -1125,6 +1127,9 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
       if (const char *ek = std::getenv("ABISMAL_B200_FILTER_CURSORS"))
         if (std::atoi(ek) >= 1 && std::atoi(ek) <= (int)kMaxFilterCursors) m->filter_cursors = (uint32_t)std::atoi(ek);
       if (const char *ec2 = std::getenv("ABISMAL_B200_FILTER_CACHE")) m->filter_cache = (uint32_t)std::atoi(ec2) & 3u;
+      if (const char *e8 = std::getenv("ABISMAL_B200_FILTER_MINB")) m->filter_minb8 = std::atoi(e8) == 8 && !m->filter_pipe;
+      if (m->filter_minb8) ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, (const void *)ab2dev::filter_kernel<false, false, 8>, 256, 0));
+      else
       ABG_M(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f, m->filter_pipe ? (const void *)ab2dev::filter_kernel<true, false>
                                                                                    : (const void *)ab2dev::filter_kernel<false, false>, 256, 0));
       // any allocation that fails switches the binned path off (the direct path needs none of this memory)
@@ -1504,6 +1509,7 @@ int abg_map_batch(abg_mapper *m, const abg_batch *b, abg_results *r) {
 namespace {
 int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
   int rc;
+  const auto t_call = std::chrono::steady_clock::now();
   const uint32_t n = b->n;
   m->cur_n = n;
   m->timed = false;
@@ -1579,6 +1585,29 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
   if (m->d_counters)
     ABG_CUDA(cudaMemcpyAsync(&m->counters, m->d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              m->s_d2h));
+  if (std::getenv("ABISMAL_B200_VERBOSE") != nullptr && n_chunks != 0) {
+    // coarse timeline of the call (host clock at the moment each stage's event has fired; everything above is
+    // enqueued by now)
+    const auto t_enq = std::chrono::steady_clock::now();
+    auto since = [&](const std::chrono::steady_clock::time_point &t0) {
+      return 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const double enq_ms = 1e3 * std::chrono::duration<double>(t_enq - t_call).count();
+    (void)cudaEventSynchronize(m->ev_in[n_chunks - 1]);
+    const double h2d_ms = since(t_call);
+    double bins_ms = 0.0;
+    if (bins) {
+      (void)cudaEventSynchronize(m->ev_bins);
+      bins_ms = since(t_call);
+    }
+    (void)cudaEventSynchronize(m->ev_k[n_chunks2 - 1]);
+    const double kern_ms = since(t_call);
+    (void)cudaEventSynchronize(m->ev_out[n_chunks2 - 1]);
+    const double d2h_ms = since(t_call);
+    std::fprintf(stderr, "[abg_map_batch] n %u, %u + %u sub-batches: enqueued %.2f ms, copies in done %.2f, hash+bins+filter done %.2f, "
+                         "last kernel done %.2f, last copy out done %.2f (ms since the call)\n",
+                 n, n_chunks, n_chunks2, enq_ms, h2d_ms, bins_ms, kern_ms, d2h_ms);
+  }
   // host side of each sub-batch as it lands, while the GPU works on the later ones
   for (uint32_t j = 0; j < n_chunks2; ++j) {
     const uint32_t c0 = j * chunk2, c1 = std::min(n, c0 + chunk2);

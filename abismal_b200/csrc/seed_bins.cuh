@@ -7,18 +7,23 @@
 // update can ever be accepted above the set's initial cutoff (0.4 x read length: the heaps start with that
 // sentinel and cutoffs only tighten).  So the batch is seeded in four kernels:
 //
-//   hash_kernel     one warp per strand: encode, hash, probe the counters (L2 resident), narrow oversized buckets
-//                   (find_candidates) -- everything of process_seeds up to the candidate ranges -- and emit one
-//                   16-byte TUPLE per (offset, table) with a non-empty range, plus the strand's 2-bit read planes;
-//   scatter_kernel  tuples -> bins by the address of their first record (one bin = 2^bin_shift records, ~32 MB),
-//                   each with a 32-byte payload: the 128 read bases its records are compared with;
-//   filter_kernel   tuples in bin order, one lane per candidate: record (L2 hit after the bin's first touch)
-//                   against payload, lower bound of the distance, survivors (~1 %) appended to their strand's list;
-//   seed_kernel     (mapper_kernels.cuh, process_binned below) one warp per strand: survivors in canonical order
-//                   (offset, two-letter before three-letter, bucket order), the deep compare of each, then the
-//                   specific and the sensitive phase replayed against the candidate set exactly as process_seeds
-//                   orders them.  Strands outside the fast path (reads with N, longer than kBinMaxLen, survivor
-//                   or tuple overflow) run process_seeds itself.
+//   hash_kernel     one warp per read / pair, its strands one after the other: encode, hash, probe the counters
+//                   (L2 resident), narrow oversized buckets (find_candidates) -- everything of process_seeds up to
+//                   the candidate ranges -- and emit one 16-byte TUPLE per (offset, table) with a non-empty range,
+//                   plus the strand's 2-bit read planes;
+//   count_kernel, bin_prefix_kernel, scatter_sorted_kernel
+//                   tuples -> bins by the address of their first record (one bin = 2^bin_shift records, 32 MB),
+//                   without global atomics: every CTA has its own write range in every bin, and sorts tiles of
+//                   8192 tuples in shared memory so that a bin receives runs of consecutive tuples;
+//   filter_kernel   tuples in bin order, 32 per warp at a time: the payload of each (the 128 read bases its records
+//                   are compared with) is built in shared memory from the strand's planes, then one lane per
+//                   candidate: record against payload, lower bound of the distance, survivors (~3 %) appended to
+//                   their strand's list;
+//   seed_kernel     (mapper_kernels.cuh, process_binned below) one warp per strand: the deep compare of its
+//                   survivors; those a phase could still accept are put into canonical order (offset, two-letter
+//                   before three-letter, bucket order) and replayed against the candidate set exactly as
+//                   process_seeds orders them.  Strands outside the fast path (reads with N, longer than
+//                   kBinMaxLen, survivor or tuple overflow) run process_seeds itself.
 #pragma once
 
 #include "mapper_kernels.cuh"
@@ -536,8 +541,8 @@ __device__ __forceinline__ void filter_candidate(const FilterParams &F, const ui
 
 // PIPE: the records of the next 32 candidates travel to shared memory (cp.async, no registers) while this round's
 // are compared: the kernel waits on the record gathers, one dependent round trip per 32 candidates.
-template <bool PIPE, bool KEEP>
-__global__ void __launch_bounds__(256, 6) filter_kernel(FilterParams F) {
+template <bool PIPE, bool KEEP, int MINB = 6>
+__global__ void __launch_bounds__(256, MINB) filter_kernel(FilterParams F) {
   __shared__ uint4 s_hdr[8][32];
   __shared__ uint4 s_pay[8][32][2];  // per tuple: {lo, hi} plane words of the 128 read bases its records are compared with
   __shared__ uint32_t s_excl[8][32];
