@@ -601,7 +601,29 @@ int copy_results_async(abg_mapper *m, const ResultDst &d, uint32_t c0, uint32_t 
 
 // Host side of reads [c0, c0 + n) once their copies have landed: staging -> caller for pageable result
 // buffers, and the used part of every CIGAR row scattered into the caller's cigar_stride rows.
+void scatter_results_part(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t c0, uint32_t n);
+
+// The CIGAR rows are the one piece of host work per read inside abg_map_batch (a 64-byte line written per read):
+// sub-batches of some size are split over a few threads, so that the part of it that cannot overlap the GPU (the
+// last sub-batch) stays short.
 void scatter_results(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t c0, uint32_t n) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const uint32_t n_thr = n >= 16384u ? std::min<uint32_t>(4u, std::max(1u, hw / 4u)) : 1u;
+  if (n_thr <= 1u) {
+    scatter_results_part(m, d, r, c0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const uint32_t per = (n + n_thr - 1) / n_thr;
+  for (uint32_t t = 1; t < n_thr; ++t) {
+    const uint32_t a = std::min(n, t * per), b = std::min(n, a + per);
+    if (b > a) th.emplace_back([=, &d] { scatter_results_part(m, d, r, c0 + a, b - a); });
+  }
+  scatter_results_part(m, d, r, c0, std::min(n, per));
+  for (std::thread &x : th) x.join();
+}
+
+void scatter_results_part(abg_mapper *m, const ResultDst &d, abg_results *r, uint32_t c0, uint32_t n) {
   const uint32_t stride = m->params.cigar_stride;
   const uint32_t w = std::min(kInlineOps, stride);
   const int n_ends = m->paired ? 2 : 1;
@@ -914,7 +936,10 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     // sub-batch size of the pipelined abg_map_batch (copies of chunk j+1 overlap the kernel of chunk j)
     const char *e = std::getenv("ABISMAL_B200_CHUNK");
     const long v = e ? std::atol(e) : 0;
-    uint32_t c = v > 0 ? (uint32_t)v : 32768u;
+    // measured through abg_map_batch at 2^20 pairs (profiles/r02_sweep_v19_e2e_chunks.txt): 32768 -> 102.8 ms,
+    // 65536 -> 99.5, 98304 -> 98.5, 131072 -> 99.9 (fewer launch tails against a longer exposed last copy + scatter);
+    // smaller batches keep at least four sub-batches of 32768
+    uint32_t c = v > 0 ? (uint32_t)v : (max_batch >= 4u * 98304u ? 98304u : 32768u);
     const uint32_t min_c = (max_batch + kMaxChunks - 1) / kMaxChunks;
     m->chunk = std::max(c, std::max(min_c, 1u));
     // sub-batch size of the kernels after the filter (binned seeding); at least `chunk`
