@@ -239,7 +239,7 @@ public:
   ab2::SeStats se_stats;
   ab2::PeStats pe_stats;
   uint64_t n_done = 0;
-  StageClock t_read1, t_read2, t_map, t_format, t_write, t_upload;
+  StageClock t_read1, t_read2, t_map, t_format, t_write, t_upload, t_engine;
 
 private:
   template <class F>
@@ -322,7 +322,11 @@ private:
     // and is rebuilt with twice as many whenever a batch reports one that did not fit.
     uint32_t engine_max_len = 256;
     abg_params params = cfg_.params;
-    std::unique_ptr<Engine> engine(new Engine(dev_index, params, cfg_.batch_size, engine_max_len));
+    std::unique_ptr<Engine> engine;
+    {
+      StageClock::Scope sc(t_engine);
+      engine.reset(new Engine(dev_index, params, cfg_.batch_size, engine_max_len));
+    }
     WorkItem *it = nullptr;
     while (!failed_ && to_map_.pop(it)) {
       const uint32_t n = it->b1.size();
@@ -642,6 +646,7 @@ int map_main(int argc, char *argv[]) {
       log_msg("total mapping time: " + fmt_secs(secs));
       // summed over the devices (they upload concurrently); the readers parse the first batches meanwhile
       log_msg("index upload to HBM: " + fmt_secs(pipe.t_upload.secs() / static_cast<double>(cfg.devices.size())) + " per device");
+      log_msg("engine set-up (device scratch, streams; summed over the mapper workers): " + fmt_secs(pipe.t_engine.secs()));
       log_msg("stage busy time: read1 " + fmt_secs(pipe.t_read1.secs()) + ", read2 " + fmt_secs(pipe.t_read2.secs()) +
               ", map (" + std::to_string(cfg.devices.size()) + " GPU) " + fmt_secs(pipe.t_map.secs()) + ", format (" +
               std::to_string(n_threads) + " threads) " + fmt_secs(pipe.t_format.secs()) + ", write " +

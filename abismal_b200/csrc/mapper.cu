@@ -1269,7 +1269,8 @@ int abg_mapper_create(abg_index *ix, const abg_params *p, uint32_t max_batch, ui
     ABG_M(cudaMalloc(&m->d_cigar[e], (size_t)max_batch * stride * 4));
     ABG_M(cudaMalloc(&m->d_ncigar[e], (size_t)max_batch * 4));
     ABG_M(cudaMalloc(&m->d_cigar_inline[e], (size_t)max_batch * w * 4));
-    ABG_M(cudaMallocHost(&m->h_seq[e], m->seq_cap + 16));
+    // (h_seq, the page-locked staging of pageable read bytes, is allocated when a caller first passes pageable memory:
+    //  page-locking max_batch x max_read_len bytes per end costs the front end's start-up more than anything else here)
     ABG_M(cudaMallocHost(&m->h_off[e], ((size_t)max_batch + 1) * 4));
     ABG_M(cudaMallocHost(&m->h_se[e], (size_t)max_batch * sizeof(abg_hit)));
     ABG_M(cudaMallocHost(&m->h_cigar[e], (size_t)max_batch * w * 4));
@@ -1398,6 +1399,7 @@ int abg_mapper_upload(abg_mapper *m, const abg_batch *b) {
     if ((rc = stage_offsets(m, off, 0, b->n, m->h_off[e])) != ABG_OK) return rc;
     const char *src = seqs[e] + off[0];
     if (!is_pinned(src)) {
+      if (!m->h_seq[e]) ABG_CUDA(cudaMallocHost(&m->h_seq[e], m->seq_cap + 16));
       std::memcpy(m->h_seq[e], src, bytes);
       src = m->h_seq[e];
     }
@@ -1562,6 +1564,7 @@ int map_batch_impl(abg_mapper *m, const abg_batch *b, abg_results *r) {
       const size_t o0 = off[c0] - off[0], bytes = off[c1] - off[c0];
       const char *src = seqs[e] + off[c0];
       if (!seq_pinned[e]) {
+        if (!m->h_seq[e]) ABG_CUDA(cudaMallocHost(&m->h_seq[e], m->seq_cap + 16));
         std::memcpy(m->h_seq[e] + o0, src, bytes);
         src = m->h_seq[e] + o0;
       }

@@ -39,6 +39,8 @@ def run(tag, cmd, n):
                 info[key.rstrip(":")] = float(ln.split(key)[1].strip().rstrip("s"))
         if "index upload to HBM:" in ln:
             info["index upload"] = float(ln.split("index upload to HBM:")[1].split("s")[0])
+        if "engine set-up" in ln:
+            info["engine set-up"] = float(ln.split("):")[1].strip().rstrip("s"))
         if "stage busy time" in ln:
             info["stages"] = ln.split("stage busy time:")[1].strip()
     mt = info.get("total mapping time", wall - info.get("loading time", 0.0))
