@@ -81,3 +81,48 @@ def test_shard_bounds_cover_everything_once():
                 lo, hi = shard_bounds(n, world, r)
                 seen += list(range(lo, hi))
             assert seen == list(range(n))
+
+
+def _ranksync_worker(rank, world, port, out_dir, failing_rank):
+    """bench.py's RankSync on gloo: a phase that raises on one rank must end every rank (exit status 1), with the
+    traceback in the failing rank's log and in the JSON error line rank 0 prints -- nobody waits in a barrier."""
+    import io
+    import json
+    sys.path.insert(0, helpers.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["RANK"] = str(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib
+    import bench
+    importlib.reload(bench)  # RANK is read at import
+    sync = bench.RankSync(dist, True, world)
+    assert sync.run("phase one", lambda: 40 + rank) == 40 + rank  # a phase that succeeds everywhere goes on
+    out = io.StringIO()
+    real_stdout, sys.stdout = sys.stdout, out
+    code = None
+    try:
+        def phase_two():
+            if rank == failing_rank:
+                raise RuntimeError("boom on rank %d" % rank)
+            return "fine"
+        sync.run("phase two", phase_two)
+    except SystemExit as e:
+        code = e.code
+    finally:
+        sys.stdout = real_stdout
+    with open(os.path.join(out_dir, "ranksync_%d.json" % rank), "w") as f:
+        json.dump({"code": code, "stdout": out.getvalue(), "error": sync.error}, f)
+
+
+def test_bench_rank_failure_ends_all_ranks_with_the_traceback(tmp_path):
+    import json
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_ranksync_worker, args=(2, port, str(tmp_path), 1), nprocs=2, join=True)
+    r0 = json.load(open(str(tmp_path / "ranksync_0.json")))
+    r1 = json.load(open(str(tmp_path / "ranksync_1.json")))
+    assert r0["code"] == 1 and r1["code"] == 1            # both ranks leave through sys.exit(1)
+    assert r0["error"] is None and "boom on rank 1" in r1["error"]
+    line = json.loads(r0["stdout"].strip().splitlines()[-1])
+    assert line["error"] == "bench failed" and "boom on rank 1" in line["ranks"]["1"] and "0" not in line["ranks"]
+    assert r1["stdout"].strip() == ""                     # only rank 0 prints
