@@ -89,3 +89,15 @@ def test_oracle_equals_reference_on_the_plain_repeat_genome(workspace, tag, args
     assert helpers.sam_body(rsam) == helpers.sam_body(osam)
     assert open(rst).read() == open(ost).read()
     assert len(helpers.sam_body(rsam)) > 10
+
+
+def test_oracle_equals_reference_on_random_configurations():
+    """tools/fuzz_oracle.py: random repeat genomes, read lengths 50-250, SE / PE, plain / -a / -R reads and random
+    map flags -- the restatement's SAM and statistics equal the reference binary's (a few seeds here; 180 more ran
+    clean in the round-2 session, and 23 through the GPU front end: profiles/r02_fuzz_cli_vs_reference.txt)."""
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tools", "fuzz_oracle.py"), "4", "4242"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-2000:]
+    assert "0 of 4 differ" in p.stdout
